@@ -1,0 +1,298 @@
+/*
+ * ndt2d_b200.h -- C ABI of libndt2d_b200.so: the B200 (sm_100a) backend for
+ * ndt_2d's scan-matching hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain host pointers
+ * and sizes (doubles, caller-owned), returns an int status and never throws.
+ * There is no CPU fallback: if no CUDA device is usable, create() fails with
+ * NDT2D_ERR_NO_DEVICE and nothing else can be called.
+ *
+ * Each function cites the reference interface it replaces; file:line are
+ * relative to the reference tree (mikeferguson/ndt_2d).  INTEGRATION.md shows
+ * the C++ plugin class (ndt_2d::ScanMatcherNDT / ndt_2d::ParticleFilter) that
+ * binds these into the reference's pluginlib seam.
+ *
+ * Conventions
+ *   pose3      : {x, y, theta}                       (pose_2d.hpp:35-55)
+ *   pts_xy     : interleaved {x0, y0, x1, y1, ...} in the sensor frame,
+ *                exactly the layout of std::vector<ndt_2d::Point>
+ *                (point.hpp:35-51), so `&points[0].x` can be passed as is
+ *   cov9       : 3x3 row-major
+ *   A handle serialises its own calls (internal mutex + one CUDA stream);
+ *   distinct handles are independent.
+ */
+#ifndef NDT2D_B200_H_
+#define NDT2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDT2D_API __attribute__((visibility("default")))
+
+typedef enum ndt2d_status
+{
+  NDT2D_OK = 0,
+  NDT2D_ERR_INVALID = 1,    /* bad argument (null pointer, non-positive resolution ...) */
+  NDT2D_ERR_NO_DEVICE = 2,  /* no usable CUDA device: the product has no CPU path */
+  NDT2D_ERR_CUDA = 3,       /* a CUDA runtime call failed; see ndt2d_last_error() */
+  NDT2D_ERR_NO_MAP = 4,     /* search/score entry called before add_scans (reference
+                               returns 0.0 and leaves outputs untouched:
+                               scan_matcher_ndt.cpp:80,159) */
+  NDT2D_ERR_SIZE = 5,       /* grid or scan larger than the device layout supports */
+  NDT2D_ERR_STATE = 6       /* call sequence error (e.g. fetch before stage) */
+} ndt2d_status;
+
+/* Parameters of one ScanMatcherNDT instance: the six ROS parameters the
+ * reference declares under "<name>." (scan_matcher_ndt.cpp:37-44, same
+ * defaults) plus range_max (:46) and the CUDA placement. */
+typedef struct ndt2d_params
+{
+  double ndt_resolution;             /* default 0.25   */
+  double search_angular_resolution;  /* default 0.0025 */
+  double search_angular_size;        /* default 0.1    */
+  double search_linear_resolution;   /* default 0.005  */
+  double search_linear_size;         /* default 0.05   */
+  int laser_max_beams;               /* default 100    */
+  double range_max;                  /* initialize(..., range_max) */
+  int device;                        /* CUDA device ordinal, -1 = current device */
+  void * stream;                     /* cudaStream_t to run on; NULL = handle-owned stream */
+  int kernel_variant;                /* 0 = auto (fastest), 1 = plain per-candidate search
+                                        kernel (kept as an on-device cross-check) */
+} ndt2d_params;
+
+typedef struct ndt2d_matcher ndt2d_matcher;
+typedef struct ndt2d_filter ndt2d_filter;
+
+/* Number of doubles in one partial search record (see ndt2d_matcher_search_staged). */
+#define NDT2D_PARTIAL_DOUBLES 16
+
+NDT2D_API const char * ndt2d_version(void);
+/* Message of the last failing CUDA call on this thread ("" if none). */
+NDT2D_API const char * ndt2d_last_error(void);
+/* Number of CUDA devices visible (0 => every create() will fail). */
+NDT2D_API int ndt2d_device_count(void);
+
+/* Fills the reference's defaults (scan_matcher_ndt.cpp:37-44); range_max = 0,
+ * device = -1, stream = NULL. */
+NDT2D_API void ndt2d_default_params(ndt2d_params * p);
+
+/* ------------------------------------------------------------------------
+ * ScanMatcherNDT  (include/ndt_2d/scan_matcher.hpp:42-91,
+ *                  src/scan_matcher_ndt.cpp:35-183)
+ * ---------------------------------------------------------------------- */
+
+/* replaces ScanMatcherNDT::initialize (scan_matcher_ndt.cpp:35-47) */
+NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher ** out);
+NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m);
+
+/* replaces ScanMatcherNDT::reset (scan_matcher_ndt.cpp:180-183) */
+NDT2D_API int ndt2d_matcher_reset(ndt2d_matcher * m);
+
+/* replaces ScanMatcherNDT::addScans (scan_matcher_ndt.cpp:49-74) and through
+ * it NDT::NDT / addScan / compute (ndt_model.cpp:118-160).  Always builds a
+ * fresh model.  poses: 3 doubles per scan; pt_offsets: n_scans+1 entries, in
+ * points; pts_xy: concatenated sensor-frame points. */
+NDT2D_API int ndt2d_matcher_add_scans(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy);
+
+/* replaces ScanMatcherNDT::matchScan (scan_matcher_ndt.cpp:76-149).
+ *   out_delta3     written only if some candidate scores < 0 (:128-134);
+ *                  *delta_written says whether it was
+ *   out_cov9       (1/s) k + (1/s^2) u u^T (:146), always written
+ *   *out_score     best_score / n (:148)
+ * Without a model: returns NDT2D_ERR_NO_MAP, *out_score = 0.0, nothing else
+ * touched (:80). */
+NDT2D_API int ndt2d_matcher_match_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+
+/* replaces ScanMatcherNDT::scorePoints (scan_matcher_ndt.cpp:156-178);
+ * scoreScan (:151-154) is this with the scan's own pose. */
+NDT2D_API int ndt2d_matcher_score_points(
+  ndt2d_matcher * m, const double * pts_xy, size_t npts, const double * pose3,
+  double * out_score);
+
+/* Batched scorePoints: one score per pose for the same points -- the body of
+ * ParticleFilter::measure's loop (particle_filter.cpp:81-87) in one launch. */
+NDT2D_API int ndt2d_matcher_score_poses(
+  ndt2d_matcher * m, const double * pts_xy, size_t npts, const double * poses3, size_t n_poses,
+  double * out_scores);
+
+/* replaces NDT::likelihood(const ScanPtr&) (ndt_model.cpp:189-201): all
+ * points, positive sign, not normalised. */
+NDT2D_API int ndt2d_matcher_likelihood_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_likelihood);
+
+/* Loop-closure batch (ndt_mapper.cpp:619-671): for each job j build a fresh
+ * model from its own scans (reset + addScans, :628-635) and run matchScan
+ * (:638-643) of the job's query scan against it, all jobs in one submission.
+ * Map scans of all jobs are concatenated: job j owns scans
+ * [job_scan_offsets[j], job_scan_offsets[j+1]); query scans likewise through
+ * query_pt_offsets.  Outputs are per job, laid out as in match_scan.
+ * The handle's model is left empty afterwards. */
+NDT2D_API int ndt2d_matcher_match_scan_batch(
+  ndt2d_matcher * m, size_t n_jobs,
+  const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
+  const double * map_pts_xy,
+  const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+
+/* ---- staged / partial search: device-resident inputs, theta-sliced ----- */
+
+/* Candidate lattice of this handle: the reference's accumulated-double loops
+ * (scan_matcher_ndt.cpp:103,117,119) replayed on the host. */
+NDT2D_API int ndt2d_matcher_search_shape(
+  const ndt2d_matcher * m, uint64_t * n_angular, uint64_t * n_linear);
+/* Copies the replayed loop values (dth: n_angular, dlin: n_linear). */
+NDT2D_API int ndt2d_matcher_search_values(const ndt2d_matcher * m, double * dth, double * dlin);
+
+/* Uploads one query scan (subsampled as scan_matcher_ndt.cpp:95-96,110) and
+ * its per-theta cos/sin (:106-107, host libm) to the device. */
+NDT2D_API int ndt2d_matcher_stage_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts);
+
+/* Launches the search over theta indices [theta_begin, theta_end) of the
+ * staged scan, asynchronously on the handle's stream.  The 16-double partial
+ * record is left on the device: at d_partial if non-NULL (a device pointer,
+ * e.g. a slot of an all-gather buffer), else in the handle.
+ *   [0] best score (sum, <= 0)      [1] best global candidate index
+ *   [2..7] k upper triangle (xx,xy,xt,yy,yt,tt)   [8..10] u   [11] s
+ *   [12] candidates evaluated       [13] points used (n)   [14],[15] reserved
+ * Global candidate index = (itheta * n_lin + ix) * n_lin + iy, i.e. the
+ * reference's loop order, so "lowest index wins" == "first wins" (:128). */
+NDT2D_API int ndt2d_matcher_search_staged(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial);
+
+/* Synchronises the stream and copies the handle-held partial record out. */
+NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16);
+
+/* Reduces n partial records (host memory) exactly like one sequential search
+ * would: lexicographic min on (score, index), sums of k/u/s, then the
+ * covariance formula (:146) and best/n (:148).  Pure arithmetic on n*16
+ * doubles; used after the single cross-GPU exchange. */
+NDT2D_API int ndt2d_combine_partials(
+  const ndt2d_matcher * m, const double * partials, size_t n_partials,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+
+/* Same reduction on the device: d_partials points at n records in device
+ * memory (e.g. the all-gather output); result fetched to the host. */
+NDT2D_API int ndt2d_matcher_combine_device(
+  ndt2d_matcher * m, const void * d_partials, size_t n_partials,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+
+/* ---- parity / introspection ------------------------------------------- */
+
+/* info[5] = size_x, size_y, origin_x, origin_y, cell_size (ndt_model.cpp:118-126) */
+NDT2D_API int ndt2d_matcher_grid_info(ndt2d_matcher * m, double * info5);
+/* Dense dump, 16 doubles per cell: valid, n, mean[2], covariance[4] (row-major),
+ * correlation[4], information[4] -- the members of ndt_2d::Cell
+ * (ndt_model.hpp:56-64).  out must hold size_x*size_y*16 doubles. */
+NDT2D_API int ndt2d_matcher_dump_cells(ndt2d_matcher * m, double * out);
+/* Cell index (NDT::getIndex, ndt_model.cpp:203-218; -1 = outside) of every
+ * map point in add_scans order, as computed on the device. */
+NDT2D_API int ndt2d_matcher_dump_keys(ndt2d_matcher * m, int32_t * out, size_t n_points);
+/* Scores of every candidate of the last search, in loop order (needs
+ * n_ang*n_lin^2 doubles); the search is re-run with score capture on. */
+NDT2D_API int ndt2d_matcher_dump_scores(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts, double * out,
+  size_t n_out);
+/* Counters: [0] kernels launched by this handle so far, [1] H2D bytes,
+ * [2] D2H bytes, [3] valid (n>=5) cells in the current model. */
+NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4);
+/* cudaStream_t the handle runs on. */
+NDT2D_API void * ndt2d_matcher_stream(ndt2d_matcher * m);
+
+/* ------------------------------------------------------------------------
+ * ParticleFilter measurement update + resampling
+ * (include/ndt_2d/particle_filter.hpp:45-115, src/particle_filter.cpp)
+ * The particle set lives on the device between calls.
+ * ---------------------------------------------------------------------- */
+
+/* replaces ParticleFilter::ParticleFilter (particle_filter.cpp:36-51):
+ * min_particles particles at (0,0,0), uniform weights, statistics updated. */
+NDT2D_API int ndt2d_filter_create(
+  size_t min_particles, size_t max_particles, int device, void * stream, ndt2d_filter ** out);
+NDT2D_API int ndt2d_filter_destroy(ndt2d_filter * f);
+
+/* Direct access to the particle set (particles_: 3 doubles each; weights_). */
+NDT2D_API int ndt2d_filter_set_particles(
+  ndt2d_filter * f, const double * particles3, const double * weights, size_t n);
+NDT2D_API int ndt2d_filter_size(ndt2d_filter * f, size_t * n);
+NDT2D_API int ndt2d_filter_get_particles(ndt2d_filter * f, double * particles3, double * weights);
+
+/* replaces ParticleFilter::init (particle_filter.cpp:53-69).  The reference
+ * draws from std::normal_distribution<float> on a random_device-seeded
+ * mt19937; here a counter-based generator seeded with `seed` (statistical
+ * parity only). */
+NDT2D_API int ndt2d_filter_init(
+  ndt2d_filter * f, double x, double y, double theta, double sigma_x, double sigma_y,
+  double sigma_theta, uint64_t seed);
+
+/* replaces ParticleFilter::update -> MotionModel::sample
+ * (particle_filter.cpp:71-76, motion_model.cpp:45-83); alphas5 = odom_alpha1..5
+ * (statistical parity only, see init). */
+NDT2D_API int ndt2d_filter_update(
+  ndt2d_filter * f, double dx, double dy, double dth, const double * alphas5, uint64_t seed);
+
+/* replaces ParticleFilter::measure (particle_filter.cpp:78-89): one
+ * scorePoints per particle against the matcher's model, then updateStatistics.
+ * The scan's own pose is ignored, as in the reference (:85). */
+NDT2D_API int ndt2d_filter_measure(
+  ndt2d_filter * f, ndt2d_matcher * m, const double * pts_xy, size_t npts);
+
+/* replaces ParticleFilter::resample (particle_filter.cpp:91-137) incl. the
+ * KD-tree bin count (kd_tree.hpp:97-189) and the trailing updateStatistics.
+ * uniforms: the variates std::discrete_distribution would consume, one per
+ * draw, at least max_particles of them; NULL = generate on the device from
+ * `seed`. */
+NDT2D_API int ndt2d_filter_resample(
+  ndt2d_filter * f, double kld_err, double kld_z, const double * uniforms, size_t n_uniforms,
+  uint64_t seed);
+
+/* replaces getMean / getCovariance (particle_filter.cpp:139-147).  Note the
+ * reference accumulates cov(2,2) across calls (`+=`, :216); so does this. */
+NDT2D_API int ndt2d_filter_stats(ndt2d_filter * f, double * mean3, double * cov9);
+/* Test hook: overwrite the retained covariance (cov_). */
+NDT2D_API int ndt2d_filter_set_cov(ndt2d_filter * f, const double * cov9);
+/* Indices drawn by the last resample (out must hold size() entries). */
+NDT2D_API int ndt2d_filter_last_draws(ndt2d_filter * f, uint64_t * out);
+
+/* ------------------------------------------------------------------------
+ * Synthetic laser world (host code; shared by tests and bench so that the
+ * oracle and the device path see identical inputs).  Not part of the
+ * reference; SURVEY.md section 8(d) defines it.
+ * ---------------------------------------------------------------------- */
+
+/* n_obstacles axis-aligned rectangles (xmin, ymin, xmax, ymax) inside a square
+ * arena of side `arena`: sides U[side_min, side_max] m, centres
+ * U[5, arena-5]^2, SplitMix64(seed). */
+NDT2D_API int ndt2d_synth_world(
+  uint64_t seed, double arena, int n_obstacles, double side_min, double side_max,
+  double * rects4);
+
+/* Ray-casts `beams` beams (angle -pi + i*2pi/beams in the sensor frame) from
+ * each pose against the arena walls and the rectangles, adds N(0, sigma)
+ * range noise (stream seed + scan index), drops returns beyond range_max and
+ * writes sensor-frame points.  pt_offsets gets n_scans+1 entries; pts_xy must
+ * hold 2*beams*n_scans doubles.  Multi-threaded on the host. */
+NDT2D_API int ndt2d_synth_scans(
+  const double * rects4, int n_rects, double arena, const double * poses3, size_t n_scans,
+  int beams, double range_max, double noise_sigma, uint64_t seed, uint64_t * pt_offsets,
+  double * pts_xy);
+
+/* SplitMix64-based uniform doubles in [0,1): out[i] for stream `seed`. */
+NDT2D_API void ndt2d_synth_uniform(uint64_t seed, size_t n, double * out);
+/* Standard normal variates (Box-Muller on the uniform stream). */
+NDT2D_API void ndt2d_synth_normal(uint64_t seed, size_t n, double * out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* NDT2D_B200_H_ */

@@ -1,0 +1,1320 @@
+// api.cu -- the C ABI of libndt2d_b200.so (include/ndt2d_b200.h): handles,
+// host-side replay of the reference's loop bounds and trigonometry, staging,
+// and the launch sequences of build.cu / search.cu / filter.cu.
+//
+// Host work kept deliberately (it is what makes cell indices bit-exact):
+//   * the (dth, dx, dy) lattices are replayed with the reference's accumulating
+//     double loops (scan_matcher_ndt.cpp:103,117,119), never as -size + i*res;
+//   * cos/sin of scan poses and of pose.theta + dth come from the host libm,
+//     the same library the reference calls (ndt_model.cpp:135-136,
+//     scan_matcher_ndt.cpp:106-107);
+//   * the scan subsampling index size_t(i * step) (:95-96,110).
+// Everything per point / per candidate runs on the device.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "ndt2d_internal.h"
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_last_error[512] = "";
+
+void ndt2d_set_error(const char * what, cudaError_t e, const char * file, int line)
+{
+  snprintf(g_last_error, sizeof(g_last_error), "%s:%d: %s -> %s (%s)", file, line, what,
+    cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+namespace
+{
+
+struct DeviceBuffer
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) {return NDT2D_OK;}
+    if (p) {
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    // grow geometrically so rolling-window rebuilds do not re-allocate
+    size_t want = bytes + bytes / 4 + 256;
+    NDT2D_CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return NDT2D_OK;
+  }
+  void release()
+  {
+    if (p) {cudaFree(p);}
+    p = nullptr;
+    cap = 0;
+  }
+  template<typename T> T * as() const {return static_cast<T *>(p);}
+};
+
+struct PinnedBuffer
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) {return NDT2D_OK;}
+    if (p) {
+      cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    NDT2D_CUDA_TRY(cudaMallocHost(&p, want));
+    cap = want;
+    return NDT2D_OK;
+  }
+  void release()
+  {
+    if (p) {cudaFreeHost(p);}
+    p = nullptr;
+    cap = 0;
+  }
+  template<typename T> T * as() const {return static_cast<T *>(p);}
+};
+
+struct DeviceGuard
+{
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) {prev = -1;}
+    if (prev != dev) {ok = cudaSetDevice(dev) == cudaSuccess;}
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0) {cudaSetDevice(prev);}
+  }
+};
+
+// Replays `for (v = -size; v < size; v += res)`.
+int replay_loop(double size, double res, size_t limit, std::vector<double> & out)
+{
+  out.clear();
+  if (!(res > 0.0) || !std::isfinite(res) || !std::isfinite(size)) {return NDT2D_ERR_INVALID;}
+  if (size > 0.0 && (2.0 * size / res) > static_cast<double>(limit)) {return NDT2D_ERR_SIZE;}
+  for (double v = -size; v < size; v += res) {
+    out.push_back(v);
+    if (out.size() > limit) {return NDT2D_ERR_SIZE;}
+  }
+  return NDT2D_OK;
+}
+
+// The reference's grid coordinate on one axis (NDT::getIndex,
+// ndt_model.cpp:205-215) as a monotone function of v:
+//   -1 below the origin, else min(unsigned((v - origin) / cell), size).
+inline int64_t ref_coord(double v, double origin, double cell, uint32_t size)
+{
+  if (v < origin) {return -1;}
+  const double q = (v - origin) / cell;
+  if (!(q < static_cast<double>(size))) {return size;}
+  return static_cast<int64_t>(static_cast<unsigned int>(q));
+}
+
+// thr[k], k = 0..size: the smallest double v with ref_coord(v) >= k.
+// ref_coord is monotone non-decreasing in v (subtraction, division by a
+// positive constant and truncation all are), so the thresholds partition the
+// axis exactly like the reference's own arithmetic does.
+void axis_thresholds(double origin, double cell, uint32_t size, std::vector<double> & thr)
+{
+  thr.resize(static_cast<size_t>(size) + 1);
+  thr[0] = origin;
+  for (uint32_t k = 1; k <= size; ++k) {
+    double v = origin + static_cast<double>(k) * cell;
+    int steps = 0;
+    // walk down while still >= k, then up until >= k
+    while (ref_coord(v, origin, cell, size) >= static_cast<int64_t>(k) && steps < 4096) {
+      v = std::nextafter(v, -std::numeric_limits<double>::infinity());
+      ++steps;
+    }
+    while (ref_coord(v, origin, cell, size) < static_cast<int64_t>(k) && steps < 8192) {
+      v = std::nextafter(v, std::numeric_limits<double>::infinity());
+      ++steps;
+    }
+    thr[k] = v;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- matcher
+struct ndt2d_matcher
+{
+  std::mutex mu;
+  ndt2d_params prm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Counters ctr{0, 0, 0};
+
+  size_t max_beams = 0;             // laser_max_beams as size_t (hpp:99)
+  std::vector<double> dth, dlin;    // replayed loops
+  DeviceBuffer d_dth, d_dlin;
+
+  bool has_model = false;
+  GridDesc g{};
+  DeviceBuffer d_occ, d_rec, d_thr, d_nvalid;
+  uint32_t rec_cap = 0;
+  uint32_t n_valid = 0;
+
+  BuildScratch bs{};
+  DeviceBuffer d_wx, d_wy, d_key0, d_key1, d_val0, d_val1, d_seglen, d_hist, d_scantmp;
+  DeviceBuffer d_scan_tf, d_offsets, d_mappts;
+  size_t n_map_points = 0;
+  int sorted_buf = 0;
+
+  bool staged = false;
+  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out;
+  double pose_x = 0, pose_y = 0;
+  uint32_t n_pts = 0;
+
+  PinnedBuffer h_stage, h_result;
+};
+
+namespace
+{
+
+ModelView model_view(const ndt2d_matcher * m)
+{
+  ModelView mv;
+  mv.g = m->g;
+  mv.occ = m->d_occ.as<uint2>();
+  mv.rec = m->d_rec.as<double>();
+  mv.thr_x = m->d_thr.as<double>();
+  mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 1);
+  mv.n_valid_cap = m->rec_cap;
+  return mv;
+}
+
+SearchView search_view(const ndt2d_matcher * m)
+{
+  SearchView sv;
+  sv.pts = m->d_pts.as<double2>();
+  sv.trig = m->d_trig.as<double2>();
+  sv.dth = m->d_dth.as<double>();
+  sv.dlin = m->d_dlin.as<double>();
+  sv.pose_x = m->pose_x;
+  sv.pose_y = m->pose_y;
+  sv.n_pts = m->n_pts;
+  sv.n_ang = static_cast<uint32_t>(m->dth.size());
+  sv.n_lin = static_cast<uint32_t>(m->dlin.size());
+  return sv;
+}
+
+// scan_matcher_ndt.cpp:95-96,110 : n = min(laser_max_beams, N); j = size_t(i * (N / n))
+size_t subsample_count(const ndt2d_matcher * m, size_t npts)
+{
+  return m->max_beams < npts ? m->max_beams : npts;
+}
+
+void subsample_points(const double * pts_xy, size_t npts, size_t n_use, double * out_xy)
+{
+  const double step = static_cast<double>(npts) / static_cast<double>(n_use);
+  for (size_t i = 0; i < n_use; ++i) {
+    const size_t j = static_cast<size_t>(i * step);
+    out_xy[2 * i] = pts_xy[2 * j];
+    out_xy[2 * i + 1] = pts_xy[2 * j + 1];
+  }
+}
+
+int add_scans_locked(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy)
+{
+  m->has_model = false;
+  m->staged = m->staged;  // a staged scan stays valid across rebuilds
+  // bounding box (scan_matcher_ndt.cpp:53-64); max_* start at DBL_MIN (> 0)
+  double min_x = DBL_MAX, max_x = DBL_MIN, min_y = DBL_MAX, max_y = DBL_MIN;
+  for (size_t k = 0; k < n_scans; ++k) {
+    const double * pose = poses + 3 * k;
+    min_x = std::min(pose[0] - m->prm.range_max, min_x);
+    max_x = std::max(pose[0] + m->prm.range_max, max_x);
+    min_y = std::min(pose[1] - m->prm.range_max, min_y);
+    max_y = std::max(pose[1] + m->prm.range_max, max_y);
+  }
+  // NDT::NDT (ndt_model.cpp:118-126): size = size_t(extent / cell + 1)
+  const double cell = m->prm.ndt_resolution;
+  const double fx = ((max_x - min_x) / cell) + 1, fy = ((max_y - min_y) / cell) + 1;
+  if (!(fx >= 0.0) || !(fy >= 0.0) || !std::isfinite(fx) || !std::isfinite(fy) ||
+    !std::isfinite(min_x) || !std::isfinite(min_y))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  if (fx > 65000.0 || fy > 65000.0) {return NDT2D_ERR_SIZE;}
+  GridDesc g;
+  g.origin_x = min_x;
+  g.origin_y = min_y;
+  g.cell_size = cell;
+  g.size_x = static_cast<uint32_t>(static_cast<size_t>(fx));
+  g.size_y = static_cast<uint32_t>(static_cast<size_t>(fy));
+  const uint64_t n_cells64 = static_cast<uint64_t>(g.size_x) * g.size_y;
+  const uint64_t n_padded64 = static_cast<uint64_t>(g.size_x + 2) * (g.size_y + 2);
+  if (n_padded64 >= (1ull << 31)) {return NDT2D_ERR_SIZE;}
+  g.pitch = g.size_x + 2;
+  g.n_cells = static_cast<uint32_t>(n_cells64);
+  g.n_padded = static_cast<uint32_t>(n_padded64);
+  g.n_words = (g.n_padded + 31) / 32;
+
+  const size_t n_points = n_scans ? static_cast<size_t>(pt_offsets[n_scans] - pt_offsets[0]) : 0;
+  if (n_points >= (1ull << 32) - 1) {return NDT2D_ERR_SIZE;}
+  const uint64_t off0 = n_scans ? pt_offsets[0] : 0;
+
+  // ---- host staging: per-scan transform, rebased offsets, axis thresholds
+  std::vector<double> thr_x, thr_y;
+  axis_thresholds(g.origin_x, g.cell_size, g.size_x, thr_x);
+  axis_thresholds(g.origin_y, g.cell_size, g.size_y, thr_y);
+  const size_t tf_bytes = n_scans * sizeof(double4);
+  const size_t off_bytes = (n_scans + 1) * sizeof(uint64_t);
+  const size_t thr_bytes = (thr_x.size() + thr_y.size()) * sizeof(double);
+  int rc = m->h_stage.ensure(tf_bytes + off_bytes + thr_bytes);
+  if (rc) {return rc;}
+  char * hs = m->h_stage.as<char>();
+  double4 * h_tf = reinterpret_cast<double4 *>(hs);
+  uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + tf_bytes);
+  double * h_thr = reinterpret_cast<double *>(hs + tf_bytes + off_bytes);
+  for (size_t k = 0; k < n_scans; ++k) {
+    const double * pose = poses + 3 * k;
+    // ndt_model.cpp:135-136
+    h_tf[k] = make_double4(pose[0], pose[1], cos(pose[2]), sin(pose[2]));
+    h_off[k] = pt_offsets[k] - off0;
+  }
+  h_off[n_scans] = n_points;
+  memcpy(h_thr, thr_x.data(), thr_x.size() * sizeof(double));
+  memcpy(h_thr + thr_x.size(), thr_y.data(), thr_y.size() * sizeof(double));
+
+  // ---- device buffers
+  const size_t np1 = n_points ? n_points : 1;
+  if ((rc = m->d_scan_tf.ensure(tf_bytes ? tf_bytes : 32))) {return rc;}
+  if ((rc = m->d_offsets.ensure(off_bytes))) {return rc;}
+  if ((rc = m->d_thr.ensure(thr_bytes))) {return rc;}
+  if ((rc = m->d_mappts.ensure(np1 * sizeof(double2)))) {return rc;}
+  if ((rc = m->d_wx.ensure(np1 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_wy.ensure(np1 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_key0.ensure(np1 * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_key1.ensure(np1 * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_val0.ensure(np1 * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_val1.ensure(np1 * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_seglen.ensure(np1 * sizeof(uint32_t)))) {return rc;}
+  const size_t sort_blocks = (np1 + 4095) / 4096;
+  if ((rc = m->d_hist.ensure(sort_blocks * 256 * sizeof(uint32_t)))) {return rc;}
+  const size_t scan_n = std::max<size_t>(sort_blocks * 256, g.n_words);
+  if ((rc = m->d_scantmp.ensure(((scan_n + 8191) / 8192 + 1) * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_occ.ensure(static_cast<size_t>(g.n_words) * sizeof(uint2)))) {return rc;}
+  if ((rc = m->d_nvalid.ensure(sizeof(uint32_t)))) {return rc;}
+  const uint64_t cap64 = std::min<uint64_t>(n_cells64, n_points / 5) + 1;
+  m->rec_cap = static_cast<uint32_t>(cap64);
+  if ((rc = m->d_rec.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
+
+  m->bs.wx = m->d_wx.as<double>();
+  m->bs.wy = m->d_wy.as<double>();
+  m->bs.key[0] = m->d_key0.as<uint32_t>();
+  m->bs.key[1] = m->d_key1.as<uint32_t>();
+  m->bs.val[0] = m->d_val0.as<uint32_t>();
+  m->bs.val[1] = m->d_val1.as<uint32_t>();
+  m->bs.seglen = m->d_seglen.as<uint32_t>();
+  m->bs.hist = m->d_hist.as<uint32_t>();
+  m->bs.scan_tmp = m->d_scantmp.as<uint32_t>();
+
+  // ---- uploads
+  cudaStream_t st = m->stream;
+  if (tf_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_scan_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
+  }
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_offsets.p, h_off, off_bytes, cudaMemcpyHostToDevice, st));
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_thr.p, h_thr, thr_bytes, cudaMemcpyHostToDevice, st));
+  if (n_points) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_mappts.p, pts_xy + 2 * off0, n_points * sizeof(double2),
+      cudaMemcpyHostToDevice, st));
+  }
+  m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
+
+  rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
+      m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_rec.as<double>(),
+      m->rec_cap, m->d_nvalid.as<uint32_t>(), st, &m->ctr, &m->sorted_buf);
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
+  m->g = g;
+  m->n_map_points = n_points;
+  m->has_model = true;
+  return NDT2D_OK;
+}
+
+int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts)
+{
+  const size_t n_use = subsample_count(m, npts);
+  if (n_use >= (1u << 30)) {return NDT2D_ERR_SIZE;}
+  const size_t n_ang = m->dth.size();
+  const size_t pts_bytes = n_use * sizeof(double2);
+  const size_t trig_bytes = n_ang * sizeof(double2);
+  int rc = m->h_stage.ensure(pts_bytes + trig_bytes + 64);
+  if (rc) {return rc;}
+  if ((rc = m->d_pts.ensure(pts_bytes ? pts_bytes : 16))) {return rc;}
+  if ((rc = m->d_trig.ensure(trig_bytes ? trig_bytes : 16))) {return rc;}
+  double * h_pts = m->h_stage.as<double>();
+  double * h_trig = h_pts + 2 * n_use;
+  if (n_use) {subsample_points(pts_xy, npts, n_use, h_pts);}
+  for (size_t k = 0; k < n_ang; ++k) {
+    // scan_matcher_ndt.cpp:106-107
+    h_trig[2 * k] = cos(pose3[2] + m->dth[k]);
+    h_trig[2 * k + 1] = sin(pose3[2] + m->dth[k]);
+  }
+  cudaStream_t st = m->stream;
+  if (pts_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes, cudaMemcpyHostToDevice, st));
+  }
+  if (trig_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_trig.p, h_trig, trig_bytes, cudaMemcpyHostToDevice, st));
+  }
+  m->ctr.h2d_bytes += pts_bytes + trig_bytes;
+  m->pose_x = pose3[0];
+  m->pose_y = pose3[1];
+  m->n_pts = static_cast<uint32_t>(n_use);
+  // search scratch
+  const size_t scratch = ndt2d_search_scratch_doubles(
+    static_cast<uint32_t>(n_ang), static_cast<uint32_t>(m->dlin.size()), m->prm.kernel_variant);
+  if ((rc = m->d_blockpart.ensure(scratch * sizeof(double)))) {return rc;}
+  if ((rc = m->d_partial.ensure(32 * sizeof(double)))) {return rc;}
+  if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
+  // the pinned staging area is reused by the next call: wait for the copies
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  m->staged = true;
+  return NDT2D_OK;
+}
+
+void unpack_result(const double * r32, double * out_delta3, int * delta_written,
+  double * out_cov9, double * out_score)
+{
+  const bool written = r32[19] != 0.0;
+  if (delta_written) {*delta_written = written ? 1 : 0;}
+  if (written && out_delta3) {
+    out_delta3[0] = r32[16];
+    out_delta3[1] = r32[17];
+    out_delta3[2] = r32[18];
+  }
+  if (out_cov9) {memcpy(out_cov9, r32 + 20, 9 * sizeof(double));}
+  if (out_score) {*out_score = r32[29];}
+}
+
+int fetch_result_locked(ndt2d_matcher * m, double * r32)
+{
+  double * h = m->h_result.as<double>();
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(h, m->d_partial.p, 32 * sizeof(double), cudaMemcpyDeviceToHost,
+    m->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->ctr.d2h_bytes += 32 * sizeof(double);
+  memcpy(r32, h, 32 * sizeof(double));
+  return NDT2D_OK;
+}
+
+int match_scan_locked(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  int rc = stage_scan_locked(m, pose3, pts_xy, npts);
+  if (rc) {return rc;}
+  rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(m->dth.size()),
+      m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(), nullptr,
+      m->stream, &m->ctr);
+  if (rc) {return rc;}
+  double r32[32];
+  if ((rc = fetch_result_locked(m, r32))) {return rc;}
+  unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
+  return NDT2D_OK;
+}
+
+int score_poses_locked(
+  ndt2d_matcher * m, const double * pts_xy, size_t npts, const double * poses3, size_t n_poses,
+  double sign, int normalise, bool subsample, double * out_scores)
+{
+  const size_t n_use = subsample ? subsample_count(m, npts) : npts;
+  if (n_use >= (1u << 30) || n_poses >= (1u << 30)) {return NDT2D_ERR_SIZE;}
+  const size_t pts_bytes = n_use * sizeof(double2);
+  const size_t tf_bytes = n_poses * sizeof(double4);
+  const size_t out_bytes = n_poses * sizeof(double);
+  int rc = m->h_stage.ensure(pts_bytes + tf_bytes + 64);
+  if (rc) {return rc;}
+  if ((rc = m->d_pts.ensure(pts_bytes ? pts_bytes : 16))) {return rc;}
+  if ((rc = m->d_pose_tf.ensure(tf_bytes ? tf_bytes : 32))) {return rc;}
+  if ((rc = m->d_out.ensure(out_bytes ? out_bytes : 8))) {return rc;}
+  if ((rc = m->h_result.ensure(std::max<size_t>(out_bytes, 64 * sizeof(double))))) {return rc;}
+  m->staged = false;  // d_pts is overwritten
+  double4 * h_tf = m->h_stage.as<double4>();
+  double * h_pts = reinterpret_cast<double *>(h_tf + n_poses);
+  for (size_t p = 0; p < n_poses; ++p) {
+    const double * pose = poses3 + 3 * p;
+    h_tf[p] = make_double4(pose[0], pose[1], cos(pose[2]), sin(pose[2]));
+  }
+  if (n_use) {
+    if (subsample) {
+      subsample_points(pts_xy, npts, n_use, h_pts);
+    } else {
+      memcpy(h_pts, pts_xy, pts_bytes);
+    }
+  }
+  cudaStream_t st = m->stream;
+  if (pts_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes, cudaMemcpyHostToDevice, st));
+  }
+  if (tf_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pose_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
+  }
+  m->ctr.h2d_bytes += pts_bytes + tf_bytes;
+  rc = ndt2d_launch_score_poses(model_view(m), m->d_pts.as<double2>(),
+      static_cast<uint32_t>(n_use), m->d_pose_tf.as<double4>(), static_cast<uint32_t>(n_poses),
+      sign, normalise, m->d_out.as<double>(), st, &m->ctr);
+  if (rc) {return rc;}
+  if (out_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->h_result.p, m->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  m->ctr.d2h_bytes += out_bytes;
+  if (out_bytes) {memcpy(out_scores, m->h_result.p, out_bytes);}
+  return NDT2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+NDT2D_API const char * ndt2d_version(void) {return "ndt2d_b200 0.1 (sm_100a)";}
+NDT2D_API const char * ndt2d_last_error(void) {return g_last_error;}
+
+NDT2D_API int ndt2d_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+NDT2D_API void ndt2d_default_params(ndt2d_params * p)
+{
+  if (!p) {return;}
+  p->ndt_resolution = 0.25;
+  p->search_angular_resolution = 0.0025;
+  p->search_angular_size = 0.1;
+  p->search_linear_resolution = 0.005;
+  p->search_linear_size = 0.05;
+  p->laser_max_beams = 100;
+  p->range_max = 0.0;
+  p->device = -1;
+  p->stream = nullptr;
+  p->kernel_variant = 0;
+}
+
+NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher ** out)
+{
+  if (!params || !out) {return NDT2D_ERR_INVALID;}
+  *out = nullptr;
+  if (!(params->ndt_resolution > 0.0) || !std::isfinite(params->ndt_resolution) ||
+    !std::isfinite(params->range_max))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  if (ndt2d_device_count() <= 0) {
+    snprintf(g_last_error, sizeof(g_last_error),
+      "no CUDA device visible: libndt2d_b200 has no CPU fallback");
+    return NDT2D_ERR_NO_DEVICE;
+  }
+  int dev = params->device;
+  if (dev < 0) {
+    NDT2D_CUDA_TRY(cudaGetDevice(&dev));
+  }
+  ndt2d_matcher * m = new (std::nothrow) ndt2d_matcher();
+  if (!m) {return NDT2D_ERR_INVALID;}
+  m->prm = *params;
+  m->device = dev;
+  // declare_parameter<int> stored into a size_t (scan_matcher_ndt.cpp:44, hpp:99)
+  m->max_beams = static_cast<size_t>(params->laser_max_beams);
+  int rc = replay_loop(params->search_angular_size, params->search_angular_resolution,
+      1u << 24, m->dth);
+  if (!rc) {
+    rc = replay_loop(params->search_linear_size, params->search_linear_resolution, 65535, m->dlin);
+  }
+  if (rc) {
+    delete m;
+    return rc;
+  }
+  DeviceGuard guard(dev);
+  if (!guard.ok) {
+    delete m;
+    return NDT2D_ERR_NO_DEVICE;
+  }
+  if (params->stream) {
+    m->stream = static_cast<cudaStream_t>(params->stream);
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      ndt2d_set_error("cudaStreamCreate", e, __FILE__, __LINE__);
+      delete m;
+      return NDT2D_ERR_CUDA;
+    }
+    m->own_stream = true;
+  }
+  const size_t na = m->dth.size(), nl = m->dlin.size();
+  rc = m->d_dth.ensure((na ? na : 1) * sizeof(double));
+  if (!rc) {rc = m->d_dlin.ensure((nl ? nl : 1) * sizeof(double));}
+  if (!rc && na) {
+    if (cudaMemcpy(m->d_dth.p, m->dth.data(), na * sizeof(double), cudaMemcpyHostToDevice) !=
+      cudaSuccess) {rc = NDT2D_ERR_CUDA;}
+  }
+  if (!rc && nl) {
+    if (cudaMemcpy(m->d_dlin.p, m->dlin.data(), nl * sizeof(double), cudaMemcpyHostToDevice) !=
+      cudaSuccess) {rc = NDT2D_ERR_CUDA;}
+  }
+  if (rc) {
+    ndt2d_matcher_destroy(m);
+    return rc;
+  }
+  m->ctr.h2d_bytes += (na + nl) * sizeof(double);
+  *out = m;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
+{
+  if (!m) {return NDT2D_OK;}
+  {
+    DeviceGuard guard(m->device);
+    if (m->stream) {cudaStreamSynchronize(m->stream);}
+    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_rec, &m->d_thr, &m->d_nvalid,
+      &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
+      &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out};
+    for (DeviceBuffer * b : bufs) {b->release();}
+    m->h_stage.release();
+    m->h_result.release();
+    if (m->own_stream && m->stream) {cudaStreamDestroy(m->stream);}
+  }
+  delete m;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_reset(ndt2d_matcher * m)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->has_model = false;  // scan_matcher_ndt.cpp:180-183
+  m->n_map_points = 0;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_add_scans(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy)
+{
+  if (!m || (n_scans && (!poses || !pt_offsets))) {return NDT2D_ERR_INVALID;}
+  if (n_scans && pt_offsets[n_scans] > pt_offsets[0] && !pts_xy) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  return add_scans_locked(m, n_scans, poses, pt_offsets, pts_xy);
+}
+
+NDT2D_API int ndt2d_matcher_match_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (!m || !pose3 || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (delta_written) {*delta_written = 0;}
+  if (!m->has_model) {
+    if (out_score) {*out_score = 0.0;}  // scan_matcher_ndt.cpp:80
+    return NDT2D_ERR_NO_MAP;
+  }
+  DeviceGuard guard(m->device);
+  return match_scan_locked(m, pose3, pts_xy, npts, out_delta3, delta_written, out_cov9, out_score);
+}
+
+NDT2D_API int ndt2d_matcher_score_points(
+  ndt2d_matcher * m, const double * pts_xy, size_t npts, const double * pose3, double * out_score)
+{
+  if (!m || !pose3 || !out_score || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {
+    *out_score = 0.0;  // scan_matcher_ndt.cpp:159
+    return NDT2D_ERR_NO_MAP;
+  }
+  DeviceGuard guard(m->device);
+  return score_poses_locked(m, pts_xy, npts, pose3, 1, -1.0, 1, true, out_score);
+}
+
+NDT2D_API int ndt2d_matcher_score_poses(
+  ndt2d_matcher * m, const double * pts_xy, size_t npts, const double * poses3, size_t n_poses,
+  double * out_scores)
+{
+  if (!m || (n_poses && (!poses3 || !out_scores)) || (npts && !pts_xy)) {
+    return NDT2D_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {
+    for (size_t i = 0; i < n_poses; ++i) {out_scores[i] = 0.0;}
+    return NDT2D_ERR_NO_MAP;
+  }
+  DeviceGuard guard(m->device);
+  return score_poses_locked(m, pts_xy, npts, poses3, n_poses, -1.0, 1, true, out_scores);
+}
+
+NDT2D_API int ndt2d_matcher_likelihood_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_likelihood)
+{
+  if (!m || !pose3 || !out_likelihood || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {
+    *out_likelihood = 0.0;
+    return NDT2D_ERR_NO_MAP;
+  }
+  DeviceGuard guard(m->device);
+  return score_poses_locked(m, pts_xy, npts, pose3, 1, 1.0, 0, false, out_likelihood);
+}
+
+NDT2D_API int ndt2d_matcher_match_scan_batch(
+  ndt2d_matcher * m, size_t n_jobs,
+  const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
+  const double * map_pts_xy,
+  const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (!m || (n_jobs && (!job_scan_offsets || !map_poses || !map_pt_offsets || !query_poses ||
+    !query_pt_offsets)))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  for (size_t j = 0; j < n_jobs; ++j) {
+    const uint64_t s0 = job_scan_offsets[j], s1 = job_scan_offsets[j + 1];
+    int rc = add_scans_locked(m, static_cast<size_t>(s1 - s0), map_poses + 3 * s0,
+        map_pt_offsets + s0, map_pts_xy);
+    if (rc) {return rc;}
+    const uint64_t q0 = query_pt_offsets[j], q1 = query_pt_offsets[j + 1];
+    if (delta_written) {delta_written[j] = 0;}
+    rc = match_scan_locked(m, query_poses + 3 * j, query_pts_xy + 2 * q0,
+        static_cast<size_t>(q1 - q0), out_delta3 ? out_delta3 + 3 * j : nullptr,
+        delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
+        out_score ? out_score + j : nullptr);
+    if (rc) {return rc;}
+  }
+  m->has_model = false;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_search_shape(
+  const ndt2d_matcher * m, uint64_t * n_angular, uint64_t * n_linear)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  if (n_angular) {*n_angular = m->dth.size();}
+  if (n_linear) {*n_linear = m->dlin.size();}
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_search_values(const ndt2d_matcher * m, double * dth, double * dlin)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  if (dth) {memcpy(dth, m->dth.data(), m->dth.size() * sizeof(double));}
+  if (dlin) {memcpy(dlin, m->dlin.data(), m->dlin.size() * sizeof(double));}
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_stage_scan(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts)
+{
+  if (!m || !pose3 || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  return stage_scan_locked(m, pose3, pts_xy, npts);
+}
+
+NDT2D_API int ndt2d_matcher_search_staged(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  if (!m->staged) {return NDT2D_ERR_STATE;}
+  const uint64_t n_ang = m->dth.size();
+  if (theta_begin > theta_end || theta_end > n_ang) {return NDT2D_ERR_INVALID;}
+  DeviceGuard guard(m->device);
+  int rc = ndt2d_launch_search(model_view(m), search_view(m), static_cast<uint32_t>(theta_begin),
+      static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
+      m->d_partial.as<double>(), nullptr, m->stream, &m->ctr);
+  if (rc) {return rc;}
+  if (d_partial) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(d_partial, m->d_partial.p,
+      NDT2D_PARTIAL_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16)
+{
+  if (!m || !partial16) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->staged) {return NDT2D_ERR_STATE;}
+  DeviceGuard guard(m->device);
+  double r32[32];
+  int rc = fetch_result_locked(m, r32);
+  if (rc) {return rc;}
+  memcpy(partial16, r32, NDT2D_PARTIAL_DOUBLES * sizeof(double));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_combine_partials(
+  const ndt2d_matcher * m, const double * partials, size_t n_partials,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (!m || (n_partials && !partials)) {return NDT2D_ERR_INVALID;}
+  double best = 0.0, best_idx = 1.0e300, s[10] = {0}, npts = 0.0;
+  for (size_t r = 0; r < n_partials; ++r) {
+    const double * p = partials + r * NDT2D_PARTIAL_DOUBLES;
+    if (p[0] < best || (p[0] == best && p[1] < best_idx)) {
+      best = p[0];
+      best_idx = p[1];
+    }
+    for (int k = 0; k < 10; ++k) {s[k] += p[2 + k];}
+    npts = std::max(npts, p[13]);
+  }
+  const bool written = best < 0.0;
+  if (delta_written) {*delta_written = written ? 1 : 0;}
+  if (written && out_delta3) {
+    const uint64_t n_lin = m->dlin.size(), n_cand = n_lin * n_lin;
+    const uint64_t idx = static_cast<uint64_t>(best_idx);
+    const uint64_t it = idx / n_cand, rem = idx - it * n_cand;
+    out_delta3[0] = m->dlin[rem / n_lin];
+    out_delta3[1] = m->dlin[rem % n_lin];
+    out_delta3[2] = m->dth[it];
+  }
+  if (out_cov9) {
+    const double sum = s[9], inv_s = 1.0 / sum, inv_s2 = 1.0 / (sum * sum);
+    const double k[9] = {s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]};
+    const double u[3] = {s[6], s[7], s[8]};
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {
+        out_cov9[r * 3 + c] = inv_s * k[r * 3 + c] + (inv_s2 * u[r]) * u[c];
+      }
+    }
+  }
+  if (out_score) {*out_score = best / npts;}
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_combine_device(
+  ndt2d_matcher * m, const void * d_partials, size_t n_partials,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (!m || !d_partials || n_partials == 0) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  int rc = m->d_partial.ensure(32 * sizeof(double));
+  if (!rc) {rc = m->h_result.ensure(64 * sizeof(double));}
+  if (rc) {return rc;}
+  rc = ndt2d_launch_combine(static_cast<const double *>(d_partials),
+      static_cast<uint32_t>(n_partials), m->d_dth.as<double>(), m->d_dlin.as<double>(),
+      static_cast<uint32_t>(m->dlin.size()), m->d_partial.as<double>(), m->stream, &m->ctr);
+  if (rc) {return rc;}
+  double r32[32];
+  if ((rc = fetch_result_locked(m, r32))) {return rc;}
+  if (delta_written) {*delta_written = 0;}
+  unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_grid_info(ndt2d_matcher * m, double * info5)
+{
+  if (!m || !info5) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  info5[0] = m->g.size_x;
+  info5[1] = m->g.size_y;
+  info5[2] = m->g.origin_x;
+  info5[3] = m->g.origin_y;
+  info5[4] = m->g.cell_size;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_dump_cells(ndt2d_matcher * m, double * out)
+{
+  if (!m || !out) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  DeviceGuard guard(m->device);
+  const size_t bytes = static_cast<size_t>(m->g.n_cells) * 16 * sizeof(double);
+  DeviceBuffer tmp;
+  int rc = tmp.ensure(bytes ? bytes : 8);
+  if (rc) {return rc;}
+  rc = ndt2d_launch_dump_cells(m->g, m->bs, m->sorted_buf, m->n_map_points, tmp.as<double>(),
+      m->stream, &m->ctr);
+  if (!rc && bytes) {
+    cudaError_t e = cudaMemcpyAsync(out, tmp.p, bytes, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) {e = cudaStreamSynchronize(m->stream);}
+    if (e != cudaSuccess) {
+      ndt2d_set_error("dump_cells copy", e, __FILE__, __LINE__);
+      rc = NDT2D_ERR_CUDA;
+    }
+    m->ctr.d2h_bytes += bytes;
+  }
+  tmp.release();
+  return rc;
+}
+
+NDT2D_API int ndt2d_matcher_dump_keys(ndt2d_matcher * m, int32_t * out, size_t n_points)
+{
+  if (!m || !out) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  if (n_points != m->n_map_points) {return NDT2D_ERR_INVALID;}
+  if (n_points == 0) {return NDT2D_OK;}
+  DeviceGuard guard(m->device);
+  // sorted (key, point index) pairs -> keys in add_scans order
+  std::vector<uint32_t> keys(n_points), vals(n_points);
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(keys.data(), m->bs.key[m->sorted_buf],
+    n_points * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(vals.data(), m->bs.val[m->sorted_buf],
+    n_points * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->ctr.d2h_bytes += 2 * n_points * sizeof(uint32_t);
+  for (size_t i = 0; i < n_points; ++i) {
+    out[vals[i]] = keys[i] >= m->g.n_cells ? -1 : static_cast<int32_t>(keys[i]);
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_dump_scores(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts, double * out,
+  size_t n_out)
+{
+  if (!m || !pose3 || !out || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  const size_t n_ang = m->dth.size(), n_lin = m->dlin.size();
+  if (n_out != n_ang * n_lin * n_lin) {return NDT2D_ERR_INVALID;}
+  if (n_out == 0) {return NDT2D_OK;}
+  DeviceGuard guard(m->device);
+  int rc = stage_scan_locked(m, pose3, pts_xy, npts);
+  if (rc) {return rc;}
+  DeviceBuffer tmp;
+  if ((rc = tmp.ensure(n_out * sizeof(double)))) {return rc;}
+  rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(n_ang),
+      m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(),
+      tmp.as<double>(), m->stream, &m->ctr);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out, tmp.p, n_out * sizeof(double), cudaMemcpyDeviceToHost,
+        m->stream);
+    if (e == cudaSuccess) {e = cudaStreamSynchronize(m->stream);}
+    if (e != cudaSuccess) {
+      ndt2d_set_error("dump_scores copy", e, __FILE__, __LINE__);
+      rc = NDT2D_ERR_CUDA;
+    }
+    m->ctr.d2h_bytes += n_out * sizeof(double);
+  }
+  tmp.release();
+  return rc;
+}
+
+NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4)
+{
+  if (!m || !out4) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  out4[0] = m->ctr.launches;
+  out4[1] = m->ctr.h2d_bytes;
+  out4[2] = m->ctr.d2h_bytes;
+  out4[3] = 0;
+  if (m->has_model) {
+    DeviceGuard guard(m->device);
+    uint32_t nv = 0;
+    if (cudaMemcpy(&nv, m->d_nvalid.p, sizeof(nv), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      out4[3] = nv;
+    }
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API void * ndt2d_matcher_stream(ndt2d_matcher * m)
+{
+  return m ? static_cast<void *>(m->stream) : nullptr;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- filter
+struct ndt2d_filter
+{
+  std::mutex mu;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Counters ctr{0, 0, 0};
+  size_t min_particles = 0, max_particles = 0;
+  uint32_t n = 0;
+  int cur = 0;
+  DeviceBuffer d_particles[2], d_weights[2], d_stats, d_cdf, d_draws, d_first, d_canon, d_table,
+    d_new_n, d_uniforms, d_pose_tf, d_pts;
+  uint32_t table_size = 0;
+  PinnedBuffer h_stage;
+};
+
+namespace
+{
+
+FilterView filter_view(ndt2d_filter * f)
+{
+  FilterView v;
+  v.particles = f->d_particles[f->cur].as<double>();
+  v.weights = f->d_weights[f->cur].as<double>();
+  v.stats = f->d_stats.as<double>();
+  return v;
+}
+
+int filter_reserve(ndt2d_filter * f, size_t n)
+{
+  int rc = 0;
+  const size_t cap = std::max<size_t>(std::max(n, f->max_particles), 1);
+  for (int b = 0; b < 2 && !rc; ++b) {
+    rc = f->d_particles[b].ensure(cap * 3 * sizeof(double));
+    if (!rc) {rc = f->d_weights[b].ensure(cap * sizeof(double));}
+  }
+  if (!rc) {rc = f->d_cdf.ensure(cap * sizeof(double));}
+  if (!rc) {rc = f->d_draws.ensure(cap * sizeof(uint32_t));}
+  if (!rc) {rc = f->d_first.ensure(cap * sizeof(uint32_t));}
+  if (!rc) {rc = f->d_canon.ensure(cap * sizeof(uint32_t));}
+  if (!rc) {rc = f->d_pose_tf.ensure(cap * sizeof(double4));}
+  if (!rc) {rc = f->d_uniforms.ensure(cap * sizeof(double));}
+  uint32_t ts = 64;
+  while (ts < 2 * cap) {ts <<= 1;}
+  if (!rc) {rc = f->d_table.ensure(static_cast<size_t>(ts) * sizeof(uint32_t));}
+  f->table_size = ts;
+  if (!rc) {rc = f->h_stage.ensure(cap * 4 * sizeof(double) + 256);}
+  return rc;
+}
+
+// When the current buffers had to grow the contents are lost: callers that
+// need them re-upload.  Used only by set_particles (which overwrites anyway).
+
+}  // namespace
+
+extern "C" {
+
+NDT2D_API int ndt2d_filter_create(
+  size_t min_particles, size_t max_particles, int device, void * stream, ndt2d_filter ** out)
+{
+  if (!out || max_particles == 0 || max_particles >= (1u << 28) ||
+    min_particles >= (1u << 28))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (ndt2d_device_count() <= 0) {
+    snprintf(g_last_error, sizeof(g_last_error),
+      "no CUDA device visible: libndt2d_b200 has no CPU fallback");
+    return NDT2D_ERR_NO_DEVICE;
+  }
+  int dev = device;
+  if (dev < 0) {NDT2D_CUDA_TRY(cudaGetDevice(&dev));}
+  ndt2d_filter * f = new (std::nothrow) ndt2d_filter();
+  if (!f) {return NDT2D_ERR_INVALID;}
+  f->device = dev;
+  f->min_particles = min_particles;
+  f->max_particles = max_particles;
+  DeviceGuard guard(dev);
+  if (stream) {
+    f->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete f;
+      return NDT2D_ERR_CUDA;
+    }
+    f->own_stream = true;
+  }
+  int rc = filter_reserve(f, std::max(min_particles, max_particles));
+  if (!rc) {rc = f->d_stats.ensure(12 * sizeof(double));}
+  if (!rc) {rc = f->d_new_n.ensure(sizeof(uint32_t));}
+  if (rc) {
+    ndt2d_filter_destroy(f);
+    return rc;
+  }
+  // particle_filter.cpp:42-50: mean/cov zero, min_particles at the origin
+  cudaMemsetAsync(f->d_stats.p, 0, 12 * sizeof(double), f->stream);
+  f->n = static_cast<uint32_t>(min_particles);
+  if (f->n) {
+    double * h = f->h_stage.as<double>();
+    for (uint32_t i = 0; i < f->n; ++i) {h[i] = 1.0 / static_cast<double>(min_particles);}
+    cudaMemsetAsync(f->d_particles[0].p, 0, static_cast<size_t>(f->n) * 3 * sizeof(double),
+      f->stream);
+    cudaMemcpyAsync(f->d_weights[0].p, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->stream);
+    rc = ndt2d_launch_filter_stats(filter_view(f), f->n, f->stream, &f->ctr);
+  }
+  if (cudaStreamSynchronize(f->stream) != cudaSuccess) {rc = NDT2D_ERR_CUDA;}
+  if (rc) {
+    ndt2d_filter_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_destroy(ndt2d_filter * f)
+{
+  if (!f) {return NDT2D_OK;}
+  {
+    DeviceGuard guard(f->device);
+    if (f->stream) {cudaStreamSynchronize(f->stream);}
+    DeviceBuffer * bufs[] = {&f->d_particles[0], &f->d_particles[1], &f->d_weights[0],
+      &f->d_weights[1], &f->d_stats, &f->d_cdf, &f->d_draws, &f->d_first, &f->d_canon,
+      &f->d_table, &f->d_new_n, &f->d_uniforms, &f->d_pose_tf, &f->d_pts};
+    for (DeviceBuffer * b : bufs) {b->release();}
+    f->h_stage.release();
+    if (f->own_stream && f->stream) {cudaStreamDestroy(f->stream);}
+  }
+  delete f;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_set_particles(
+  ndt2d_filter * f, const double * particles3, const double * weights, size_t n)
+{
+  if (!f || (n && (!particles3 || !weights)) || n >= (1u << 28)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  int rc = filter_reserve(f, n);
+  if (rc) {return rc;}
+  f->n = static_cast<uint32_t>(n);
+  if (n) {
+    double * h = f->h_stage.as<double>();
+    memcpy(h, particles3, n * 3 * sizeof(double));
+    memcpy(h + 3 * n, weights, n * sizeof(double));
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_particles[f->cur].p, h, n * 3 * sizeof(double),
+      cudaMemcpyHostToDevice, f->stream));
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_weights[f->cur].p, h + 3 * n, n * sizeof(double),
+      cudaMemcpyHostToDevice, f->stream));
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+    f->ctr.h2d_bytes += n * 4 * sizeof(double);
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_size(ndt2d_filter * f, size_t * n)
+{
+  if (!f || !n) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  *n = f->n;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_get_particles(ndt2d_filter * f, double * particles3, double * weights)
+{
+  if (!f) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  const size_t n = f->n;
+  if (n == 0) {return NDT2D_OK;}
+  double * h = f->h_stage.as<double>();
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(h, f->d_particles[f->cur].p, n * 3 * sizeof(double),
+    cudaMemcpyDeviceToHost, f->stream));
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(h + 3 * n, f->d_weights[f->cur].p, n * sizeof(double),
+    cudaMemcpyDeviceToHost, f->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->ctr.d2h_bytes += n * 4 * sizeof(double);
+  if (particles3) {memcpy(particles3, h, n * 3 * sizeof(double));}
+  if (weights) {memcpy(weights, h + 3 * n, n * sizeof(double));}
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_init(
+  ndt2d_filter * f, double x, double y, double theta, double sigma_x, double sigma_y,
+  double sigma_theta, uint64_t seed)
+{
+  if (!f) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  int rc = ndt2d_launch_filter_init(filter_view(f), f->n, x, y, theta, sigma_x, sigma_y,
+      sigma_theta, seed, f->stream, &f->ctr);
+  if (!rc) {rc = ndt2d_launch_filter_stats(filter_view(f), f->n, f->stream, &f->ctr);}
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_update(
+  ndt2d_filter * f, double dx, double dy, double dth, const double * alphas5, uint64_t seed)
+{
+  if (!f || !alphas5) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  // MotionModel::sample, scalar part (motion_model.cpp:48-66); angle helpers
+  // follow the ROS 2 `angles` package.
+  auto norm = [](double a) {
+      const double r = fmod(a + M_PI, 2.0 * M_PI);
+      return (r <= 0.0) ? r + M_PI : r - M_PI;
+    };
+  auto diff = [&](double from, double to) {return norm(to - from);};
+  const double a1 = alphas5[0], a2 = alphas5[1], a3 = alphas5[2], a4 = alphas5[3];
+  const double trans = std::hypot(dx, dy);
+  const double rot1 = (trans > 0.01) ? atan2(dy, dx) : 0.0;
+  const double rot2 = diff(rot1, dth);
+  const double rot1_ = std::min(std::fabs(diff(rot1, 0.0)), std::fabs(diff(rot1, M_PI)));
+  const double rot2_ = std::min(std::fabs(diff(rot2, 0.0)), std::fabs(diff(rot2, M_PI)));
+  const double s_rot1 = std::sqrt(a1 * rot1_ * rot1_ + a2 * trans * trans);
+  const double s_trans = std::sqrt(a3 * trans * trans + a4 * rot1_ * rot1_ + a4 * rot2_ * rot2_);
+  const double s_rot2 = std::sqrt(a1 * rot2_ * rot2_ + a2 * trans * trans);
+  int rc = ndt2d_launch_filter_motion(filter_view(f), f->n, rot1, trans, rot2, s_rot1, s_trans,
+      s_rot2, seed, f->stream, &f->ctr);
+  if (!rc) {rc = ndt2d_launch_filter_stats(filter_view(f), f->n, f->stream, &f->ctr);}
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_measure(
+  ndt2d_filter * f, ndt2d_matcher * m, const double * pts_xy, size_t npts)
+{
+  if (!f || !m || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  std::lock_guard<std::mutex> lock_m(m->mu);
+  if (f->device != m->device) {return NDT2D_ERR_INVALID;}
+  DeviceGuard guard(f->device);
+  const size_t n = f->n;
+  cudaStream_t st = f->stream;
+  if (!m->has_model) {
+    // scorePoints returns 0.0 for every particle (scan_matcher_ndt.cpp:159);
+    // updateStatistics then divides by a zero sum, as the reference would.
+    if (n) {
+      NDT2D_CUDA_TRY(cudaMemsetAsync(f->d_weights[f->cur].p, 0, n * sizeof(double), st));
+    }
+  } else if (n) {
+    // make sure the model build (matcher stream) is complete
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const size_t n_use = subsample_count(m, npts);
+    int rc = f->d_pts.ensure(n_use ? n_use * sizeof(double2) : 16);
+    if (!rc) {rc = f->h_stage.ensure((n * 4 + n_use * 2) * sizeof(double) + 256);}
+    if (rc) {return rc;}
+    // particle poses -> host, cos/sin by the host libm (toEigen: conversions.hpp:64-68)
+    double * h_part = f->h_stage.as<double>();
+    double4 * h_tf = reinterpret_cast<double4 *>(h_part);  // written after the read below
+    std::vector<double> part(n * 3);
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(h_part, f->d_particles[f->cur].p, n * 3 * sizeof(double),
+      cudaMemcpyDeviceToHost, st));
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(part.data(), h_part, n * 3 * sizeof(double));
+    f->ctr.d2h_bytes += n * 3 * sizeof(double);
+    for (size_t i = 0; i < n; ++i) {
+      h_tf[i] = make_double4(part[3 * i], part[3 * i + 1], cos(part[3 * i + 2]),
+          sin(part[3 * i + 2]));
+    }
+    double * h_pts = reinterpret_cast<double *>(h_tf + n);
+    if (n_use) {subsample_points(pts_xy, npts, n_use, h_pts);}
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_pose_tf.p, h_tf, n * sizeof(double4),
+      cudaMemcpyHostToDevice, st));
+    if (n_use) {
+      NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_pts.p, h_pts, n_use * sizeof(double2),
+        cudaMemcpyHostToDevice, st));
+    }
+    f->ctr.h2d_bytes += n * sizeof(double4) + n_use * sizeof(double2);
+    rc = ndt2d_launch_score_poses(model_view(m), f->d_pts.as<double2>(),
+        static_cast<uint32_t>(n_use), f->d_pose_tf.as<double4>(), static_cast<uint32_t>(n), -1.0,
+        1, f->d_weights[f->cur].as<double>(), st, &f->ctr);
+    if (rc) {return rc;}
+  }
+  int rc = ndt2d_launch_filter_stats(filter_view(f), f->n, st, &f->ctr);
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_resample(
+  ndt2d_filter * f, double kld_err, double kld_z, const double * uniforms, size_t n_uniforms,
+  uint64_t seed)
+{
+  if (!f) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  if (uniforms && n_uniforms < f->max_particles) {return NDT2D_ERR_INVALID;}
+  DeviceGuard guard(f->device);
+  cudaStream_t st = f->stream;
+  const double * d_u = nullptr;
+  if (uniforms) {
+    int rc = f->h_stage.ensure(f->max_particles * sizeof(double));
+    if (rc) {return rc;}
+    memcpy(f->h_stage.p, uniforms, f->max_particles * sizeof(double));
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_uniforms.p, f->h_stage.p,
+      f->max_particles * sizeof(double), cudaMemcpyHostToDevice, st));
+    f->ctr.h2d_bytes += f->max_particles * sizeof(double);
+    d_u = f->d_uniforms.as<double>();
+  }
+  const int nxt = f->cur ^ 1;
+  int rc = ndt2d_launch_filter_resample(filter_view(f), f->n,
+      static_cast<uint32_t>(f->min_particles), static_cast<uint32_t>(f->max_particles), kld_err,
+      kld_z, d_u, seed, f->d_cdf.as<double>(), f->d_particles[nxt].as<double>(),
+      f->d_weights[nxt].as<double>(), f->d_draws.as<uint32_t>(), f->d_first.as<uint32_t>(),
+      f->d_canon.as<uint32_t>(), f->d_table.as<uint32_t>(), f->table_size,
+      f->d_new_n.as<uint32_t>(), st, &f->ctr);
+  if (rc) {return rc;}
+  uint32_t new_n = 0;
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(&new_n, f->d_new_n.p, sizeof(new_n), cudaMemcpyDeviceToHost, st));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  f->ctr.d2h_bytes += sizeof(new_n);
+  f->cur = nxt;
+  f->n = new_n;
+  rc = ndt2d_launch_filter_stats(filter_view(f), f->n, st, &f->ctr);  // :136
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_stats(ndt2d_filter * f, double * mean3, double * cov9)
+{
+  if (!f) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  double h[12];
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(h, f->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, f->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->ctr.d2h_bytes += sizeof(h);
+  if (mean3) {memcpy(mean3, h, 3 * sizeof(double));}
+  if (cov9) {memcpy(cov9, h + 3, 9 * sizeof(double));}
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_set_cov(ndt2d_filter * f, const double * cov9)
+{
+  if (!f || !cov9) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(f->d_stats.as<double>() + 3, cov9, 9 * sizeof(double),
+    cudaMemcpyHostToDevice, f->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_filter_last_draws(ndt2d_filter * f, uint64_t * out)
+{
+  if (!f || !out) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(f->mu);
+  DeviceGuard guard(f->device);
+  const size_t n = f->n;
+  if (n == 0) {return NDT2D_OK;}
+  std::vector<uint32_t> h(n);
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(h.data(), f->d_draws.p, n * sizeof(uint32_t),
+    cudaMemcpyDeviceToHost, f->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  for (size_t i = 0; i < n; ++i) {out[i] = h[i];}
+  return NDT2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,531 @@
+// build.cu -- NDT model construction on the device (kernels K1..K3).
+//
+// Replaces NDT::addScan / Cell::addPoint / NDT::compute / Cell::compute
+// (ndt_model.cpp:50-103, 132-160) with a sort-by-cell-key segmented reduction:
+//
+//   K1  transform_key   every map point -> world coordinates + cell key
+//   K2  radix sort      STABLE LSD sort of (key, point index), 8-bit digits
+//   K3a segment_count   per occupied cell: point count, occupancy bit if n >= 5
+//       scan            rank prefix over the occupancy words
+//   K3b segment_moments per occupied cell with n >= 5: the reference's running
+//                       mean / second-moment recurrence replayed in order,
+//                       covariance, eigenvalue clamp, information -> packed record
+//
+// Because the sort is stable, the points of one cell stay in (scan, point)
+// order, so the sequential recurrence of Cell::addPoint is reproduced term by
+// term: cell statistics are bit-identical to a sequential CPU build.  No float
+// atomics anywhere (only an integer atomicOr for the occupancy bit).
+//
+// All arithmetic that decides a cell index or enters the recurrence uses the
+// round-to-nearest intrinsics (__dadd_rn, __dmul_rn, __ddiv_rn), which nvcc
+// never contracts into FMAs -- the reference's x86-64 build has none either.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ndt2d_internal.h"
+
+namespace
+{
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per block
+constexpr int kSortWarps = kSortThreads / 32;
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 8192 values per block
+
+constexpr double kNegHalfLog2e = -0.72134752044448170368;  // -0.5 * log2(e)
+
+// ------------------------------------------------------------------ K1
+// NDT::getIndex (ndt_model.cpp:203-218); returns n_cells for "outside".
+__device__ __forceinline__ uint32_t cell_key(const GridDesc & g, double x, double y)
+{
+  if (x < g.origin_x || y < g.origin_y) {
+    return g.n_cells;
+  }
+  const uint32_t gx = __double2uint_rz(__ddiv_rn(__dsub_rn(x, g.origin_x), g.cell_size));
+  const uint32_t gy = __double2uint_rz(__ddiv_rn(__dsub_rn(y, g.origin_y), g.cell_size));
+  if (gx >= g.size_x || gy >= g.size_y) {
+    return g.n_cells;
+  }
+  return gy * g.size_x + gx;
+}
+
+// NDT::addScan (ndt_model.cpp:132-152): p = pose; p += R(theta) * point.
+__global__ void __launch_bounds__(128) transform_key_kernel(
+  GridDesc g, const double4 * __restrict__ scan_tf, const uint64_t * __restrict__ offsets,
+  uint32_t n_scans, const double2 * __restrict__ pts, double * __restrict__ wx,
+  double * __restrict__ wy, uint32_t * __restrict__ key, uint32_t * __restrict__ val)
+{
+  for (uint32_t s = blockIdx.x; s < n_scans; s += gridDim.x) {
+    const double4 tf = scan_tf[s];  // x, y, cos, sin
+    const uint64_t lo = offsets[s], hi = offsets[s + 1];
+    for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+      const double2 pt = pts[p];
+      const double X =
+        __dadd_rn(tf.x, __dsub_rn(__dmul_rn(pt.x, tf.z), __dmul_rn(pt.y, tf.w)));
+      const double Y =
+        __dadd_rn(tf.y, __dadd_rn(__dmul_rn(pt.x, tf.w), __dmul_rn(pt.y, tf.z)));
+      wx[p] = X;
+      wy[p] = Y;
+      key[p] = cell_key(g, X, Y);
+      val[p] = static_cast<uint32_t>(p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ scan
+// Exclusive scan of uint32 values, three phases for arrays above one tile.
+// MODE 0: plain array in place.  MODE 1: uint2 occupancy words, in = popc(.x),
+// out -> .y.
+template<int MODE>
+__device__ __forceinline__ uint32_t scan_load(const void * data, size_t i)
+{
+  if (MODE == 0) {
+    return static_cast<const uint32_t *>(data)[i];
+  }
+  return __popc(static_cast<const uint2 *>(data)[i].x);
+}
+template<int MODE>
+__device__ __forceinline__ void scan_store(void * data, size_t i, uint32_t v)
+{
+  if (MODE == 0) {
+    static_cast<uint32_t *>(data)[i] = v;
+  } else {
+    static_cast<uint2 *>(data)[i].y = v;
+  }
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t * total)
+{
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) {incl += t;}
+  }
+  if (lane == 31) {warp_sums[warp] = incl;}
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t ws = warp_sums[lane];
+    uint32_t wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) {wi += t;}
+    }
+    warp_sums[lane] = wi - ws;  // exclusive warp prefix
+    if (lane == 31) {*total = wi;}
+  }
+  __syncthreads();
+  const uint32_t r = warp_sums[warp] + incl - v;
+  __syncthreads();
+  return r;
+}
+
+template<int MODE>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(
+  const void * data, size_t n, uint32_t * block_sums)
+{
+  __shared__ uint32_t total;
+  const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) {s += scan_load<MODE>(data, base + k);}
+  }
+  block_exclusive_scan_1024(s, &total);
+  if (threadIdx.x == 0) {block_sums[blockIdx.x] = total;}
+}
+
+// single block: exclusive scan of up to kScanTile block sums, in place
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(uint32_t * sums, uint32_t n)
+{
+  __shared__ uint32_t total;
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) {carry_s = 0;}
+  __syncthreads();
+  for (uint32_t start = 0; start < n; start += kScanTile) {
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+    const uint32_t base = start + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      v[k] = (base + k < n) ? sums[base + k] : 0u;
+      s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan_1024(s, &total) + carry_s;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (base + k < n) {sums[base + k] = ex;}
+      ex += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {carry_s += total;}
+    __syncthreads();
+  }
+}
+
+template<int MODE>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(
+  void * data, size_t n, const uint32_t * block_sums)
+{
+  __shared__ uint32_t total;
+  const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? scan_load<MODE>(data, base + k) : 0u;
+    s += v[k];
+  }
+  uint32_t ex = block_exclusive_scan_1024(s, &total) + (block_sums ? block_sums[blockIdx.x] : 0u);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) {scan_store<MODE>(data, base + k, ex);}
+    ex += v[k];
+  }
+}
+
+template<int MODE>
+int launch_scan(void * d_data, size_t n, uint32_t * d_tmp, cudaStream_t stream, Counters * ctr)
+{
+  if (n == 0) {return NDT2D_OK;}
+  const uint32_t nblk = static_cast<uint32_t>((n + kScanTile - 1) / kScanTile);
+  if (nblk == 1) {
+    scan_apply_kernel<MODE><<<1, kScanThreads, 0, stream>>>(d_data, n, nullptr);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
+  scan_reduce_kernel<MODE><<<nblk, kScanThreads, 0, stream>>>(d_data, n, d_tmp);
+  NDT2D_LAUNCH_CHECK(ctr);
+  scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(d_tmp, nblk);
+  NDT2D_LAUNCH_CHECK(ctr);
+  scan_apply_kernel<MODE><<<nblk, kScanThreads, 0, stream>>>(d_data, n, d_tmp);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}
+
+// ------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(
+  const uint32_t * __restrict__ keys, size_t n, int shift, uint32_t * __restrict__ hist,
+  uint32_t nblk)
+{
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t tile = static_cast<size_t>(blockIdx.x) * kSortTile;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const size_t i = tile + static_cast<size_t>(k) * kSortThreads + threadIdx.x;
+    if (i < n) {
+      atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  hist[static_cast<size_t>(threadIdx.x) * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// Stable scatter.  Warp w owns the contiguous sub-tile
+// [tile + w*32*ITEMS, tile + (w+1)*32*ITEMS) and walks it in element order,
+// so (block, warp, step, lane) order == input order.
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
+  const uint32_t * __restrict__ keys_in, const uint32_t * __restrict__ vals_in, size_t n,
+  int shift, const uint32_t * __restrict__ hist_scanned, uint32_t nblk,
+  uint32_t * __restrict__ keys_out, uint32_t * __restrict__ vals_out)
+{
+  __shared__ uint32_t cnt[kSortWarps][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) {
+    (&cnt[0][0])[i] = 0;
+  }
+  __syncthreads();
+
+  const size_t sub = static_cast<size_t>(blockIdx.x) * kSortTile +
+    static_cast<size_t>(warp) * 32 * kSortItems;
+  uint32_t k[kSortItems], v[kSortItems], local[kSortItems];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int s = 0; s < kSortItems; ++s) {
+    const size_t i = sub + static_cast<size_t>(s) * 32 + lane;
+    const bool active = i < n;
+    k[s] = active ? keys_in[i] : 0u;
+    v[s] = active ? vals_in[i] : 0u;
+    // inactive lanes get a private pseudo digit so they match nobody
+    const uint32_t d = active ? ((k[s] >> shift) & 255u) : (256u + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t r = __popc(peers & lt_mask);
+    uint32_t base = 0;
+    if (active) {base = cnt[warp][d];}
+    __syncwarp();
+    if (active && r == 0) {cnt[warp][d] = base + __popc(peers);}
+    __syncwarp();
+    local[s] = base + r;
+  }
+  __syncthreads();
+  {
+    // thread d: exclusive prefix over warps + global base of (digit d, this block)
+    const int d = threadIdx.x;
+    uint32_t run = hist_scanned[static_cast<size_t>(d) * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t t = cnt[w][d];
+      cnt[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < kSortItems; ++s) {
+    const size_t i = sub + static_cast<size_t>(s) * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (k[s] >> shift) & 255u;
+      const uint32_t pos = cnt[warp][d] + local[s];
+      keys_out[pos] = k[s];
+      vals_out[pos] = v[s];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K3
+__device__ __forceinline__ uint32_t padded_index(const GridDesc & g, uint32_t key)
+{
+  const uint32_t gy = key / g.size_x, gx = key - gy * g.size_x;
+  return (gy + 1) * g.pitch + gx + 1;
+}
+
+// K3a: heads count their segment; cells with n >= 5 get their occupancy bit.
+__global__ void __launch_bounds__(256) segment_count_kernel(
+  GridDesc g, const uint32_t * __restrict__ key, size_t n, uint32_t * __restrict__ seglen,
+  uint2 * __restrict__ occ)
+{
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) {return;}
+  const uint32_t k = key[i];
+  if (k >= g.n_cells) {return;}
+  if (i > 0 && key[i - 1] == k) {return;}
+  size_t j = i + 1;
+  while (j < n && key[j] == k) {++j;}
+  const uint32_t len = static_cast<uint32_t>(j - i);
+  seglen[i] = len;
+  if (len >= 5) {
+    const uint32_t p = padded_index(g, k);
+    atomicOr(&occ[p >> 5].x, 1u << (p & 31u));
+  }
+}
+
+struct CellStats
+{
+  double n, mean[2], corr[3] /*xx, xy, yy*/, cov[3], info[4];
+};
+
+// Cell::addPoint recurrence (ndt_model.cpp:50-63), one point.
+__device__ __forceinline__ void stats_add(CellStats & c, double x, double y)
+{
+  const double n = c.n, n1 = __dadd_rn(n, 1.0);
+  c.mean[0] = __ddiv_rn(__dadd_rn(__dmul_rn(c.mean[0], n), x), n1);
+  c.mean[1] = __ddiv_rn(__dadd_rn(__dmul_rn(c.mean[1], n), y), n1);
+  c.corr[0] = __ddiv_rn(__dadd_rn(__dmul_rn(c.corr[0], n), __dmul_rn(x, x)), n1);
+  c.corr[1] = __ddiv_rn(__dadd_rn(__dmul_rn(c.corr[1], n), __dmul_rn(x, y)), n1);
+  c.corr[2] = __ddiv_rn(__dadd_rn(__dmul_rn(c.corr[2], n), __dmul_rn(y, y)), n1);
+  c.n = n1;
+}
+
+// Cell::compute (ndt_model.cpp:65-103) for n >= 3.
+__device__ __forceinline__ void stats_finalize(CellStats & c)
+{
+  const double scale = __ddiv_rn(c.n, __dsub_rn(c.n, 1.0));
+  c.cov[0] = __dmul_rn(__dsub_rn(c.corr[0], __dmul_rn(c.mean[0], c.mean[0])), scale);
+  c.cov[1] = __dmul_rn(__dsub_rn(c.corr[1], __dmul_rn(c.mean[0], c.mean[1])), scale);
+  c.cov[2] = __dmul_rn(__dsub_rn(c.corr[2], __dmul_rn(c.mean[1], c.mean[1])), scale);
+  // eigenvalues of the symmetric 2x2 (closed form; the reference asks Eigen's
+  // EigenSolver, ndt_model.cpp:84-87 -- only the clamp decision depends on it)
+  const double a = c.cov[0], b = c.cov[1], d = c.cov[2];
+  const double mid = __dmul_rn(0.5, __dadd_rn(a, d));
+  const double half = __dmul_rn(0.5, __dsub_rn(a, d));
+  const double rad = __dsqrt_rn(__dadd_rn(__dmul_rn(half, half), __dmul_rn(b, b)));
+  double small = __dsub_rn(mid, rad), large = __dadd_rn(mid, rad);
+  if (small > large) {
+    const double t = small;
+    small = large;
+    large = t;
+  }
+  if (small < __dmul_rn(0.001, large)) {
+    const double det = __dmul_rn(__dmul_rn(0.001, large), large);
+    c.info[0] = __ddiv_rn(d, det);
+    c.info[1] = __ddiv_rn(-b, det);
+    c.info[2] = __ddiv_rn(-b, det);
+    c.info[3] = __ddiv_rn(a, det);
+  } else {
+    const double invdet = __ddiv_rn(1.0, __dsub_rn(__dmul_rn(a, d), __dmul_rn(b, b)));
+    c.info[0] = __dmul_rn(d, invdet);
+    c.info[1] = __dmul_rn(-b, invdet);
+    c.info[2] = __dmul_rn(-b, invdet);
+    c.info[3] = __dmul_rn(a, invdet);
+  }
+}
+
+__device__ __forceinline__ void stats_walk(
+  CellStats & c, const uint32_t * __restrict__ val, const double * __restrict__ wx,
+  const double * __restrict__ wy, size_t i, uint32_t len)
+{
+  c.n = 0.0;
+  c.mean[0] = c.mean[1] = 0.0;
+  c.corr[0] = c.corr[1] = c.corr[2] = 0.0;
+  for (uint32_t j = 0; j < len; ++j) {
+    const uint32_t p = val[i + j];
+    stats_add(c, wx[p], wy[p]);
+  }
+}
+
+// K3b: heads of cells with n >= 5 replay the recurrence and emit the record.
+__global__ void __launch_bounds__(128) segment_moments_kernel(
+  GridDesc g, const uint32_t * __restrict__ key, const uint32_t * __restrict__ val, size_t n,
+  const uint32_t * __restrict__ seglen, const double * __restrict__ wx,
+  const double * __restrict__ wy, const uint2 * __restrict__ occ, double * __restrict__ rec,
+  uint32_t rec_cap, uint32_t * __restrict__ n_valid)
+{
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    // total number of occupied cells = prefix + popc of the last word
+    const uint2 last = occ[g.n_words - 1];
+    *n_valid = last.y + __popc(last.x);
+  }
+  if (i >= n) {return;}
+  const uint32_t k = key[i];
+  if (k >= g.n_cells) {return;}
+  if (i > 0 && key[i - 1] == k) {return;}
+  const uint32_t len = seglen[i];
+  if (len < 5) {return;}
+  CellStats c;
+  stats_walk(c, val, wx, wy, i, len);
+  stats_finalize(c);
+  const uint32_t p = padded_index(g, k);
+  const uint2 w = occ[p >> 5];
+  const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
+  if (rank >= rec_cap) {return;}
+  double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
+  r[0] = c.mean[0];
+  r[1] = c.mean[1];
+  r[2] = kNegHalfLog2e * c.info[0];
+  r[3] = kNegHalfLog2e * (c.info[1] + c.info[2]);
+  r[4] = kNegHalfLog2e * c.info[3];
+  r[5] = c.n;
+}
+
+// Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.
+__global__ void __launch_bounds__(128) segment_dump_kernel(
+  GridDesc g, const uint32_t * __restrict__ key, const uint32_t * __restrict__ val, size_t n,
+  const uint32_t * __restrict__ seglen, const double * __restrict__ wx,
+  const double * __restrict__ wy, double * __restrict__ out)
+{
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) {return;}
+  const uint32_t k = key[i];
+  if (k >= g.n_cells) {return;}
+  if (i > 0 && key[i - 1] == k) {return;}
+  const uint32_t len = seglen[i];
+  CellStats c;
+  stats_walk(c, val, wx, wy, i, len);
+  double * o = out + static_cast<size_t>(k) * 16;
+  o[1] = c.n;
+  o[2] = c.mean[0];
+  o[3] = c.mean[1];
+  o[8] = c.corr[0];
+  o[9] = c.corr[1];
+  o[10] = 0.0;  // correlation(1,0) is never written (ndt_model.cpp:55)
+  o[11] = c.corr[2];
+  if (len >= 3) {
+    stats_finalize(c);
+    o[0] = 1.0;
+    o[4] = c.cov[0];
+    o[5] = c.cov[1];
+    o[6] = c.cov[1];
+    o[7] = c.cov[2];
+    o[12] = c.info[0];
+    o[13] = c.info[1];
+    o[14] = c.info[2];
+    o[15] = c.info[3];
+  }
+}
+
+int bits_needed(uint32_t max_value)
+{
+  int b = 1;
+  while (b < 32 && (max_value >> b) != 0u) {++b;}
+  return b;
+}
+
+}  // namespace
+
+int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
+  cudaStream_t stream, Counters * ctr)
+{
+  return launch_scan<0>(d_data, n, d_tmp, stream, ctr);
+}
+
+int ndt2d_launch_build(
+  const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
+  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, double * d_rec,
+  uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr, int * sorted_buf)
+{
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, static_cast<size_t>(g.n_words) * sizeof(uint2), stream));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, sizeof(uint32_t), stream));
+  int cur = 0;
+  if (n_points > 0) {
+    const uint32_t grid = static_cast<uint32_t>(n_scans < 65535u * 8u ? n_scans : 65535u * 8u);
+    transform_key_kernel<<<grid, 128, 0, stream>>>(
+      g, d_scan_tf, d_offsets, static_cast<uint32_t>(n_scans), d_pts, s.wx, s.wy, s.key[0],
+      s.val[0]);
+    NDT2D_LAUNCH_CHECK(ctr);
+
+    const uint32_t nblk = static_cast<uint32_t>((n_points + kSortTile - 1) / kSortTile);
+    const int bits = bits_needed(g.n_cells);
+    for (int shift = 0; shift < bits; shift += 8) {
+      radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(
+        s.key[cur], n_points, shift, s.hist, nblk);
+      NDT2D_LAUNCH_CHECK(ctr);
+      const int rc = launch_scan<0>(s.hist, static_cast<size_t>(256) * nblk, s.scan_tmp, stream, ctr);
+      if (rc != NDT2D_OK) {return rc;}
+      radix_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(
+        s.key[cur], s.val[cur], n_points, shift, s.hist, nblk, s.key[cur ^ 1], s.val[cur ^ 1]);
+      NDT2D_LAUNCH_CHECK(ctr);
+      cur ^= 1;
+    }
+    const uint32_t nb = static_cast<uint32_t>((n_points + 255) / 256);
+    segment_count_kernel<<<nb, 256, 0, stream>>>(g, s.key[cur], n_points, s.seglen, d_occ);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
+  {
+    const int rc = launch_scan<1>(d_occ, g.n_words, s.scan_tmp, stream, ctr);
+    if (rc != NDT2D_OK) {return rc;}
+  }
+  if (n_points > 0) {
+    const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);
+    segment_moments_kernel<<<nb, 128, 0, stream>>>(
+      g, s.key[cur], s.val[cur], n_points, s.seglen, s.wx, s.wy, d_occ, d_rec, rec_cap,
+      d_n_valid);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
+  *sorted_buf = cur;
+  return NDT2D_OK;
+}
+
+int ndt2d_launch_dump_cells(
+  const GridDesc & g, const BuildScratch & s, int sorted_buf, size_t n_points, double * d_out,
+  cudaStream_t stream, Counters * ctr)
+{
+  NDT2D_CUDA_TRY(
+    cudaMemsetAsync(d_out, 0, static_cast<size_t>(g.n_cells) * 16 * sizeof(double), stream));
+  if (n_points > 0) {
+    const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);
+    segment_dump_kernel<<<nb, 128, 0, stream>>>(
+      g, s.key[sorted_buf], s.val[sorted_buf], n_points, s.seglen, s.wx, s.wy, d_out);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
+  return NDT2D_OK;
+}

@@ -1,0 +1,171 @@
+// ndt2d_internal.h -- shared declarations of the libndt2d_b200 translation units.
+#ifndef NDT2D_INTERNAL_H_
+#define NDT2D_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ndt2d_b200.h"
+
+// Description of one NDT grid, passed by value to kernels.
+//
+// The reference's grid (ndt_model.cpp:118-126) is size_x * size_y cells with
+// origin (origin_x, origin_y).  On the device every lookup goes through a
+// PADDED grid of (size_x + 2) * (size_y + 2) cells: padded coordinate
+// ex = 0 means "x < origin_x" and ex = size_x + 1 means "grid_x >= size_x",
+// the two ways NDT::getIndex (ndt_model.cpp:203-218) returns -1.  Border cells
+// are never occupied, so out-of-map points need no special case.
+struct GridDesc
+{
+  double origin_x, origin_y, cell_size;
+  uint32_t size_x, size_y;  // reference cells per axis
+  uint32_t pitch;           // size_x + 2
+  uint32_t n_cells;         // size_x * size_y
+  uint32_t n_padded;        // (size_x + 2) * (size_y + 2)
+  uint32_t n_words;         // ceil(n_padded / 32)
+};
+
+// Device-resident model of one matcher.
+//   occ[w]   .x = occupancy bits of padded cells 32w..32w+31 (cell has n >= 5,
+//                 the only cells Cell::score does not return 0 for,
+//                 ndt_model.cpp:107-111)
+//            .y = number of occupied cells before word w  (rank prefix)
+//   rec[r*6] = mean_x, mean_y, a, b, c, n   of the r-th occupied cell, where
+//              (a, b, c) = -0.5*log2(e) * (I00, I01, I11): the exponent of
+//              Cell::score (ndt_model.cpp:113-115) in base 2
+//   thr_x[k] = smallest double x whose reference grid_x is >= k  (k=0: origin)
+struct ModelView
+{
+  GridDesc g;
+  const uint2 * occ;
+  const double * rec;
+  const double * thr_x;  // size_x + 1 entries
+  const double * thr_y;  // size_y + 1 entries
+  uint32_t n_valid_cap;
+};
+
+#define NDT2D_REC_DOUBLES 6
+
+// One staged query scan + candidate lattice.
+struct SearchView
+{
+  const double2 * pts;   // n subsampled sensor-frame points
+  const double2 * trig;  // n_ang (cos, sin) of pose.theta + dth
+  const double * dth;    // n_ang
+  const double * dlin;   // n_lin
+  double pose_x, pose_y;
+  uint32_t n_pts, n_ang, n_lin;
+};
+
+// Per-block partial of the search (8 doubles):
+//   [0] best score  [1] best global index (as double; < 2^53)
+//   [2] S  [3] Sx  [4] Sy  [5] Sxx  [6] Sxy  [7] Syy     (sums over the block's
+//   candidates of score * {1, dx, dy, dx^2, dx*dy, dy^2}); [8] = dth of the block
+#define NDT2D_BLOCK_PARTIAL 9
+
+struct Counters
+{
+  uint64_t launches, h2d_bytes, d2h_bytes;
+};
+
+// ---- build.cu -----------------------------------------------------------
+struct BuildScratch
+{
+  // all device pointers, capacities in elements
+  double * wx, * wy;        // world coordinates per map point
+  uint32_t * key[2];        // ping-pong sort keys (cell index, n_cells = outside)
+  uint32_t * val[2];        // ping-pong values (point index)
+  uint32_t * seglen;        // per sorted position: segment length (heads only)
+  uint32_t * hist;          // radix histogram [256][n_blocks]
+  uint32_t * scan_tmp;      // scratch of the scan kernel
+  size_t cap_points, cap_hist;
+};
+
+// Launches K1..K3 on `stream`: transform + key, stable radix sort by cell key,
+// per-cell sequential moments, occupancy bitmap + rank prefix, packed records.
+// d_scan_tf: per scan {x, y, cos, sin}; d_offsets: n_scans + 1 point offsets;
+// d_pts: sensor-frame points.  Returns the index (0/1) of the sorted buffers.
+int ndt2d_launch_build(
+  const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
+  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, double * d_rec,
+  uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr, int * sorted_buf);
+
+// Debug/parity: dense dump (16 doubles per reference cell) from the sorted
+// buffers of the last build.
+int ndt2d_launch_dump_cells(
+  const GridDesc & g, const BuildScratch & s, int sorted_buf, size_t n_points, double * d_out,
+  cudaStream_t stream, Counters * ctr);
+
+// Generic exclusive scan of n uint32 (in place), single launch sequence.
+int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
+  cudaStream_t stream, Counters * ctr);
+
+// ---- search.cu ----------------------------------------------------------
+// Search theta slices [theta_begin, theta_end); writes the 32-double record
+// (partial + finished outputs, see ndt2d_launch_combine) to d_partial32.  d_block_partials: scratch, >= capacity returned by
+// ndt2d_search_scratch_doubles().  d_scores (optional): per-candidate scores.
+size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, int variant);
+int ndt2d_launch_search(
+  const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
+  int variant, double * d_block_partials, double * d_partial32, double * d_scores,
+  cudaStream_t stream, Counters * ctr);
+
+// Combine n 16-double partial records (device) into one 32-double record
+// (device): [0..15] partial, [16..18] delta, [19] delta_written,
+// [20..28] covariance, [29] best / n.
+int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,
+  const double * d_dlin, uint32_t n_lin, double * d_out32, cudaStream_t stream, Counters * ctr);
+
+// Batched pose scoring: d_pose_tf[p] = {x, y, cos, sin}; out[p] = scorePoints.
+// sign = -1 / normalise = 1 reproduces scorePoints (scan_matcher_ndt.cpp:156-178);
+// sign = +1 / normalise = 0 reproduces NDT::likelihood(ScanPtr) (ndt_model.cpp:189-201).
+int ndt2d_launch_score_poses(
+  const ModelView & mv, const double2 * d_pts, uint32_t n_pts, const double4 * d_pose_tf,
+  uint32_t n_poses, double sign, int normalise, double * d_out, cudaStream_t stream,
+  Counters * ctr);
+
+// ---- filter.cu ----------------------------------------------------------
+struct FilterView
+{
+  double * particles;  // 3 * cap
+  double * weights;    // cap
+  double * stats;      // [0..2] mean, [3..11] cov (row-major), persistent
+};
+int ndt2d_launch_pose_tf(const double * d_particles, uint32_t n, double4 * d_pose_tf,
+  cudaStream_t stream, Counters * ctr);
+int ndt2d_launch_filter_stats(FilterView f, uint32_t n, cudaStream_t stream, Counters * ctr);
+int ndt2d_launch_filter_resample(
+  FilterView f, uint32_t n, uint32_t min_particles, uint32_t max_particles, double kld_err,
+  double kld_z, const double * d_uniforms, uint64_t seed, double * d_cdf, double * d_new_particles,
+  double * d_new_weights, uint32_t * d_draws, uint32_t * d_first, uint32_t * d_canon,
+  uint32_t * d_table, uint32_t table_size, uint32_t * d_new_n, cudaStream_t stream,
+  Counters * ctr);
+int ndt2d_launch_filter_init(FilterView f, uint32_t n, double x, double y, double th, double sx,
+  double sy, double sth, uint64_t seed, cudaStream_t stream, Counters * ctr);
+int ndt2d_launch_filter_motion(FilterView f, uint32_t n, double rot1, double trans, double rot2,
+  double s_rot1, double s_trans, double s_rot2, uint64_t seed, cudaStream_t stream,
+  Counters * ctr);
+
+// ---- error plumbing -----------------------------------------------------
+void ndt2d_set_error(const char * what, cudaError_t e, const char * file, int line);
+
+#define NDT2D_CUDA_TRY(expr)                                        \
+  do {                                                              \
+    cudaError_t e__ = (expr);                                       \
+    if (e__ != cudaSuccess) {                                       \
+      ndt2d_set_error(#expr, e__, __FILE__, __LINE__);              \
+      return NDT2D_ERR_CUDA;                                        \
+    }                                                               \
+  } while (0)
+
+#define NDT2D_LAUNCH_CHECK(ctr)                                     \
+  do {                                                              \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) {                                       \
+      ndt2d_set_error("kernel launch", e__, __FILE__, __LINE__);    \
+      return NDT2D_ERR_CUDA;                                        \
+    }                                                               \
+    if (ctr) {(ctr)->launches += 1;}                                \
+  } while (0)
+
+#endif  // NDT2D_INTERNAL_H_

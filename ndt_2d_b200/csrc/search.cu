@@ -1,0 +1,422 @@
+// search.cu -- candidate scoring on the device (kernels K4, K5).
+//
+// Replaces ScanMatcherNDT::matchScan's three nested loops
+// (scan_matcher_ndt.cpp:103-143) together with NDT::likelihood(vector<Point>)
+// / NDT::likelihood(Vector2d) / NDT::getIndex / Cell::score
+// (ndt_model.cpp:105-116, 162-187, 203-218), and ScanMatcherNDT::scorePoints
+// (scan_matcher_ndt.cpp:156-178) for batches of poses.
+//
+// Exactness contract:
+//  * A point's position is formed with the reference's own operation sequence
+//    in IEEE double, using the never-contracted *_rn intrinsics:
+//       outer = (px*c - py*s) + pose     (scan_matcher_ndt.cpp:111-114)
+//       inner = outer + d                (:123-124)
+//    and cos/sin come from the HOST libm (staged per theta), so the cell a
+//    point falls in is the reference's cell, bit for bit.
+//  * The Gaussian exponent is evaluated in double from double means; only the
+//    final 2^t uses the FP32 special-function unit (relative error ~2e-7,
+//    inside the 1e-5 contract).  Per-candidate sums are double.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ndt2d_internal.h"
+
+namespace
+{
+
+constexpr int kPlainThreads = 256;
+constexpr int kPlainChunk = 2048;     // outer points staged per pass (32 KB)
+constexpr int kPlainMaxBlocksX = 32;  // candidate chunks per theta slice
+
+// ------------------------------------------------------------------ lookup
+// Padded cell coordinate of x on one axis, by the reference's own arithmetic
+// (NDT::getIndex, ndt_model.cpp:205-215): 0 = below the origin,
+// size + 1 = at or beyond size.
+__device__ __forceinline__ uint32_t padded_coord_exact(
+  double v, double origin, double cell_size, uint32_t size)
+{
+  if (v < origin) {return 0u;}
+  const uint32_t gi = __double2uint_rz(__ddiv_rn(__dsub_rn(v, origin), cell_size));
+  return (gi >= size ? size : gi) + 1u;
+}
+
+// Likelihood of one map-frame point given its padded cell index: 0 for an
+// unoccupied cell, else exp(-0.5 q^T I q) (Cell::score, ndt_model.cpp:105-116).
+__device__ __forceinline__ double cell_likelihood(
+  const uint2 * __restrict__ occ, const double * __restrict__ rec, uint32_t pidx, double x,
+  double y)
+{
+  const uint2 w = occ[pidx >> 5];
+  const uint32_t bit = pidx & 31u;
+  if (((w.x >> bit) & 1u) == 0u) {return 0.0;}
+  const uint32_t rank = w.y + __popc(w.x & ((1u << bit) - 1u));
+  const double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
+  const double qx = x - r[0], qy = y - r[1];
+  const double t = qx * (r[2] * qx + r[3] * qy) + r[4] * (qy * qy);
+  return static_cast<double>(exp2f(static_cast<float>(t)));
+}
+
+__device__ __forceinline__ double point_likelihood_exact(const ModelView & mv, double x, double y)
+{
+  const uint32_t ex = padded_coord_exact(x, mv.g.origin_x, mv.g.cell_size, mv.g.size_x);
+  const uint32_t ey = padded_coord_exact(y, mv.g.origin_y, mv.g.cell_size, mv.g.size_y);
+  return cell_likelihood(mv.occ, mv.rec, ey * mv.g.pitch + ex, x, y);
+}
+
+// ------------------------------------------------------------------ reduce
+struct Best
+{
+  double score;
+  double index;
+};
+
+// strict '<' with lowest index on ties == the reference's first-wins rule
+// (scan_matcher_ndt.cpp:128); NaN never wins.
+__device__ __forceinline__ void best_merge(Best & a, double score, double index)
+{
+  if (score < a.score || (score == a.score && index < a.index)) {
+    a.score = score;
+    a.index = index;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void warp_best(Best & b)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double s = __shfl_xor_sync(0xffffffffu, b.score, o);
+    const double i = __shfl_xor_sync(0xffffffffu, b.index, o);
+    best_merge(b, s, i);
+  }
+}
+
+// Block-level reduction of (best, 6 sums) into out[0..7]; all threads call.
+template<int THREADS>
+__device__ __forceinline__ void block_reduce_partial(Best b, double (&sum)[6], double * out)
+{
+  constexpr int W = THREADS / 32;
+  __shared__ double red[W][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_best(b);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {sum[k] = warp_sum(sum[k]);}
+  if (lane == 0) {
+    red[warp][0] = b.score;
+    red[warp][1] = b.index;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {red[warp][2 + k] = sum[k];}
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best t{red[0][0], red[0][1]};
+    double s[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {s[k] = red[0][2 + k];}
+    for (int w = 1; w < W; ++w) {
+      best_merge(t, red[w][0], red[w][1]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {s[k] += red[w][2 + k];}
+    }
+    out[0] = t.score;
+    out[1] = t.index;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {out[2 + k] = s[k];}
+  }
+  __syncthreads();
+}
+
+constexpr double kNoIndex = 1.0e300;
+
+// ------------------------------------------------------------------ K4, plain
+// One thread per candidate, one theta slice per blockIdx.y, reference
+// arithmetic for every cell lookup (two double divides per evaluation).  Kept
+// as the simple on-device cross-check of the tiled kernel.
+__global__ void __launch_bounds__(kPlainThreads) search_plain_kernel(
+  ModelView mv, SearchView sv, uint32_t theta_begin, double * __restrict__ block_partials,
+  double * __restrict__ scores)
+{
+  __shared__ double2 outer[kPlainChunk];
+  const uint32_t itheta = theta_begin + blockIdx.y;
+  const double2 cs = sv.trig[itheta];
+  const double dth = sv.dth[itheta];
+  const uint32_t n_lin = sv.n_lin;
+  const uint32_t n_cand = n_lin * n_lin;
+
+  Best best{0.0, kNoIndex};
+  double sum[6] = {0, 0, 0, 0, 0, 0};
+
+  for (uint32_t base = blockIdx.x * kPlainThreads; base < n_cand;
+    base += gridDim.x * kPlainThreads)
+  {
+    const uint32_t c = base + threadIdx.x;
+    const bool active = c < n_cand;
+    const uint32_t ix = active ? c / n_lin : 0u;
+    const uint32_t iy = active ? c - ix * n_lin : 0u;
+    const double dx = sv.dlin[ix], dy = sv.dlin[iy];
+    double acc = 0.0;
+    for (uint32_t p0 = 0; p0 < sv.n_pts; p0 += kPlainChunk) {
+      const uint32_t np = min(static_cast<uint32_t>(kPlainChunk), sv.n_pts - p0);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < np; i += kPlainThreads) {
+        const double2 p = sv.pts[p0 + i];
+        double2 o;
+        o.x = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
+        o.y = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
+        outer[i] = o;
+      }
+      __syncthreads();
+      if (active) {
+        for (uint32_t i = 0; i < np; ++i) {
+          const double2 o = outer[i];
+          acc += point_likelihood_exact(mv, __dadd_rn(o.x, dx), __dadd_rn(o.y, dy));
+        }
+      }
+    }
+    if (active) {
+      const double score = -acc;
+      const double gidx =
+        static_cast<double>(static_cast<uint64_t>(itheta) * n_cand + c);
+      if (scores) {scores[static_cast<uint64_t>(itheta) * n_cand + c] = score;}
+      best_merge(best, score, gidx);
+      sum[0] += score;
+      sum[1] += dx * score;
+      sum[2] += dy * score;
+      sum[3] += (dx * dx) * score;
+      sum[4] += (dx * dy) * score;
+      sum[5] += (dy * dy) * score;
+    }
+  }
+  double * out = block_partials +
+    (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * NDT2D_BLOCK_PARTIAL;
+  block_reduce_partial<kPlainThreads>(best, sum, out);
+  if (threadIdx.x == 0) {out[8] = dth;}
+}
+
+// ------------------------------------------------------------------ finish
+// rec[0..15] partial record (see ndt2d_b200.h); rec[16..31] finished outputs:
+//   [16..18] delta (dx, dy, dth)  [19] delta_written  [20..28] covariance
+//   [29] best / n
+__device__ void finish_record(double * rec, const double * dth, const double * dlin,
+  uint32_t n_lin)
+{
+  const double best = rec[0];
+  const double n = rec[13];
+  const bool written = best < 0.0;
+  rec[19] = written ? 1.0 : 0.0;
+  rec[16] = rec[17] = rec[18] = 0.0;
+  if (written && dth && dlin) {
+    const uint64_t idx = static_cast<uint64_t>(rec[1]);
+    const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
+    const uint64_t it = idx / n_cand, rem = idx - it * n_cand;
+    const uint64_t ix = rem / n_lin, iy = rem - ix * n_lin;
+    rec[16] = dlin[ix];
+    rec[17] = dlin[iy];
+    rec[18] = dth[it];
+  }
+  // covariance = (1/s) k + ((1/(s*s)) u) u^T      (scan_matcher_ndt.cpp:146)
+  const double s = rec[11];
+  const double inv_s = 1.0 / s, inv_s2 = 1.0 / (s * s);
+  const double k[9] = {rec[2], rec[3], rec[4], rec[3], rec[5], rec[6], rec[4], rec[6], rec[7]};
+  const double u[3] = {rec[8], rec[9], rec[10]};
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      rec[20 + r * 3 + c] = inv_s * k[r * 3 + c] + (inv_s2 * u[r]) * u[c];
+    }
+  }
+  rec[29] = best / n;  // :148 (n == 0 -> NaN, as in the reference)
+  rec[30] = rec[31] = 0.0;
+}
+
+// Reduce the per-block partials of one launch into the 32-double record.
+__global__ void __launch_bounds__(256) search_final_kernel(
+  const double * __restrict__ block_partials, uint32_t n_blocks, SearchView sv,
+  double n_candidates, double * __restrict__ out32)
+{
+  Best best{0.0, kNoIndex};
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // kxx kxy kxt kyy kyt ktt ux uy ut s
+  for (uint32_t b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+    const double * p = block_partials + static_cast<size_t>(b) * NDT2D_BLOCK_PARTIAL;
+    best_merge(best, p[0], p[1]);
+    const double S = p[2], Sx = p[3], Sy = p[4], Sxx = p[5], Sxy = p[6], Syy = p[7], t = p[8];
+    acc[0] += Sxx;
+    acc[1] += Sxy;
+    acc[2] += t * Sx;
+    acc[3] += Syy;
+    acc[4] += t * Sy;
+    acc[5] += (t * t) * S;
+    acc[6] += Sx;
+    acc[7] += Sy;
+    acc[8] += t * S;
+    acc[9] += S;
+  }
+  __shared__ double red[8][12];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_best(best);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {acc[k] = warp_sum(acc[k]);}
+  if (lane == 0) {
+    red[warp][0] = best.score;
+    red[warp][1] = best.index;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {red[warp][2 + k] = acc[k];}
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best t{red[0][0], red[0][1]};
+    double s[10];
+    for (int k = 0; k < 10; ++k) {s[k] = red[0][2 + k];}
+    for (int w = 1; w < 8; ++w) {
+      best_merge(t, red[w][0], red[w][1]);
+      for (int k = 0; k < 10; ++k) {s[k] += red[w][2 + k];}
+    }
+    out32[0] = t.score;
+    out32[1] = t.index;
+    for (int k = 0; k < 10; ++k) {out32[2 + k] = s[k];}
+    out32[12] = n_candidates;
+    out32[13] = static_cast<double>(sv.n_pts);
+    out32[14] = out32[15] = 0.0;
+    finish_record(out32, sv.dth, sv.dlin, sv.n_lin);
+  }
+}
+
+// Lexicographic min + sums over n partial records (one per GPU / theta range).
+__global__ void combine_kernel(
+  const double * __restrict__ partials, uint32_t n, const double * dth, const double * dlin,
+  uint32_t n_lin, double * __restrict__ out32)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) {return;}
+  Best best{0.0, kNoIndex};
+  double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double cands = 0.0, npts = 0.0;
+  for (uint32_t r = 0; r < n; ++r) {
+    const double * p = partials + static_cast<size_t>(r) * NDT2D_PARTIAL_DOUBLES;
+    best_merge(best, p[0], p[1]);
+    for (int k = 0; k < 10; ++k) {s[k] += p[2 + k];}
+    cands += p[12];
+    npts = fmax(npts, p[13]);
+  }
+  out32[0] = best.score;
+  out32[1] = best.index;
+  for (int k = 0; k < 10; ++k) {out32[2 + k] = s[k];}
+  out32[12] = cands;
+  out32[13] = npts;
+  out32[14] = out32[15] = 0.0;
+  finish_record(out32, dth, dlin, n_lin);
+}
+
+// An empty theta range still has to produce a neutral record.
+__global__ void empty_partial_kernel(SearchView sv, double * __restrict__ out32)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) {return;}
+  for (int k = 0; k < 32; ++k) {out32[k] = 0.0;}
+  out32[1] = kNoIndex;
+  out32[13] = static_cast<double>(sv.n_pts);
+  finish_record(out32, sv.dth, sv.dlin, sv.n_lin);
+}
+
+// ------------------------------------------------------------------ K5
+// One warp per pose; lanes stride over the points.
+//   x' = (c*px + (-s)*py) + tx ,  y' = (s*px + c*py) + ty
+// which is toEigen(pose) * (px, py, 1) (conversions.hpp:64-68; the z column
+// of the rotation is exactly zero).
+__global__ void __launch_bounds__(256) score_poses_kernel(
+  ModelView mv, const double2 * __restrict__ pts, uint32_t n_pts,
+  const double4 * __restrict__ pose_tf, uint32_t n_poses, double sign, int normalise,
+  double * __restrict__ out)
+{
+  const uint32_t pose = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pose >= n_poses) {return;}
+  const double4 tf = pose_tf[pose];  // x, y, cos, sin
+  double acc = 0.0;
+  for (uint32_t i = lane; i < n_pts; i += 32) {
+    const double2 p = pts[i];
+    const double x = __dadd_rn(__dadd_rn(__dmul_rn(tf.z, p.x), __dmul_rn(-tf.w, p.y)), tf.x);
+    const double y = __dadd_rn(__dadd_rn(__dmul_rn(tf.w, p.x), __dmul_rn(tf.z, p.y)), tf.y);
+    acc += point_likelihood_exact(mv, x, y);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    double v = sign * acc;
+    if (normalise) {v = v / static_cast<double>(n_pts);}
+    out[pose] = v;
+  }
+}
+
+uint32_t plain_blocks_x(uint32_t n_lin)
+{
+  const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
+  const uint64_t chunks = (n_cand + kPlainThreads - 1) / kPlainThreads;
+  return static_cast<uint32_t>(chunks < kPlainMaxBlocksX ? (chunks ? chunks : 1) : kPlainMaxBlocksX);
+}
+
+}  // namespace
+
+size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, int variant)
+{
+  (void)variant;
+  return static_cast<size_t>(n_ang ? n_ang : 1) * plain_blocks_x(n_lin) * NDT2D_BLOCK_PARTIAL;
+}
+
+int ndt2d_launch_search(
+  const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
+  int variant, double * d_block_partials, double * d_partial32, double * d_scores,
+  cudaStream_t stream, Counters * ctr)
+{
+  (void)variant;
+  if (theta_end <= theta_begin || sv.n_lin == 0) {
+    empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
+  const uint32_t n_theta = theta_end - theta_begin;
+  const uint32_t bx = plain_blocks_x(sv.n_lin);
+  // gridDim.y is limited to 65535: slice the theta range if needed
+  uint32_t done = 0;
+  while (done < n_theta) {
+    const uint32_t ny = min(n_theta - done, 65535u);
+    dim3 grid(bx, ny);
+    search_plain_kernel<<<grid, kPlainThreads, 0, stream>>>(
+      mv, sv, theta_begin + done,
+      d_block_partials + static_cast<size_t>(done) * bx * NDT2D_BLOCK_PARTIAL, d_scores);
+    NDT2D_LAUNCH_CHECK(ctr);
+    done += ny;
+  }
+  const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
+  search_final_kernel<<<1, 256, 0, stream>>>(
+    d_block_partials, n_theta * bx, sv, n_candidates, d_partial32);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}
+
+int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,
+  const double * d_dlin, uint32_t n_lin, double * d_out32, cudaStream_t stream, Counters * ctr)
+{
+  combine_kernel<<<1, 32, 0, stream>>>(d_partials, n, d_dth, d_dlin, n_lin, d_out32);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}
+
+int ndt2d_launch_score_poses(
+  const ModelView & mv, const double2 * d_pts, uint32_t n_pts, const double4 * d_pose_tf,
+  uint32_t n_poses, double sign, int normalise, double * d_out, cudaStream_t stream,
+  Counters * ctr)
+{
+  if (n_poses == 0) {return NDT2D_OK;}
+  const uint32_t warps_per_block = 256 / 32;
+  const uint32_t grid = (n_poses + warps_per_block - 1) / warps_per_block;
+  score_poses_kernel<<<grid, 256, 0, stream>>>(
+    mv, d_pts, n_pts, d_pose_tf, n_poses, sign, normalise, d_out);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}

@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference's scan-matcher plugin interface over the C ABI.
+
+Same names, argument meaning and error behaviour as ndt_2d::ScanMatcher /
+ndt_2d::ScanMatcherNDT (include/ndt_2d/scan_matcher.hpp:42-91,
+src/scan_matcher_ndt.cpp:35-183) so that parity tests read like calls into the
+reference.  The C++ drop-in class lives in ndt_2d_b200/cpp/; this module exists
+for tests and bench.py.  All computation happens in libndt2d_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class Pose2d:
+    """include/ndt_2d/pose_2d.hpp:35-55"""
+    x: float = 0.0
+    y: float = 0.0
+    theta: float = 0.0
+
+    def as_array(self) -> np.ndarray:
+        return np.array([self.x, self.y, self.theta], dtype=np.float64)
+
+
+@dataclass
+class Scan:
+    """include/ndt_2d/scan.hpp:40-90: id, pose (map frame), points (sensor frame)."""
+    id: int = 0
+    pose: Pose2d = field(default_factory=Pose2d)
+    points: np.ndarray = field(default_factory=lambda: np.zeros((0, 2)))
+
+    def getPose(self) -> Pose2d:
+        return self.pose
+
+    def setPose(self, pose: Pose2d) -> None:
+        self.pose = pose
+
+    def getPoints(self) -> np.ndarray:
+        return self.points
+
+    def setPoints(self, points) -> None:
+        self.points = L.f64(points).reshape(-1, 2)
+
+
+class ParameterNode:
+    """Stand-in for the rclcpp::Node the plugin reads its parameters from:
+    declare_parameter(name, default) returns the override if one was given."""
+
+    def __init__(self, overrides: Optional[dict] = None):
+        self.overrides = dict(overrides or {})
+        self.declared = {}
+
+    def declare_parameter(self, name: str, default):
+        value = self.overrides.get(name, default)
+        self.declared[name] = value
+        return type(default)(value)
+
+
+def _pose3(pose) -> np.ndarray:
+    if isinstance(pose, Pose2d):
+        return pose.as_array()
+    return L.f64(pose).reshape(3)
+
+
+class ScanMatcherNDT:
+    """B200 backend behind the reference's ScanMatcher interface."""
+
+    def __init__(self, device: int = -1, stream: int = 0, kernel_variant: int = 0):
+        self._h = C.c_void_p()
+        self._device = device
+        self._stream = stream
+        self._variant = kernel_variant
+        self.params: Optional[L.Params] = None
+
+    # ---- ScanMatcher::initialize (scan_matcher_ndt.cpp:35-47)
+    def initialize(self, name: str, node: ParameterNode, range_max: float) -> None:
+        p = L.Params()
+        L.lib.ndt2d_default_params(C.byref(p))
+        p.ndt_resolution = node.declare_parameter(name + ".ndt_resolution", 0.25)
+        p.search_angular_resolution = node.declare_parameter(name + ".search_angular_resolution", 0.0025)
+        p.search_angular_size = node.declare_parameter(name + ".search_angular_size", 0.1)
+        p.search_linear_resolution = node.declare_parameter(name + ".search_linear_resolution", 0.005)
+        p.search_linear_size = node.declare_parameter(name + ".search_linear_size", 0.05)
+        p.laser_max_beams = node.declare_parameter(name + ".laser_max_beams", 100)
+        p.range_max = float(range_max)
+        p.device = self._device
+        p.stream = self._stream or None
+        p.kernel_variant = self._variant
+        self._destroy()
+        L.check(L.lib.ndt2d_matcher_create(C.byref(p), C.byref(self._h)), "ndt2d_matcher_create")
+        self.params = p
+
+    @classmethod
+    def from_params(cls, params: dict, name: str = "m", **kw) -> "ScanMatcherNDT":
+        node = ParameterNode({f"{name}.{k}": v for k, v in params.items() if k != "range_max"})
+        m = cls(**kw)
+        m.initialize(name, node, params.get("range_max", 0.0))
+        return m
+
+    def _destroy(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.ndt2d_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def close(self):
+        self._destroy()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h.value:
+            raise RuntimeError("ScanMatcherNDT.initialize() has not been called")
+        return self._h
+
+    # ---- ScanMatcher::addScans (scan_matcher_ndt.cpp:49-74)
+    def addScans(self, scans: Sequence[Scan]) -> None:
+        scans = list(scans)
+        poses = np.array([[s.pose.x, s.pose.y, s.pose.theta] for s in scans], dtype=np.float64).reshape(-1, 3)
+        counts = [np.asarray(s.points).reshape(-1, 2).shape[0] for s in scans]
+        offs = np.zeros(len(scans) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(counts)
+        pts = (np.concatenate([L.f64(s.points).reshape(-1, 2) for s in scans], 0)
+               if scans else np.zeros((0, 2)))
+        self.add_scans_raw(poses, offs, pts)
+
+    def add_scans_raw(self, poses: np.ndarray, offsets: np.ndarray, points: np.ndarray) -> None:
+        poses = L.f64(poses).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        points = L.f64(points).reshape(-1, 2)
+        L.check(L.lib.ndt2d_matcher_add_scans(self.handle, poses.shape[0], L.dptr(poses),
+                                              L.u64ptr(offsets), L.dptr(points)),
+                "ndt2d_matcher_add_scans")
+
+    # ---- ScanMatcher::matchScan (scan_matcher_ndt.cpp:76-149)
+    def matchScan(self, scan: Scan, pose: Optional[Pose2d] = None,
+                  covariance: Optional[np.ndarray] = None):
+        """Returns (score, pose, covariance).  `pose` (the correction delta) is
+        only modified when a candidate scored below zero and `covariance` only
+        when a map exists -- exactly the reference's in/out semantics."""
+        pose = pose if pose is not None else Pose2d()
+        cov = covariance if covariance is not None else np.zeros((3, 3))
+        score, delta, written, cov_out, status = self.match_scan_raw(scan.pose, scan.points)
+        if status == L.ERR_NO_MAP:
+            return 0.0, pose, cov
+        if written:
+            pose.x, pose.y, pose.theta = (float(v) for v in delta)
+        cov[...] = cov_out
+        return score, pose, cov
+
+    def match_scan_raw(self, pose, points):
+        pose3 = _pose3(pose)
+        pts = L.f64(points).reshape(-1, 2)
+        delta = np.zeros(3)
+        cov = np.zeros((3, 3))
+        written = C.c_int(0)
+        score = C.c_double(0.0)
+        st = L.check(L.lib.ndt2d_matcher_match_scan(self.handle, L.dptr(pose3), L.dptr(pts),
+                                                    pts.shape[0], L.dptr(delta), C.byref(written),
+                                                    L.dptr(cov), C.byref(score)),
+                     "ndt2d_matcher_match_scan", allow=(L.ERR_NO_MAP,))
+        return score.value, delta, bool(written.value), cov, st
+
+    # ---- ScanMatcher::scoreScan / scorePoints (scan_matcher_ndt.cpp:151-178)
+    def scoreScan(self, scan: Scan) -> float:
+        return self.scorePoints(scan.points, scan.pose)
+
+    def scorePoints(self, points, pose) -> float:
+        pts = L.f64(points).reshape(-1, 2)
+        pose3 = _pose3(pose)
+        out = C.c_double(0.0)
+        L.check(L.lib.ndt2d_matcher_score_points(self.handle, L.dptr(pts), pts.shape[0],
+                                                 L.dptr(pose3), C.byref(out)),
+                "ndt2d_matcher_score_points", allow=(L.ERR_NO_MAP,))
+        return out.value
+
+    def scorePoses(self, points, poses) -> np.ndarray:
+        pts = L.f64(points).reshape(-1, 2)
+        poses = L.f64(poses).reshape(-1, 3)
+        out = np.zeros(poses.shape[0])
+        L.check(L.lib.ndt2d_matcher_score_poses(self.handle, L.dptr(pts), pts.shape[0],
+                                                L.dptr(poses), poses.shape[0], L.dptr(out)),
+                "ndt2d_matcher_score_poses", allow=(L.ERR_NO_MAP,))
+        return out
+
+    def likelihoodScan(self, scan: Scan) -> float:
+        """NDT::likelihood(const ScanPtr&) (ndt_model.cpp:189-201)."""
+        pts = L.f64(scan.points).reshape(-1, 2)
+        pose3 = _pose3(scan.pose)
+        out = C.c_double(0.0)
+        L.check(L.lib.ndt2d_matcher_likelihood_scan(self.handle, L.dptr(pose3), L.dptr(pts),
+                                                    pts.shape[0], C.byref(out)),
+                "ndt2d_matcher_likelihood_scan", allow=(L.ERR_NO_MAP,))
+        return out.value
+
+    # ---- ScanMatcher::reset (scan_matcher_ndt.cpp:180-183)
+    def reset(self) -> None:
+        L.check(L.lib.ndt2d_matcher_reset(self.handle), "ndt2d_matcher_reset")
+
+    # ---- batch (loop closure, ndt_mapper.cpp:619-671)
+    def match_scan_batch(self, job_scan_offsets, map_poses, map_offsets, map_points, query_poses,
+                         query_offsets, query_points):
+        jso = np.ascontiguousarray(job_scan_offsets, dtype=np.uint64)
+        n_jobs = jso.shape[0] - 1
+        mp, mo, mpts = L.f64(map_poses).reshape(-1, 3), np.ascontiguousarray(map_offsets, dtype=np.uint64), L.f64(map_points).reshape(-1, 2)
+        qp, qo, qpts = L.f64(query_poses).reshape(-1, 3), np.ascontiguousarray(query_offsets, dtype=np.uint64), L.f64(query_points).reshape(-1, 2)
+        delta = np.zeros((n_jobs, 3))
+        written = np.zeros(n_jobs, dtype=np.int32)
+        cov = np.zeros((n_jobs, 3, 3))
+        score = np.zeros(n_jobs)
+        L.check(L.lib.ndt2d_matcher_match_scan_batch(
+            self.handle, n_jobs, L.u64ptr(jso), L.dptr(mp), L.u64ptr(mo), L.dptr(mpts), L.dptr(qp),
+            L.u64ptr(qo), L.dptr(qpts), L.dptr(delta), written.ctypes.data_as(C.POINTER(C.c_int)),
+            L.dptr(cov), L.dptr(score)), "ndt2d_matcher_match_scan_batch")
+        return score, delta, written.astype(bool), cov
+
+    # ---- staged / partial search
+    def search_shape(self):
+        na, nl = C.c_uint64(0), C.c_uint64(0)
+        L.check(L.lib.ndt2d_matcher_search_shape(self.handle, C.byref(na), C.byref(nl)), "search_shape")
+        return int(na.value), int(nl.value)
+
+    def search_values(self):
+        na, nl = self.search_shape()
+        dth, dlin = np.zeros(na), np.zeros(nl)
+        L.check(L.lib.ndt2d_matcher_search_values(self.handle, L.dptr(dth), L.dptr(dlin)), "search_values")
+        return dth, dlin
+
+    def stage_scan(self, pose, points) -> None:
+        pose3 = _pose3(pose)
+        pts = L.f64(points).reshape(-1, 2)
+        L.check(L.lib.ndt2d_matcher_stage_scan(self.handle, L.dptr(pose3), L.dptr(pts), pts.shape[0]),
+                "ndt2d_matcher_stage_scan")
+
+    def search_staged(self, theta_begin: int, theta_end: int, d_partial: int = 0) -> None:
+        L.check(L.lib.ndt2d_matcher_search_staged(self.handle, theta_begin, theta_end,
+                                                  d_partial or None), "ndt2d_matcher_search_staged")
+
+    def fetch_partial(self) -> np.ndarray:
+        out = np.zeros(L.PARTIAL_DOUBLES)
+        L.check(L.lib.ndt2d_matcher_fetch_partial(self.handle, L.dptr(out)), "ndt2d_matcher_fetch_partial")
+        return out
+
+    def combine_partials(self, partials: np.ndarray):
+        partials = L.f64(partials).reshape(-1, L.PARTIAL_DOUBLES)
+        delta, cov = np.zeros(3), np.zeros((3, 3))
+        written, score = C.c_int(0), C.c_double(0.0)
+        L.check(L.lib.ndt2d_combine_partials(self.handle, L.dptr(partials), partials.shape[0],
+                                             L.dptr(delta), C.byref(written), L.dptr(cov),
+                                             C.byref(score)), "ndt2d_combine_partials")
+        return score.value, delta, bool(written.value), cov
+
+    def combine_device(self, d_partials: int, n: int):
+        delta, cov = np.zeros(3), np.zeros((3, 3))
+        written, score = C.c_int(0), C.c_double(0.0)
+        L.check(L.lib.ndt2d_matcher_combine_device(self.handle, d_partials, n, L.dptr(delta),
+                                                   C.byref(written), L.dptr(cov), C.byref(score)),
+                "ndt2d_matcher_combine_device")
+        return score.value, delta, bool(written.value), cov
+
+    # ---- parity / introspection
+    def grid_info(self):
+        info = np.zeros(5)
+        L.check(L.lib.ndt2d_matcher_grid_info(self.handle, L.dptr(info)), "grid_info")
+        return int(info[0]), int(info[1]), info[2], info[3], info[4]
+
+    def dump_cells(self) -> np.ndarray:
+        sx, sy, *_ = self.grid_info()
+        out = np.zeros((sx * sy, 16))
+        L.check(L.lib.ndt2d_matcher_dump_cells(self.handle, L.dptr(out)), "dump_cells")
+        return out
+
+    def dump_keys(self, n_points: int) -> np.ndarray:
+        out = np.zeros(n_points, dtype=np.int32)
+        L.check(L.lib.ndt2d_matcher_dump_keys(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              n_points), "dump_keys")
+        return out
+
+    def dump_scores(self, pose, points) -> np.ndarray:
+        na, nl = self.search_shape()
+        pose3 = _pose3(pose)
+        pts = L.f64(points).reshape(-1, 2)
+        out = np.zeros(na * nl * nl)
+        L.check(L.lib.ndt2d_matcher_dump_scores(self.handle, L.dptr(pose3), L.dptr(pts), pts.shape[0],
+                                                L.dptr(out), out.shape[0]), "dump_scores")
+        return out.reshape(na, nl, nl)
+
+    def counters(self) -> dict:
+        out = np.zeros(4, dtype=np.uint64)
+        L.check(L.lib.ndt2d_matcher_counters(self.handle, L.u64ptr(out)), "counters")
+        return dict(launches=int(out[0]), h2d_bytes=int(out[1]), d2h_bytes=int(out[2]),
+                    valid_cells=int(out[3]))
+
+    def stream(self) -> int:
+        return int(L.lib.ndt2d_matcher_stream(self.handle) or 0)
