@@ -36,8 +36,6 @@ constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 8192 values per block
 
-constexpr double kNegHalfLog2e = -0.72134752044448170368;  // -0.5 * log2(e)
-
 // ------------------------------------------------------------------ K1
 // NDT::getIndex (ndt_model.cpp:203-218); returns n_cells for "outside".
 __device__ __forceinline__ uint32_t cell_key(const GridDesc & g, double x, double y)
@@ -409,12 +407,14 @@ __global__ void __launch_bounds__(128) segment_moments_kernel(
   const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
   if (rank >= rec_cap) {return;}
   double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
+  // -0.5 * information: scaling by a power of two is exact, so the device
+  // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
   r[0] = c.mean[0];
   r[1] = c.mean[1];
-  r[2] = kNegHalfLog2e * c.info[0];
-  r[3] = kNegHalfLog2e * (c.info[1] + c.info[2]);
-  r[4] = kNegHalfLog2e * c.info[3];
-  r[5] = c.n;
+  r[2] = -0.5 * c.info[0];  // (0,0)
+  r[3] = -0.5 * c.info[2];  // (1,0)
+  r[4] = -0.5 * c.info[1];  // (0,1)
+  r[5] = -0.5 * c.info[3];  // (1,1)
 }
 
 // Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.

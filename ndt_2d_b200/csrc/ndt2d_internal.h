@@ -30,9 +30,9 @@ struct GridDesc
 //                 the only cells Cell::score does not return 0 for,
 //                 ndt_model.cpp:107-111)
 //            .y = number of occupied cells before word w  (rank prefix)
-//   rec[r*6] = mean_x, mean_y, a, b, c, n   of the r-th occupied cell, where
-//              (a, b, c) = -0.5*log2(e) * (I00, I01, I11): the exponent of
-//              Cell::score (ndt_model.cpp:113-115) in base 2
+//   rec[r*6] = mean_x, mean_y, -0.5*I(0,0), -0.5*I(1,0), -0.5*I(0,1), -0.5*I(1,1)
+//              of the r-th occupied cell: what Cell::score (ndt_model.cpp:113-115)
+//              needs, 48 bytes
 //   thr_x[k] = smallest double x whose reference grid_x is >= k  (k=0: origin)
 struct ModelView
 {

@@ -25,6 +25,7 @@
 namespace
 {
 
+constexpr double kLog2e = 1.44269504088896340736;
 constexpr int kPlainThreads = 256;
 constexpr int kPlainChunk = 2048;     // outer points staged per pass (32 KB)
 constexpr int kPlainMaxBlocksX = 32;  // candidate chunks per theta slice
@@ -52,9 +53,14 @@ __device__ __forceinline__ double cell_likelihood(
   if (((w.x >> bit) & 1u) == 0u) {return 0.0;}
   const uint32_t rank = w.y + __popc(w.x & ((1u << bit) - 1u));
   const double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
-  const double qx = x - r[0], qy = y - r[1];
-  const double t = qx * (r[2] * qx + r[3] * qy) + r[4] * (qy * qy);
-  return static_cast<double>(exp2f(static_cast<float>(t)));
+  // exponent = ((-0.5 q^T) I) q with the reference's own grouping and no FMA
+  // (Eigen evaluates it left to right, ndt_model.cpp:113-114): near-singular
+  // information matrices cancel exactly where the reference's do.
+  const double qx = __dsub_rn(x, r[0]), qy = __dsub_rn(y, r[1]);
+  const double r0 = __dadd_rn(__dmul_rn(qx, r[2]), __dmul_rn(qy, r[3]));
+  const double r1 = __dadd_rn(__dmul_rn(qx, r[4]), __dmul_rn(qy, r[5]));
+  const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
+  return static_cast<double>(exp2f(static_cast<float>(e * kLog2e)));
 }
 
 __device__ __forceinline__ double point_likelihood_exact(const ModelView & mv, double x, double y)

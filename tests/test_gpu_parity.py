@@ -1,0 +1,391 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, on identical
+synthetic inputs.  Contract (BASELINE.json north_star):
+  * cell indices and candidate counts: bit-exact
+  * per-cell mean / covariance and scores: within 1e-5 relative
+  * best pose identical unless reference scores tie within that tolerance
+Scores additionally get an absolute floor of 1e-30: a per-point likelihood below
+2^-126 flushes to zero in the FP32 exp2 the device uses for the final 2^t.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from ndt_2d_b200 import ParticleFilter, Pose2d, Scan, ScanMatcherNDT, synth
+from ndt_2d_b200 import _lib as L
+from oracle import binding as B
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5       # the north_star tolerance
+ATOL_SCORE = 1e-30
+
+
+def world_points(poses, offsets, points):
+    """NDT::addScan's transform (ndt_model.cpp:135-143) in numpy: separate IEEE
+    multiplies/adds, no FMA, cos/sin from the host libm."""
+    out = np.empty_like(points)
+    for k in range(poses.shape[0]):
+        lo, hi = int(offsets[k]), int(offsets[k + 1])
+        c, s = math.cos(poses[k, 2]), math.sin(poses[k, 2])
+        px, py = points[lo:hi, 0], points[lo:hi, 1]
+        out[lo:hi, 0] = poses[k, 0] + (px * c - py * s)
+        out[lo:hi, 1] = poses[k, 1] + (px * s + py * c)
+    return out
+
+
+def ref_keys(grid, wp):
+    """NDT::getIndex (ndt_model.cpp:203-218), vectorised."""
+    sx, sy, ox, oy, cs = grid
+    x, y = wp[:, 0], wp[:, 1]
+    inside = (x >= ox) & (y >= oy)
+    gx = np.zeros(x.shape, dtype=np.int64)
+    gy = np.zeros(x.shape, dtype=np.int64)
+    gx[inside] = np.trunc((x[inside] - ox) / cs).astype(np.int64)
+    gy[inside] = np.trunc((y[inside] - oy) / cs).astype(np.int64)
+    inside &= (gx < sx) & (gy < sy)
+    return np.where(inside, gy * sx + gx, -1).astype(np.int32)
+
+
+def check_cells(gpu_cells, orc_cells):
+    """valid, n, mean, covariance, correlation exact; information to 1e-12 (same IEEE
+    operations on both sides), far inside the 1e-5 contract."""
+    assert np.array_equal(gpu_cells[:, 1], orc_cells[:, 1])                       # n
+    assert np.array_equal(gpu_cells[:, 0], orc_cells[:, 0])                       # valid
+    assert np.array_equal(gpu_cells[:, 2:4], orc_cells[:, 2:4])                   # mean
+    assert np.array_equal(gpu_cells[:, 8:12], orc_cells[:, 8:12])                 # correlation
+    assert np.array_equal(gpu_cells[:, 4:8], orc_cells[:, 4:8])                   # covariance
+    np.testing.assert_allclose(gpu_cells[:, 12:16], orc_cells[:, 12:16], rtol=1e-12, atol=0)
+
+
+def check_match(gpu, orc, scores_gpu=None, scores_orc=None):
+    sg, dg, wg, cg = gpu
+    so, do, wo, co = orc
+    assert wg == wo
+    np.testing.assert_allclose(sg, so, rtol=RTOL, atol=ATOL_SCORE)
+    np.testing.assert_allclose(cg, co, rtol=RTOL, atol=RTOL * np.abs(co).max())
+    if wo and not np.array_equal(dg, do):
+        # allowed only when the two candidates tie within tolerance in the reference
+        assert scores_orc is not None, "best pose differs and no score volume to justify a tie"
+        flat = scores_orc.ravel()
+        best = flat.min()
+        tied = np.abs(flat - best) <= RTOL * abs(best)
+        assert tied.sum() > 1, f"best pose differs without a tie: gpu {dg} oracle {do}"
+    if scores_gpu is not None:
+        assert scores_gpu.shape == scores_orc.shape                               # candidate count
+        np.testing.assert_allclose(scores_gpu, scores_orc, rtol=RTOL, atol=ATOL_SCORE)
+
+
+@pytest.fixture(scope="module")
+def o(oracle, gpu):
+    return oracle
+
+
+# ------------------------------------------------------------------ build
+@pytest.mark.parametrize("cfg", ["config1", "config4"])
+def test_build_parity(o, cfg):
+    w = getattr(synth, cfg)()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    assert m.grid_info() == mo.grid()                                             # grid, bit-exact
+    keys = m.dump_keys(w.map_points.shape[0])
+    wp = world_points(w.map_poses, w.map_offsets, w.map_points)
+    expect = ref_keys(mo.grid(), wp)
+    assert np.array_equal(keys, expect)                                           # cell indices
+    # spot-check the vectorised restatement against the oracle's own getIndex
+    for i in range(0, wp.shape[0], 97):
+        assert mo.get_index(wp[i, 0], wp[i, 1]) == expect[i]
+    check_cells(m.dump_cells(), mo.dump_cells())
+    assert m.counters()["valid_cells"] == int((mo.dump_cells()[:, 1] >= 5).sum())
+
+
+def test_build_bounding_box_quirk(o):
+    """max_* start at DBL_MIN (scan_matcher_ndt.cpp:54,56): all-negative poses stretch
+    the grid up to ~0; points outside the grid are dropped, not clamped."""
+    p = dict(ndt_resolution=0.25, search_angular_resolution=0.01, search_angular_size=0.02,
+             search_linear_resolution=0.05, search_linear_size=0.1, laser_max_beams=100,
+             range_max=5.0)
+    poses = np.array([[-30.0, -40.0, 0.3], [-31.0, -40.5, -0.2]])
+    pts = np.concatenate([np.array([[1.0, 0.2], [1.01, 0.21], [0.99, 0.19], [1.0, 0.22], [1.02, 0.2],
+                                    [9.0, 9.0], [-4.9, 0.0]]),
+                          np.array([[2.0, 0.7], [2.01, 0.71], [1.99, 0.69]])])
+    offs = np.array([0, 7, 10], dtype=np.uint64)
+    m = ScanMatcherNDT.from_params(p)
+    m.add_scans_raw(poses, offs, pts)
+    mo = o.new_matcher(p)
+    mo.add_scans(poses, offs, pts)
+    assert m.grid_info() == mo.grid()
+    assert np.array_equal(m.dump_keys(10), ref_keys(mo.grid(), world_points(poses, offs, pts)))
+    check_cells(m.dump_cells(), mo.dump_cells())
+
+
+def test_build_empty_and_ragged(o):
+    w = synth.config1()
+    m = ScanMatcherNDT.from_params(w.params)
+    mo = o.new_matcher(w.params)
+    # scans with zero points in the middle, and a model with no points at all
+    poses = w.map_poses[:3]
+    offs = np.array([0, int(w.map_offsets[1]), int(w.map_offsets[1]), int(w.map_offsets[2])], dtype=np.uint64)
+    m.add_scans_raw(poses, offs, w.map_points)
+    mo.add_scans(poses, offs, w.map_points)
+    assert m.grid_info() == mo.grid()
+    check_cells(m.dump_cells(), mo.dump_cells())
+    offs0 = np.zeros(4, dtype=np.uint64)
+    m.add_scans_raw(poses, offs0, np.zeros((0, 2)))
+    mo.add_scans(poses, offs0, np.zeros((0, 2)))
+    assert m.grid_info() == mo.grid()
+    assert not m.dump_cells().any()
+    s, d, written, cov, _ = m.match_scan_raw(w.query_pose, w.query_points)
+    so, do, wo, co, _ = mo.match_scan(w.query_pose, w.query_points)
+    assert (s, written) == (so, wo) and np.all(np.isnan(cov)) and np.all(np.isnan(co))
+
+
+def test_build_degenerate_cell_is_nan_like_reference(o):
+    """Q7: >= 5 identical points -> zero covariance -> inf/NaN information; the score
+    volume must be NaN-poisoned in the same candidates."""
+    p = dict(ndt_resolution=0.5, search_angular_resolution=0.01, search_angular_size=0.02,
+             search_linear_resolution=0.05, search_linear_size=0.1, laser_max_beams=100,
+             range_max=4.0)
+    poses = np.array([[0.0, 0.0, 0.0]])
+    pts = np.array([[1.1, 1.1]] * 6 + [[2.3, 0.4], [2.35, 0.45], [2.32, 0.42], [2.31, 0.47], [2.36, 0.41]])
+    offs = np.array([0, pts.shape[0]], dtype=np.uint64)
+    m = ScanMatcherNDT.from_params(p)
+    m.add_scans_raw(poses, offs, pts)
+    mo = o.new_matcher(p)
+    mo.add_scans(poses, offs, pts)
+    gc, oc = m.dump_cells(), mo.dump_cells()
+    assert np.array_equal(np.isnan(gc), np.isnan(oc)) and np.array_equal(np.isinf(gc), np.isinf(oc))
+    q = np.array([[1.1, 1.1], [2.3, 0.45]])
+    sg = m.dump_scores([0.0, 0.0, 0.0], q)
+    _, _, _, _, so = mo.match_scan([0.0, 0.0, 0.0], q, want_scores=True)
+    assert np.array_equal(np.isnan(sg), np.isnan(so))
+    ok = ~np.isnan(so)
+    np.testing.assert_allclose(sg[ok], so[ok], rtol=RTOL, atol=ATOL_SCORE)
+
+
+# ------------------------------------------------------------------ search
+@pytest.mark.parametrize("beams", [360, 100])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_match_scan_config1(o, beams, variant):
+    w = synth.config1(laser_max_beams=beams)
+    m = ScanMatcherNDT.from_params(w.params, kernel_variant=variant)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    assert m.search_shape() == (200, 10)                                          # candidate counts
+    so, do, wo, co, scores_o = mo.match_scan(w.query_pose, w.query_points, want_scores=True)
+    sg, dg, wg, cg, st = m.match_scan_raw(w.query_pose, w.query_points)
+    scores_g = m.dump_scores(w.query_pose, w.query_points)
+    check_match((sg, dg, wg, cg), (so, do, wo, co), scores_g, scores_o)
+    # the reference-style call: pose is the in/out correction
+    score, pose, cov = m.matchScan(Scan(0, Pose2d(*w.query_pose), w.query_points))
+    assert score == sg and (pose.x, pose.y, pose.theta) == tuple(dg)
+
+
+def test_match_scan_plugin_defaults(o):
+    """Plugin defaults (scan_matcher_ndt.cpp:37-44): 21 x 21 x 80 candidates."""
+    w = synth.config1()
+    p = dict(range_max=10.0)
+    m = ScanMatcherNDT.from_params(p)
+    assert m.search_shape() == (80, 21)
+    full = dict(ndt_resolution=0.25, search_angular_resolution=0.0025, search_angular_size=0.1,
+                search_linear_resolution=0.005, search_linear_size=0.05, laser_max_beams=100,
+                range_max=10.0)
+    mo = o.new_matcher(full)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    guess = w.true_pose - np.array([0.02, -0.03, 0.04])
+    so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
+    dth, dlin = m.search_values()
+    assert dlin[-1] == 0.04999999999999999 and len(dlin) == 21                   # accumulated bound
+
+
+def test_match_scan_edge_cases(o):
+    w = synth.config1()
+    m = ScanMatcherNDT.from_params(w.params)
+    mo = o.new_matcher(w.params)
+    # no map: 0.0 and outputs untouched (scan_matcher_ndt.cpp:80)
+    pose, cov = Pose2d(1.0, 2.0, 3.0), np.full((3, 3), 7.0)
+    score, pose, cov = m.matchScan(Scan(0, Pose2d(*w.query_pose), w.query_points), pose, cov)
+    assert score == 0.0 and (pose.x, pose.y, pose.theta) == (1.0, 2.0, 3.0) and np.all(cov == 7.0)
+    assert m.scorePoints(w.query_points, w.query_pose) == 0.0
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    # scan far outside the map: every candidate scores 0 -> pose untouched, NaN covariance
+    sg, dg, wg, cg, _ = m.match_scan_raw([500.0, 500.0, 0.0], w.query_points)
+    so, do, wo, co, _ = mo.match_scan([500.0, 500.0, 0.0], w.query_points)
+    assert (sg, wg) == (so, wo) == (0.0, False) and np.all(np.isnan(cg)) and np.all(np.isnan(co))
+    # empty scan: n == 0 -> 0/0
+    sg, dg, wg, cg, _ = m.match_scan_raw(w.query_pose, np.zeros((0, 2)))
+    so, do, wo, co, _ = mo.match_scan(w.query_pose, np.zeros((0, 2)))
+    assert math.isnan(sg) and math.isnan(so) and not wg and not wo
+    # reset drops the model
+    m.reset()
+    assert m.match_scan_raw(w.query_pose, w.query_points)[4] == L.ERR_NO_MAP
+
+
+def test_match_scan_config4_reduced(o):
+    """The large-search shapes (1080 beams, 0.01 m / 0.002 rad steps) on a window the
+    oracle finishes in seconds."""
+    w = synth.config4(scale=0.04)
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    guess = w.true_pose - np.array([0.05, -0.03, 0.06])
+    so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
+
+
+def test_theta_sliced_search_matches_full(o):
+    """Partial searches over theta ranges + one combine == the full search (the
+    multi-GPU path, exercised on one device)."""
+    w = synth.config1()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    full = m.match_scan_raw(w.query_pose, w.query_points)
+    na, _ = m.search_shape()
+    m.stage_scan(w.query_pose, w.query_points)
+    for cuts in ([0, na], [0, 67, 134, na], [0, 0, 1, na - 1, na], [0, 25, 50, 75, 100, 125, 150, 175, na]):
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            m.search_staged(a, b)
+            parts.append(m.fetch_partial())
+        parts = np.array(parts)
+        assert parts[:, 12].sum() == na * 100
+        s, d, written, cov = m.combine_partials(parts)
+        assert written == full[2] and np.array_equal(d, full[1])
+        np.testing.assert_allclose(s, full[0], rtol=1e-13)
+        np.testing.assert_allclose(cov, full[3], rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------ scoring
+def test_score_points_and_poses(o):
+    w = synth.config1(laser_max_beams=100)
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    poses = w.true_pose[None, :] + 0.05 * synth.normal(3, 3 * 257).reshape(-1, 3)
+    poses = np.concatenate([poses, [[500.0, 500.0, 0.0], list(w.true_pose)]])
+    expect = np.array([mo.score_points(w.query_points, p) for p in poses])
+    got = m.scorePoses(w.query_points, poses)
+    np.testing.assert_allclose(got, expect, rtol=RTOL, atol=ATOL_SCORE)
+    assert got[-2] == 0.0
+    for p in poses[:5]:
+        np.testing.assert_allclose(m.scorePoints(w.query_points, p), mo.score_points(w.query_points, p),
+                                   rtol=RTOL, atol=ATOL_SCORE)
+    scan = Scan(0, Pose2d(*w.true_pose), w.query_points)
+    np.testing.assert_allclose(m.scoreScan(scan), mo.score_points(w.query_points, w.true_pose), rtol=RTOL)
+    # NDT::likelihood(ScanPtr): all points, positive, not normalised
+    import ctypes as C
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lk = o.ndt_likelihood_scan(o.matcher_ndt(mo.h), d(np.ascontiguousarray(w.true_pose)),
+                               d(w.query_points), w.query_points.shape[0])
+    np.testing.assert_allclose(m.likelihoodScan(scan), lk, rtol=RTOL)
+    assert lk > 0
+
+
+# ------------------------------------------------------------------ loop closure batch
+def test_match_scan_batch(o):
+    w = synth.config3(n_jobs=4)
+    m = ScanMatcherNDT.from_params(w.params)
+    score, delta, written, cov = m.match_scan_batch(w.job_scan_offsets, w.map_poses, w.map_offsets,
+                                                    w.map_points, w.query_poses, w.query_offsets,
+                                                    w.query_points)
+    mo = o.new_matcher(w.params)
+    for j in range(4):
+        s0, s1 = int(w.job_scan_offsets[j]), int(w.job_scan_offsets[j + 1])
+        mo.reset()
+        offs = w.map_offsets[s0:s1 + 1]
+        mo.add_scans(w.map_poses[s0:s1], offs - offs[0], w.map_points[int(offs[0]):int(offs[-1])])
+        q0, q1 = int(w.query_offsets[j]), int(w.query_offsets[j + 1])
+        so, do, wo, co, sc = mo.match_scan(w.query_poses[j], w.query_points[q0:q1], want_scores=True)
+        check_match((score[j], delta[j], written[j], cov[j]), (so, do, wo, co), None, sc)
+    assert m.match_scan_raw(w.query_poses[0], w.query_points[:10])[4] == L.ERR_NO_MAP
+
+
+# ------------------------------------------------------------------ particle filter
+def test_filter_measure_and_statistics(o):
+    w = synth.config2(n_side=12, n_particles=700)
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    P = w.particles.shape[0]
+    f = ParticleFilter(100, P)
+    assert f.size() == 100 and np.all(f.get_particles()[0] == 0.0)                # ctor state
+    f.set_particles(w.particles, np.full(P, 1.0 / P))
+    f.measure(m, Scan(0, Pose2d(), w.scan_points))
+    raw = B.pf_measure(o, mo, w.particles, w.scan_points)
+    wn, mean_o, cov_o = B.pf_update_statistics(o, w.particles, raw, np.zeros((3, 3)))
+    pg, wg = f.get_particles()
+    assert np.array_equal(pg, w.particles)
+    np.testing.assert_allclose(wg, wn, rtol=RTOL, atol=1e-30)
+    np.testing.assert_allclose(f.getMean(), mean_o, rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(f.getCovariance(), cov_o, rtol=RTOL, atol=RTOL * np.abs(cov_o).max())
+    # cov(2,2) accumulates across calls like the reference (particle_filter.cpp:216)
+    f.measure(m, Scan(0, Pose2d(), w.scan_points))
+    _, _, cov_o2 = B.pf_update_statistics(o, w.particles, raw, cov_o)
+    np.testing.assert_allclose(f.getCovariance()[2, 2], cov_o2[2, 2], rtol=RTOL)
+    assert f.getCovariance()[2, 2] > cov_o[2, 2]
+
+
+@pytest.mark.parametrize("seed,kld_err,kld_z,min_p,max_p", [
+    (11, 0.01, 2.3, 500, 5000), (12, 0.05, 1.0, 50, 400), (13, 0.99, 0.01, 50, 100),
+    (14, 0.01, 2.3, 10, 37)])
+def test_filter_resample(o, seed, kld_err, kld_z, min_p, max_p):
+    P = max_p
+    particles = np.stack([1.25 + 0.8 * synth.normal(seed, P), 0.5 + 0.8 * synth.normal(seed + 1, P),
+                          1.57 + 0.4 * synth.normal(seed + 2, P)], 1)
+    weights = synth.uniform(seed + 3, P) + 0.01
+    weights /= weights.sum()
+    u = synth.uniform(seed + 4, max_p)
+    po, wo, idx = B.pf_resample(o, particles, weights, min_p, max_p, kld_err, kld_z, u)
+    f = ParticleFilter(min_p, max_p)
+    f.set_particles(particles, weights)
+    f.set_covariance(np.zeros((3, 3)))
+    f.resample(kld_err, kld_z, uniforms=u)
+    assert f.size() == po.shape[0]                                                # KLD stop index
+    assert np.array_equal(f.last_draws(), idx)                                    # drawn indices
+    pg, wg = f.get_particles()
+    assert np.array_equal(pg, po)
+    wn, mean_o, cov_o = B.pf_update_statistics(o, po, wo, np.zeros((3, 3)))
+    np.testing.assert_allclose(wg, wn, rtol=1e-12)
+    np.testing.assert_allclose(f.getMean(), mean_o, rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(f.getCovariance(), cov_o, rtol=RTOL, atol=RTOL * np.abs(cov_o).max())
+    # device-generated uniforms replay the documented host stream
+    f2 = ParticleFilter(min_p, max_p)
+    f2.set_particles(particles, weights)
+    f2.resample(kld_err, kld_z, uniforms=None, seed=seed + 4)
+    assert f2.size() == po.shape[0] and np.array_equal(f2.last_draws(), idx)
+
+
+def test_filter_init_update_statistical(o):
+    """test/particle_tests.cpp:160-204: loose statistical checks (the reference's RNG is
+    random_device-seeded, so only distributions can be compared)."""
+    from ndt_2d_b200 import MotionModel
+    f = ParticleFilter(2000, 4000, MotionModel(0.1, 0.1, 0.1, 0.1, 0.0))
+    f.init(1.25, 0.5, 1.57, 0.1, 0.1, 0.3, seed=5)
+    mean, cov = f.getMean(), f.getCovariance()
+    assert abs(mean[0] - 1.25) < 0.02 and abs(mean[1] - 0.5) < 0.02 and abs(mean[2] - 1.57) < 0.05
+    assert abs(cov[0, 0] - 0.01) < 0.003 and abs(cov[1, 1] - 0.01) < 0.003 and abs(cov[2, 2] - 0.09) < 0.02
+    f.update(1.5, 0.0, 0.0, seed=6)
+    mean = f.getMean()
+    # tolerances of the reference's own test (EXPECT_NEAR(..., 0.4)); the expected y is
+    # 0.5 + 1.5 * E[sin(theta + rot1 noise)] ~ 1.78, not 2.0
+    assert abs(mean[0] - 1.25) < 0.4 and abs(mean[1] - 2.0) < 0.4 and abs(mean[2] - 1.57) < 0.4
+    f.resample(0.99, 0.01, seed=7)
+    mean = f.getMean()
+    assert abs(mean[0] - 1.25) < 0.4 and abs(mean[1] - 2.0) < 0.4
+    f.init(0.0, 0.0, 3.14, 0.1, 0.1, 0.1, seed=8)                                  # circular mean
+    assert abs(o.shortest_angular_distance(f.getMean()[2], 3.14)) < 0.05
+    f.init(0.0, 0.0, 0.0, 0.1, 0.1, 0.1, seed=9)
+    f.update(-1.0, 0.0, 0.0, seed=10)
+    mean = f.getMean()
+    assert abs(mean[0] + 1.0) < 0.2 and abs(mean[1]) < 0.2 and abs(mean[2]) < 0.2
