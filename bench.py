@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- candidate poses scored per second / matchScan latency of the B200 path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], "Large correlative search"): one 1080-beam scan
+matched against a rolling NDT of 10 scans (0.25 m cells), +-2 m @0.01 m x +-pi @0.002 rad
+= 3142 x 400 x 400 = 502,720,000 candidate poses per matchScan.  One step = one
+matchScan.  With N GPUs the theta slices are split contiguously over the ranks
+(strong scaling: total work fixed) and the partial results are combined by ONE
+all-gather of a 128-byte record per rank + a device-side lexicographic reduce.
+
+Prints ONE JSON line (rank 0).  Keys: see the contract in the task statement; extra
+keys: `other_workloads` (the remaining BASELINE configs, timed outside the main
+region), `parity` (the checked result of the timed search).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "ndt_candidate_poses_scored_per_sec"
+UNIT = "candidates/s"
+ALGO_BYTES_PER_EVAL = 32  # one packed cell record per (candidate, point)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_sample(workload, n_theta: int, threads: int, prefer_ref: bool = True):
+    """Times the reference's own CPU matchScan on a bounded theta sample of the workload.
+
+    The UNMODIFIED reference (oracle/_ref, its sources compiled in place) is run with a
+    narrower search_angular_size -- a legal parameter value -- so each thread scores
+    n_theta x n_lin^2 candidates with exactly the per-candidate work of the full search.
+    Falls back to the C restatement (kind "port") only if oracle/_ref is missing."""
+    from oracle import binding as B
+    lib = B.load_ref() if prefer_ref else None
+    kind = "reference" if lib is not None else "port"
+    if lib is None:
+        lib = B.load_oracle()
+    p = dict(workload.params)
+    p["search_angular_size"] = 0.5 * n_theta * p["search_angular_resolution"]
+    matchers = []
+    for t in range(threads):
+        m = lib.new_matcher(p)
+        m.add_scans(workload.map_poses, workload.map_offsets, workload.map_points)
+        matchers.append(m)
+    o = B.load_oracle()
+    na = o.loop_values(p["search_angular_size"], p["search_angular_resolution"], None, 0)
+    nl = o.loop_values(p["search_linear_size"], p["search_linear_resolution"], None, 0)
+    cand_per_thread = na * nl * nl
+
+    def run(t):
+        pose = workload.query_pose + np.array([0.0, 0.0, t * n_theta * p["search_angular_resolution"]])
+        matchers[t].match_scan(pose, workload.query_points)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=run, args=(t,)) for t in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return cand_per_thread * threads / dt, dt, kind, cand_per_thread * threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ndt_2d_b200 import synth
+    w = synth.config4()
+    threads = os.cpu_count() or 1
+    n_theta = 2
+    vals, times = [], []
+    kind, cands = "reference", 0
+    for i in range(args.warmup + args.steps):
+        v, dt, kind, cands = reference_sample(w, n_theta, threads)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals))
+    sample = (f"{threads} threads x {n_theta} theta slices x 400 x 400 candidates x 1080 beams per step "
+              f"(of 3142 slices), unmodified reference matchScan with a narrower search_angular_size")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "config4_large_search (BASELINE.json configs[3]), bounded theta sample",
+                   "candidates_per_step": cands, "beams": 1080},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def other_workloads(torch, dev_index: int):
+    """The remaining BASELINE configs, a few repetitions each (not the headline)."""
+    from ndt_2d_b200 import ParticleFilter, Pose2d, Scan, ScanMatcherNDT, synth
+    out = {}
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    # config 1: local match (addScans + scoreScan + matchScan, ndt_mapper.cpp:508-515)
+    for beams in (360, 100):
+        w = synth.config1(laser_max_beams=beams)
+        m = ScanMatcherNDT.from_params(w.params, device=dev_index)
+        scan = Scan(0, Pose2d(*w.query_pose), w.query_points)
+
+        def triple():
+            m.reset()
+            m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+            m.scoreScan(scan)
+            return m.match_scan_raw(w.query_pose, w.query_points)
+        t_triple = timed(triple)
+        t_match = timed(lambda: m.match_scan_raw(w.query_pose, w.query_points))
+        na, nl = m.search_shape()
+        out[f"config1_local_match_beams{beams}"] = {
+            "candidates": na * nl * nl, "matchScan_ms": t_match * 1e3,
+            "reset_addScans_scoreScan_matchScan_ms": t_triple * 1e3,
+            "candidates_per_s": na * nl * nl / t_match}
+        m.close()
+    # config 2: particle filter measure + resample
+    w = synth.config2()
+    m = ScanMatcherNDT.from_params(w.params, device=dev_index)
+    t_build = timed(lambda: m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points), reps=3, warm=1)
+    f = ParticleFilter(w.min_particles, w.max_particles, device=dev_index)
+    P = w.particles.shape[0]
+    scan = Scan(0, Pose2d(), w.scan_points)
+
+    def measure():
+        f.set_particles(w.particles, np.full(P, 1.0 / P))
+        f.measure(m, scan)
+    t_meas = timed(measure)
+
+    def resample():
+        f.set_particles(w.particles, np.full(P, 1.0 / P))
+        f.measure(m, scan)
+        f.resample(w.kld_err, w.kld_z, seed=9)
+    t_res = timed(resample) - t_meas
+    out["config2_particle_filter"] = {
+        "particles": P, "beams": int(w.scan_points.shape[0]), "map_points": int(w.map_points.shape[0]),
+        "global_ndt_build_ms": t_build * 1e3, "set_particles_plus_measure_ms": t_meas * 1e3,
+        "resample_ms": max(t_res, 0.0) * 1e3, "particles_per_s": P / t_meas,
+        "resampled_size": f.size()}
+    f.close()
+    m.close()
+    # config 3: loop-closure batch
+    w = synth.config3()
+    m = ScanMatcherNDT.from_params(w.params, device=dev_index)
+    t_batch = timed(lambda: m.match_scan_batch(w.job_scan_offsets, w.map_poses, w.map_offsets,
+                                               w.map_points, w.query_poses, w.query_offsets,
+                                               w.query_points), reps=3, warm=1)
+    na, nl = m.search_shape()
+    n_jobs = w.query_poses.shape[0]
+    out["config3_loop_closure_batch"] = {
+        "jobs": n_jobs, "candidates": n_jobs * na * nl * nl, "batch_ms": t_batch * 1e3,
+        "candidates_per_s": n_jobs * na * nl * nl / t_batch}
+    m.close()
+    # config 5: model build
+    w = synth.config5()
+    m = ScanMatcherNDT.from_params(w.params, device=dev_index)
+    pinned_pts = torch.from_numpy(w.points).pin_memory()
+    t_b = timed(lambda: m.add_scans_raw(w.poses, w.offsets, pinned_pts.numpy()), reps=3, warm=1)
+    sx, sy, *_ = m.grid_info()
+    npts = int(w.points.shape[0])
+    nocc = m.counters()["valid_cells"]
+    algo = 16 * npts + 24 * w.poses.shape[0] + 48 * nocc
+    out["config5_model_build"] = {
+        "scans": int(w.poses.shape[0]), "points": npts, "grid": [sx, sy], "valid_cells": nocc,
+        "add_scans_ms_e2e_pinned_host": t_b * 1e3, "points_per_s": npts / t_b,
+        "algorithmic_GBps_e2e": algo / t_b / 1e9}
+    m.close()
+    return out
+
+
+def run_ours(args):
+    import torch
+    from ndt_2d_b200 import ScanMatcherNDT, lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if lib.ndt2d_device_count() <= 0 or not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: ndt_2d_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = synth.config4(scale=args.scale)
+    # a dedicated (non-default) stream shared by torch (events, NCCL) and the library
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    m = ScanMatcherNDT.from_params(w.params, device=local_rank, stream=stream.cuda_stream)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    na, nl = m.search_shape()
+    n_pts = min(int(w.params["laser_max_beams"]), int(w.query_points.shape[0]))
+    total_candidates = na * nl * nl
+    lo, hi = (na * rank) // world, (na * (rank + 1)) // world
+    my_candidates = (hi - lo) * nl * nl
+
+    gathered = torch.zeros(world * 16, dtype=torch.float64, device=dev)
+    mine = gathered[rank * 16:(rank + 1) * 16]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        """Inputs resident in HBM: launch this rank's theta slices, exchange, combine."""
+        m.search_staged(lo, hi, mine.data_ptr())
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, mine.clone())
+
+    def e2e_step():
+        """Through the C ABI with host buffers: H2D scan + search (+ exchange) + D2H result."""
+        if world == 1:
+            return m.match_scan_raw(w.query_pose, w.query_points)[:4]
+        m.stage_scan(w.query_pose, w.query_points)
+        m.search_staged(lo, hi, mine.data_ptr())
+        dist.all_gather_into_tensor(gathered, mine.clone())
+        return m.combine_device(gathered.data_ptr(), world)
+
+    # ---- device-resident timing
+    m.stage_scan(w.query_pose, w.query_points)
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    c0 = m.counters()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush, outside the per-step event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        device_step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = m.counters()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = total_candidates / (ms_per_step * 1e-3)
+    launches = (c1["launches"] - c0["launches"]) // max(args.steps, 1)
+
+    # result of the timed search (every rank combines the same gathered records)
+    score, delta, written, cov = m.combine_device(gathered.data_ptr(), world)
+
+    # ---- end-to-end timing (host buffers, copies inside)
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    c0 = m.counters()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    c1 = m.counters()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = total_candidates * args.steps / e2e_s
+    h2d = (c1["h2d_bytes"] - c0["h2d_bytes"]) // args.steps
+    d2h = (c1["d2h_bytes"] - c0["d2h_bytes"]) // args.steps
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    kernel_ms = ms_per_step  # the search kernel is the step (final reduce is a few microseconds)
+    achieved = my_candidates * n_pts * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("search_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- parity of the timed result against the oracle on a bounded window around the winner
+    parity = {"checked": False}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu, parity = cpu_baseline_and_parity(w, m, (score, delta, written, cov), args)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "config4_large_search (BASELINE.json configs[3]): 1080-beam scan vs 10-scan NDT "
+                        "@0.25 m, +-2 m @0.01 m, +-pi @0.002 rad" + ("" if args.scale == 1.0 else f", window scale {args.scale}"),
+            "candidates_per_step": total_candidates, "n_angular": na, "n_linear": nl, "beams_used": n_pts,
+            "point_evaluations_per_step": total_candidates * n_pts,
+            "parallelism": f"theta-sliced x{world}" if world > 1 else "single GPU",
+            "l2_flush": "256 MiB memset between steps, outside the per-step CUDA event pairs",
+            "matchScan_latency_ms": ms_per_step,
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "matchScan_latency_ms": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 32 B x (candidate, point) evaluations of this rank; the "
+                             "cell table is shared-memory/L2 resident so DRAM traffic is ~0 and frac can "
+                             "exceed 1 -- see DESIGN.md"},
+        "wall_s_timed_region": wall,
+        "parity": parity,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_other:
+        try:
+            line["other_workloads"] = other_workloads(torch, local_rank)
+        except Exception as e:  # never lose the headline because a side measurement failed
+            line["other_workloads"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_and_parity(w, m, result, args):
+    """cpu_baseline: single-threaded reference on a bounded theta sample (rank 0, N=1).
+    parity: the reference's matchScan on a window centred on the device's winner must
+    find the same candidate with the same score."""
+    from oracle import binding as B
+    n_theta = 4
+    value, dt, kind, cands = reference_sample(w, n_theta, 1)
+    cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{n_theta} of 3142 theta slices x 400 x 400 candidates x 1080 beams "
+                     f"({cands} candidates, {dt:.1f} s), single thread, g++ -O3"}
+    score, delta, written, cov = result
+    parity = {"checked": False}
+    if written:
+        o = B.load_oracle()
+        mo = o.new_matcher(w.params)
+        mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+        dth, _ = m.search_values()
+        it = int(np.argmin(np.abs(dth - delta[2])))
+        lo, hi = max(0, it - 1), min(len(dth), it + 2)
+        s_o, ncand, d_o, w_o, _ = mo.match_scan_window(w.query_pose, w.query_points, lo, hi)
+        n_pts = min(int(w.params["laser_max_beams"]), int(w.query_points.shape[0]))
+        parity = {"checked": True, "window_theta": [lo, hi], "oracle_score": s_o, "device_score": score,
+                  "rel_err": abs(s_o - score) / abs(s_o) if s_o else None,
+                  "same_pose": bool(np.array_equal(d_o, delta)), "oracle_delta": d_o.tolist(),
+                  "device_delta": [float(x) for x in delta]}
+    return cpu, parity
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the search window (debug only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,7 +169,7 @@ struct ndt2d_matcher
 
   bool has_model = false;
   GridDesc g{};
-  DeviceBuffer d_occ, d_rec, d_thr, d_nvalid;
+  DeviceBuffer d_occ, d_occd, d_rec, d_thr, d_nvalid;
   uint32_t rec_cap = 0;
   uint32_t n_valid = 0;
 
@@ -195,6 +195,7 @@ ModelView model_view(const ndt2d_matcher * m)
   ModelView mv;
   mv.g = m->g;
   mv.occ = m->d_occ.as<uint2>();
+  mv.occ_dilated = m->d_occd.as<uint32_t>();
   mv.rec = m->d_rec.as<double>();
   mv.thr_x = m->d_thr.as<double>();
   mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 1);
@@ -211,6 +212,7 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.dlin = m->d_dlin.as<double>();
   sv.pose_x = m->pose_x;
   sv.pose_y = m->pose_y;
+  sv.linear_res = m->prm.search_linear_resolution;
   sv.n_pts = m->n_pts;
   sv.n_ang = static_cast<uint32_t>(m->dth.size());
   sv.n_lin = static_cast<uint32_t>(m->dlin.size());
@@ -265,7 +267,7 @@ int add_scans_locked(
   g.size_y = static_cast<uint32_t>(static_cast<size_t>(fy));
   const uint64_t n_cells64 = static_cast<uint64_t>(g.size_x) * g.size_y;
   const uint64_t n_padded64 = static_cast<uint64_t>(g.size_x + 2) * (g.size_y + 2);
-  if (n_padded64 >= (1ull << 31)) {return NDT2D_ERR_SIZE;}
+  if (n_padded64 >= (1ull << 28)) {return NDT2D_ERR_SIZE;}
   g.pitch = g.size_x + 2;
   g.n_cells = static_cast<uint32_t>(n_cells64);
   g.n_padded = static_cast<uint32_t>(n_padded64);
@@ -315,7 +317,9 @@ int add_scans_locked(
   if ((rc = m->d_hist.ensure(sort_blocks * 256 * sizeof(uint32_t)))) {return rc;}
   const size_t scan_n = std::max<size_t>(sort_blocks * 256, g.n_words);
   if ((rc = m->d_scantmp.ensure(((scan_n + 8191) / 8192 + 1) * sizeof(uint32_t)))) {return rc;}
-  if ((rc = m->d_occ.ensure(static_cast<size_t>(g.n_words) * sizeof(uint2)))) {return rc;}
+  // +4 words of slack: the search kernel's bulk copies round sizes up to 16 bytes
+  if ((rc = m->d_occ.ensure((static_cast<size_t>(g.n_words) + 4) * sizeof(uint2)))) {return rc;}
+  if ((rc = m->d_occd.ensure((static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t)))) {return rc;}
   if ((rc = m->d_nvalid.ensure(sizeof(uint32_t)))) {return rc;}
   const uint64_t cap64 = std::min<uint64_t>(n_cells64, n_points / 5) + 1;
   m->rec_cap = static_cast<uint32_t>(cap64);
@@ -345,8 +349,8 @@ int add_scans_locked(
   m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
 
   rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
-      m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_rec.as<double>(),
-      m->rec_cap, m->d_nvalid.as<uint32_t>(), st, &m->ctr, &m->sorted_buf);
+      m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
+      m->d_rec.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st, &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
   NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
   m->g = g;
@@ -387,7 +391,8 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   m->n_pts = static_cast<uint32_t>(n_use);
   // search scratch
   const size_t scratch = ndt2d_search_scratch_doubles(
-    static_cast<uint32_t>(n_ang), static_cast<uint32_t>(m->dlin.size()), m->prm.kernel_variant);
+    static_cast<uint32_t>(n_ang), static_cast<uint32_t>(m->dlin.size()), m->prm.ndt_resolution,
+    m->prm.search_linear_resolution);
   if ((rc = m->d_blockpart.ensure(scratch * sizeof(double)))) {return rc;}
   if ((rc = m->d_partial.ensure(32 * sizeof(double)))) {return rc;}
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
@@ -595,7 +600,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
-    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_rec, &m->d_thr, &m->d_nvalid,
+    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out};

@@ -453,6 +453,31 @@ __global__ void __launch_bounds__(128) segment_dump_kernel(
   }
 }
 
+// 32 occupancy bits starting at padded cell `pos` (may straddle two words).
+__device__ __forceinline__ uint32_t occ_bits_at(
+  const uint2 * __restrict__ occ, uint32_t n_words, uint64_t pos)
+{
+  const uint64_t w = pos >> 5;
+  const uint32_t sh = static_cast<uint32_t>(pos & 31u);
+  const uint32_t lo = w < n_words ? occ[w].x : 0u;
+  const uint32_t hi = (w + 1) < n_words ? occ[w + 1].x : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+// K3c: dilated occupancy D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1].
+// A patch of search candidates whose first candidate puts a point in padded
+// cell c can only touch those four cells (search.cu), so one D bit rejects the
+// whole patch.
+__global__ void __launch_bounds__(256) dilate_kernel(
+  GridDesc g, const uint2 * __restrict__ occ, uint32_t * __restrict__ occ_dilated)
+{
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= g.n_words) {return;}
+  const uint64_t pos = static_cast<uint64_t>(w) << 5;
+  occ_dilated[w] = occ_bits_at(occ, g.n_words, pos) | occ_bits_at(occ, g.n_words, pos + 1) |
+    occ_bits_at(occ, g.n_words, pos + g.pitch) | occ_bits_at(occ, g.n_words, pos + g.pitch + 1);
+}
+
 int bits_needed(uint32_t max_value)
 {
   int b = 1;
@@ -470,10 +495,12 @@ int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
 
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
-  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, double * d_rec,
-  uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr, int * sorted_buf)
+  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
+  double * d_rec, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr,
+  int * sorted_buf)
 {
-  NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, static_cast<size_t>(g.n_words) * sizeof(uint2), stream));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint2), stream));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ_dilated, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, sizeof(uint32_t), stream));
   int cur = 0;
   if (n_points > 0) {
@@ -503,6 +530,8 @@ int ndt2d_launch_build(
   {
     const int rc = launch_scan<1>(d_occ, g.n_words, s.scan_tmp, stream, ctr);
     if (rc != NDT2D_OK) {return rc;}
+    dilate_kernel<<<(g.n_words + 255) / 256, 256, 0, stream>>>(g, d_occ, d_occ_dilated);
+    NDT2D_LAUNCH_CHECK(ctr);
   }
   if (n_points > 0) {
     const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);

@@ -38,6 +38,7 @@ struct ModelView
 {
   GridDesc g;
   const uint2 * occ;
+  const uint32_t * occ_dilated;  // D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1]
   const double * rec;
   const double * thr_x;  // size_x + 1 entries
   const double * thr_y;  // size_y + 1 entries
@@ -54,6 +55,7 @@ struct SearchView
   const double * dth;    // n_ang
   const double * dlin;   // n_lin
   double pose_x, pose_y;
+  double linear_res;     // search_linear_resolution (patch sizing of the tiled kernel)
   uint32_t n_pts, n_ang, n_lin;
 };
 
@@ -87,8 +89,9 @@ struct BuildScratch
 // d_pts: sensor-frame points.  Returns the index (0/1) of the sorted buffers.
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
-  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, double * d_rec,
-  uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr, int * sorted_buf);
+  const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
+  double * d_rec, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr,
+  int * sorted_buf);
 
 // Debug/parity: dense dump (16 doubles per reference cell) from the sorted
 // buffers of the last build.
@@ -104,7 +107,16 @@ int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
 // Search theta slices [theta_begin, theta_end); writes the 32-double record
 // (partial + finished outputs, see ndt2d_launch_combine) to d_partial32.  d_block_partials: scratch, >= capacity returned by
 // ndt2d_search_scratch_doubles().  d_scores (optional): per-candidate scores.
-size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, int variant);
+size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_size,
+  double linear_res);
+
+// search_tiled.cu: the production kernel (variant 0).
+size_t ndt2d_tiled_scratch_doubles(const GridDesc & g, uint32_t n_ang, uint32_t n_lin,
+  double linear_res);
+int ndt2d_launch_search_tiled(
+  const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
+  uint32_t n_theta, double * d_block_partials, double * d_scores, cudaStream_t stream,
+  Counters * ctr, uint32_t * n_blocks);
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,

@@ -21,127 +21,16 @@
 #include <stdint.h>
 
 #include "ndt2d_internal.h"
+#include "search_common.cuh"
 
 namespace
 {
 
-constexpr double kLog2e = 1.44269504088896340736;
 constexpr int kPlainThreads = 256;
 constexpr int kPlainChunk = 2048;     // outer points staged per pass (32 KB)
 constexpr int kPlainMaxBlocksX = 32;  // candidate chunks per theta slice
 
-// ------------------------------------------------------------------ lookup
-// Padded cell coordinate of x on one axis, by the reference's own arithmetic
-// (NDT::getIndex, ndt_model.cpp:205-215): 0 = below the origin,
-// size + 1 = at or beyond size.
-__device__ __forceinline__ uint32_t padded_coord_exact(
-  double v, double origin, double cell_size, uint32_t size)
-{
-  if (v < origin) {return 0u;}
-  const uint32_t gi = __double2uint_rz(__ddiv_rn(__dsub_rn(v, origin), cell_size));
-  return (gi >= size ? size : gi) + 1u;
-}
-
-// Likelihood of one map-frame point given its padded cell index: 0 for an
-// unoccupied cell, else exp(-0.5 q^T I q) (Cell::score, ndt_model.cpp:105-116).
-__device__ __forceinline__ double cell_likelihood(
-  const uint2 * __restrict__ occ, const double * __restrict__ rec, uint32_t pidx, double x,
-  double y)
-{
-  const uint2 w = occ[pidx >> 5];
-  const uint32_t bit = pidx & 31u;
-  if (((w.x >> bit) & 1u) == 0u) {return 0.0;}
-  const uint32_t rank = w.y + __popc(w.x & ((1u << bit) - 1u));
-  const double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
-  // exponent = ((-0.5 q^T) I) q with the reference's own grouping and no FMA
-  // (Eigen evaluates it left to right, ndt_model.cpp:113-114): near-singular
-  // information matrices cancel exactly where the reference's do.
-  const double qx = __dsub_rn(x, r[0]), qy = __dsub_rn(y, r[1]);
-  const double r0 = __dadd_rn(__dmul_rn(qx, r[2]), __dmul_rn(qy, r[3]));
-  const double r1 = __dadd_rn(__dmul_rn(qx, r[4]), __dmul_rn(qy, r[5]));
-  const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
-  return static_cast<double>(exp2f(static_cast<float>(e * kLog2e)));
-}
-
-__device__ __forceinline__ double point_likelihood_exact(const ModelView & mv, double x, double y)
-{
-  const uint32_t ex = padded_coord_exact(x, mv.g.origin_x, mv.g.cell_size, mv.g.size_x);
-  const uint32_t ey = padded_coord_exact(y, mv.g.origin_y, mv.g.cell_size, mv.g.size_y);
-  return cell_likelihood(mv.occ, mv.rec, ey * mv.g.pitch + ex, x, y);
-}
-
-// ------------------------------------------------------------------ reduce
-struct Best
-{
-  double score;
-  double index;
-};
-
-// strict '<' with lowest index on ties == the reference's first-wins rule
-// (scan_matcher_ndt.cpp:128); NaN never wins.
-__device__ __forceinline__ void best_merge(Best & a, double score, double index)
-{
-  if (score < a.score || (score == a.score && index < a.index)) {
-    a.score = score;
-    a.index = index;
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  }
-  return v;
-}
-
-__device__ __forceinline__ void warp_best(Best & b)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double s = __shfl_xor_sync(0xffffffffu, b.score, o);
-    const double i = __shfl_xor_sync(0xffffffffu, b.index, o);
-    best_merge(b, s, i);
-  }
-}
-
-// Block-level reduction of (best, 6 sums) into out[0..7]; all threads call.
-template<int THREADS>
-__device__ __forceinline__ void block_reduce_partial(Best b, double (&sum)[6], double * out)
-{
-  constexpr int W = THREADS / 32;
-  __shared__ double red[W][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  warp_best(b);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {sum[k] = warp_sum(sum[k]);}
-  if (lane == 0) {
-    red[warp][0] = b.score;
-    red[warp][1] = b.index;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {red[warp][2 + k] = sum[k];}
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Best t{red[0][0], red[0][1]};
-    double s[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {s[k] = red[0][2 + k];}
-    for (int w = 1; w < W; ++w) {
-      best_merge(t, red[w][0], red[w][1]);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {s[k] += red[w][2 + k];}
-    }
-    out[0] = t.score;
-    out[1] = t.index;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {out[2 + k] = s[k];}
-  }
-  __syncthreads();
-}
-
-constexpr double kNoIndex = 1.0e300;
+using namespace ndt2d_dev;
 
 // ------------------------------------------------------------------ K4, plain
 // One thread per candidate, one theta slice per blockIdx.y, reference
@@ -368,10 +257,15 @@ uint32_t plain_blocks_x(uint32_t n_lin)
 
 }  // namespace
 
-size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, int variant)
+size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_size,
+  double linear_res)
 {
-  (void)variant;
-  return static_cast<size_t>(n_ang ? n_ang : 1) * plain_blocks_x(n_lin) * NDT2D_BLOCK_PARTIAL;
+  const size_t plain =
+    static_cast<size_t>(n_ang ? n_ang : 1) * plain_blocks_x(n_lin) * NDT2D_BLOCK_PARTIAL;
+  GridDesc g{};
+  g.cell_size = cell_size;
+  const size_t tiled = ndt2d_tiled_scratch_doubles(g, n_ang, n_lin, linear_res);
+  return plain > tiled ? plain : tiled;
 }
 
 int ndt2d_launch_search(
@@ -379,13 +273,23 @@ int ndt2d_launch_search(
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
   cudaStream_t stream, Counters * ctr)
 {
-  (void)variant;
   if (theta_end <= theta_begin || sv.n_lin == 0) {
     empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
     NDT2D_LAUNCH_CHECK(ctr);
     return NDT2D_OK;
   }
   const uint32_t n_theta = theta_end - theta_begin;
+  const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
+  if (variant != 1) {
+    uint32_t n_blocks = 0;
+    const int rc = ndt2d_launch_search_tiled(mv, sv, sv.linear_res, theta_begin, n_theta,
+        d_block_partials, d_scores, stream, ctr, &n_blocks);
+    if (rc != NDT2D_OK) {return rc;}
+    search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_blocks, sv, n_candidates,
+      d_partial32);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
   uint32_t done = 0;
@@ -398,7 +302,6 @@ int ndt2d_launch_search(
     NDT2D_LAUNCH_CHECK(ctr);
     done += ny;
   }
-  const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
   search_final_kernel<<<1, 256, 0, stream>>>(
     d_block_partials, n_theta * bx, sv, n_candidates, d_partial32);
   NDT2D_LAUNCH_CHECK(ctr);
