@@ -280,7 +280,8 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    m = ScanMatcherNDT.from_params(w.params, device=local_rank, stream=stream.cuda_stream)
+    m = ScanMatcherNDT.from_params(w.params, device=local_rank, stream=stream.cuda_stream,
+                                   kernel_variant=args.variant)
     m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
     na, nl = m.search_shape()
     n_pts = min(int(w.params["laser_max_beams"]), int(w.query_points.shape[0]))
@@ -459,6 +460,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the search window (debug only)")
+    ap.add_argument("--variant", type=int, default=0, help="search kernel variant (A/B runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()

@@ -60,8 +60,10 @@ typedef struct ndt2d_params
   double range_max;                  /* initialize(..., range_max) */
   int device;                        /* CUDA device ordinal, -1 = current device */
   void * stream;                     /* cudaStream_t to run on; NULL = handle-owned stream */
-  int kernel_variant;                /* 0 = auto (fastest), 1 = plain per-candidate search
-                                        kernel (kept as an on-device cross-check) */
+  int kernel_variant;                /* 0 = production search kernel (warp-per-region),
+                                        1 = plain per-candidate kernel (reference arithmetic
+                                        per evaluation; the on-device cross-check),
+                                        2 = previous tiled kernel (A/B runs) */
 } ndt2d_params;
 
 typedef struct ndt2d_matcher ndt2d_matcher;

@@ -180,7 +180,7 @@ struct ndt2d_matcher
   int sorted_buf = 0;
 
   bool staged = false;
-  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out;
+  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter;
   double pose_x = 0, pose_y = 0;
   uint32_t n_pts = 0;
 
@@ -395,6 +395,7 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
     m->prm.search_linear_resolution);
   if ((rc = m->d_blockpart.ensure(scratch * sizeof(double)))) {return rc;}
   if ((rc = m->d_partial.ensure(32 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_counter.ensure(64))) {return rc;}
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
   // the pinned staging area is reused by the next call: wait for the copies
   NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
@@ -435,7 +436,7 @@ int match_scan_locked(
   if (rc) {return rc;}
   rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(m->dth.size()),
       m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(), nullptr,
-      m->stream, &m->ctr);
+      m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
   if (rc) {return rc;}
   double r32[32];
   if ((rc = fetch_result_locked(m, r32))) {return rc;}
@@ -603,7 +604,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
-      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out};
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();
@@ -760,7 +761,7 @@ NDT2D_API int ndt2d_matcher_search_staged(
   DeviceGuard guard(m->device);
   int rc = ndt2d_launch_search(model_view(m), search_view(m), static_cast<uint32_t>(theta_begin),
       static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
-      m->d_partial.as<double>(), nullptr, m->stream, &m->ctr);
+      m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
   if (rc) {return rc;}
   if (d_partial) {
     NDT2D_CUDA_TRY(cudaMemcpyAsync(d_partial, m->d_partial.p,
@@ -919,7 +920,7 @@ NDT2D_API int ndt2d_matcher_dump_scores(
   if ((rc = tmp.ensure(n_out * sizeof(double)))) {return rc;}
   rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(n_ang),
       m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(),
-      tmp.as<double>(), m->stream, &m->ctr);
+      tmp.as<double>(), m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(out, tmp.p, n_out * sizeof(double), cudaMemcpyDeviceToHost,
         m->stream);

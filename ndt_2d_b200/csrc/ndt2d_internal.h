@@ -110,17 +110,25 @@ int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
 size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_size,
   double linear_res);
 
-// search_tiled.cu: the production kernel (variant 0).
+// search_tiled.cu: the previous production kernel (variant 2, kept for A/B runs).
 size_t ndt2d_tiled_scratch_doubles(const GridDesc & g, uint32_t n_ang, uint32_t n_lin,
   double linear_res);
 int ndt2d_launch_search_tiled(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_block_partials, double * d_scores, cudaStream_t stream,
   Counters * ctr, uint32_t * n_blocks);
+// search_region.cu: the production kernel (variant 0): one warp per
+// (theta, region of candidates) job, jobs handed out through *d_counter.
+size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res);
+int ndt2d_launch_search_region(
+  const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
+  uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
+  cudaStream_t stream, Counters * ctr, uint32_t * n_jobs);
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
-  cudaStream_t stream, Counters * ctr);
+  uint32_t * d_counter, cudaStream_t stream, Counters * ctr);
 
 // Combine n 16-double partial records (device) into one 32-double record
 // (device): [0..15] partial, [16..18] delta, [19] delta_written,

@@ -265,13 +265,15 @@ size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_
   GridDesc g{};
   g.cell_size = cell_size;
   const size_t tiled = ndt2d_tiled_scratch_doubles(g, n_ang, n_lin, linear_res);
-  return plain > tiled ? plain : tiled;
+  const size_t region = ndt2d_region_scratch_doubles(cell_size, n_ang, n_lin, linear_res);
+  const size_t a = plain > tiled ? plain : tiled;
+  return a > region ? a : region;
 }
 
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
-  cudaStream_t stream, Counters * ctr)
+  uint32_t * d_counter, cudaStream_t stream, Counters * ctr)
 {
   if (theta_end <= theta_begin || sv.n_lin == 0) {
     empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
@@ -280,7 +282,17 @@ int ndt2d_launch_search(
   }
   const uint32_t n_theta = theta_end - theta_begin;
   const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
-  if (variant != 1) {
+  if (variant != 1 && variant != 2) {
+    uint32_t n_jobs = 0;
+    const int rc = ndt2d_launch_search_region(mv, sv, sv.linear_res, theta_begin, n_theta,
+        d_block_partials, d_scores, d_counter, stream, ctr, &n_jobs);
+    if (rc != NDT2D_OK) {return rc;}
+    search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_jobs, sv, n_candidates,
+      d_partial32);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
+  if (variant == 2) {
     uint32_t n_blocks = 0;
     const int rc = ndt2d_launch_search_tiled(mv, sv, sv.linear_res, theta_begin, n_theta,
         d_block_partials, d_scores, stream, ctr, &n_blocks);

@@ -1,0 +1,408 @@
+// search_region.cu -- the production correlative-search kernel (K4).
+//
+// Replaces the three nested loops of ScanMatcherNDT::matchScan
+// (scan_matcher_ndt.cpp:103-143) and, inside them, NDT::likelihood /
+// NDT::getIndex / Cell::score (ndt_model.cpp:105-116, 162-187, 203-218).
+//
+// Work decomposition
+//   job    = (theta slice, REGION of Rw x Rw adjacent (dx, dy) candidates),
+//            Rw chosen so that (Rw - 1) * search_linear_resolution < cell size:
+//            for a fixed scan point the candidates of a region can only put it
+//            into the 2 x 2 cells starting at the cell of the region's first
+//            candidate.
+//   warp   = one job at a time, taken from a global atomic job counter
+//            (persistent CTAs, dynamic balance: job cost varies with how much
+//            of the scan overlaps the map).  Warps never synchronise with each
+//            other inside the job loop.
+//   scan   = 32 scan points per step, one per lane: rotate + translate with the
+//            reference's own operation order (scan_matcher_ndt.cpp:111-114),
+//            padded cell coordinate of the region's first candidate from the
+//            host-tabulated thresholds (bit-exact, no division), one bit test
+//            in the DILATED occupancy bitmap D[c] = E[c]|E[c+1]|E[c+pitch]|
+//            E[c+pitch+1].  A clear bit rejects the point for all Rw*Rw
+//            candidates at once -- most of a large search is empty space.
+//   item   = a (point, region) pair whose D bit is set, processed by the whole
+//            warp: lanes compute the exact candidate coordinates of the
+//            region's columns / rows (one __dadd_rn each), a ballot against the
+//            next threshold gives the exact split of the region between the
+//            2 x 2 cells, and for every OCCUPIED cell the candidates of its
+//            sub-rectangle are flattened over the 32 lanes -- every lane
+//            evaluates a Gaussian that the reference evaluates too.
+//   sums   = per-candidate score sums live in shared memory, private to the
+//            warp (Rw*Rw doubles), accumulated in scan-point order.
+//
+// Staging: D and the threshold tables are bulk-copied into shared memory once
+// per CTA with cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier when
+// they fit; E (+ rank prefix) and the 48-byte cell records are read with
+// warp-uniform loads through L1.  DRAM traffic is a few hundred KB per launch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ndt2d_internal.h"
+#include "search_common.cuh"
+
+namespace
+{
+
+using namespace ndt2d_dev;
+
+constexpr uint32_t kMaxRw = 25;                 // region side (candidates)
+constexpr uint32_t kWarps = 8;                  // warps per CTA
+constexpr uint32_t kAccDoubles = kMaxRw * kMaxRw;
+constexpr uint32_t kWarpSmemDoubles = kAccDoubles + 64 + 7;  // acc + xs[32] + ys[32] (+ pad)
+constexpr size_t kSmemTabBudget = 96 * 1024;    // D + thresholds in shared memory up to this
+constexpr uint32_t kCtasPerSm = 4;
+constexpr uint32_t kTargetJobs = 148 * kWarps * 2;  // shrink regions of small searches
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void * p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+    "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void * dst, const void * src, uint32_t bytes,
+  uint64_t * bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t phase)
+{
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  }
+}
+// 2^x on the special-function unit; results below 2^-126 flush to zero (the
+// parity tests carry the matching absolute floor).
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct RegionPlan
+{
+  uint32_t Rw;        // region side
+  uint32_t Q;         // regions per axis
+  uint32_t n_jobs;    // n_theta * Q * Q
+  uint32_t thr_doubles;  // size_x + 1 + size_y + 1
+  uint32_t tab_bytes; // D + thresholds, 16-byte rounded (0 = keep in global memory)
+  bool smem_tab;
+  uint32_t grid;
+  size_t smem_bytes;
+};
+
+// Padded coordinate pc(v) = #{k in [0, size] : thr[k] <= v}  (0 = below the
+// origin, size + 1 = beyond the grid).  The product with 1/cell only provides a
+// starting guess; the answer is fixed by the thresholds, which the host derived
+// from the reference's own arithmetic (api.cu: axis_thresholds).
+template<bool SMEM>
+__device__ __forceinline__ uint32_t padded_coord(
+  double v, const double * __restrict__ thr, uint32_t size, double origin, double inv_cell)
+{
+  if (!(v >= thr[0])) {return 0u;}
+  const double q = (v - origin) * inv_cell;
+  uint32_t pc = (q >= static_cast<double>(size)) ? size : static_cast<uint32_t>(q);
+  pc += 1u;
+  while (pc <= size && v >= thr[pc]) {++pc;}
+  while (pc > 1u && v < thr[pc - 1u]) {--pc;}
+  return pc;
+}
+
+template<bool SMEM_TAB>
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+search_region_kernel(
+  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
+  uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
+  double * __restrict__ scores, uint32_t * __restrict__ job_counter)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc / xs / ys]
+  const uint32_t * occd;
+  const double * thr_x;
+  const double * thr_y;
+  unsigned char * sp = smem_raw + 16;
+  if (SMEM_TAB) {
+    occd = reinterpret_cast<const uint32_t *>(sp);
+    sp += tab_d_bytes;
+    thr_x = reinterpret_cast<const double *>(sp);
+    thr_y = thr_x + (mv.g.size_x + 1);
+    sp += tab_thr_bytes;
+    if (threadIdx.x == 0) {
+      mbar_init(mbar, 1);
+      mbar_expect_tx(mbar, tab_d_bytes + tab_thr_bytes);
+      bulk_copy_g2s(const_cast<uint32_t *>(occd), mv.occ_dilated, tab_d_bytes, mbar);
+      bulk_copy_g2s(const_cast<double *>(thr_x), mv.thr_x, tab_thr_bytes, mbar);
+    }
+  } else {
+    occd = mv.occ_dilated;
+    thr_x = mv.thr_x;
+    thr_y = mv.thr_y;
+  }
+  double * acc = reinterpret_cast<double *>(sp) + static_cast<size_t>(warp) * kWarpSmemDoubles;
+  double * xs = acc + kAccDoubles;
+  double * ys = xs + 32;
+
+  const uint32_t n_lin = sv.n_lin;
+  const uint32_t pitch = mv.g.pitch;
+  const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y;
+  const double inv_cell = 1.0 / mv.g.cell_size;
+  const double cell2 = mv.g.cell_size * mv.g.cell_size;
+  const double origin_x = mv.g.origin_x, origin_y = mv.g.origin_y;
+  const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
+  const uint32_t QQ = Q * Q;
+  const uint32_t RR = Rw * Rw;
+  const uint32_t inv_rw = 65536u / Rw + 1u;
+
+  if (SMEM_TAB) {
+    __syncthreads();       // mbarrier initialised before anyone polls it
+    mbar_wait(mbar, 0);
+  }
+
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) {job = atomicAdd(job_counter, 1u);}
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= n_jobs) {break;}
+    const uint32_t it = job / QQ, rr = job - it * QQ;
+    const uint32_t rx = rr / Q, ry = rr - rx * Q;
+    const uint32_t itheta = theta_begin + it;
+    const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
+    const uint32_t nxc = min(Rw, n_lin - jx0), nyc = min(Rw, n_lin - jy0);  // columns / rows
+    const double2 cs = sv.trig[itheta];
+    const double my_dlx = sv.dlin[jx0 + min(lane, nxc - 1u)];
+    const double my_dly = sv.dlin[jy0 + min(lane, nyc - 1u)];
+    const double dlx0 = __shfl_sync(0xffffffffu, my_dlx, 0);
+    const double dly0 = __shfl_sync(0xffffffffu, my_dly, 0);
+
+    for (uint32_t k = lane; k < RR; k += 32) {acc[k] = 0.0;}
+    __syncwarp();
+
+    for (uint32_t p0 = 0; p0 < sv.n_pts; p0 += 32) {
+      const uint32_t i = p0 + lane;
+      double ox = 0.0, oy = 0.0;
+      uint32_t pcx = 0, pcy = 0, idx = 0;
+      bool hit = false;
+      if (i < sv.n_pts) {
+        const double2 p = sv.pts[i];
+        // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
+        ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
+        oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
+        pcx = padded_coord<SMEM_TAB>(__dadd_rn(ox, dlx0), thr_x, size_x, origin_x, inv_cell);
+        pcy = padded_coord<SMEM_TAB>(__dadd_rn(oy, dly0), thr_y, size_y, origin_y, inv_cell);
+        idx = pcy * pitch + pcx;
+        hit = ((occd[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        // ---- item: scan point (p0 + src) against this region
+        const double pox = __shfl_sync(0xffffffffu, ox, src);
+        const double poy = __shfl_sync(0xffffffffu, oy, src);
+        const uint32_t bx = __shfl_sync(0xffffffffu, pcx, src);
+        const uint32_t by = __shfl_sync(0xffffffffu, pcy, src);
+        const uint32_t base = by * pitch + bx;
+        // exact candidate coordinates (scan_matcher_ndt.cpp:123-124), lane = column / row
+        const double xa = __dadd_rn(pox, my_dlx), ya = __dadd_rn(poy, my_dly);
+        // columns / rows still in the first cell: below the next threshold
+        const bool in_x0 = (bx > size_x) || (xa < thr_x[min(bx, size_x)]);
+        const bool in_y0 = (by > size_y) || (ya < thr_y[min(by, size_y)]);
+        const uint32_t nx = __popc(__ballot_sync(0xffffffffu, lane < nxc && in_x0));
+        const uint32_t ny = __popc(__ballot_sync(0xffffffffu, lane < nyc && in_y0));
+        xs[lane] = xa;
+        ys[lane] = ya;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t v = 0; v < 4; ++v) {
+          const uint32_t vx = v & 1u, vy = v >> 1;
+          const uint32_t cx0 = vx ? nx : 0u, w = vx ? nxc - nx : nx;
+          const uint32_t cy0 = vy ? ny : 0u, h = vy ? nyc - ny : ny;
+          if (w == 0u || h == 0u) {continue;}
+          const uint32_t cidx = base + vx + vy * pitch;
+          const uint2 ow = __ldg(mv.occ + (cidx >> 5));
+          const uint32_t bit = cidx & 31u;
+          if (((ow.x >> bit) & 1u) == 0u) {continue;}
+          const uint32_t rank = ow.y + __popc(ow.x & ((1u << bit) - 1u));
+          const double2 * r2 = reinterpret_cast<const double2 *>(
+            mv.rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+          const double2 mean = __ldg(r2), i0010 = __ldg(r2 + 1), i0111 = __ldg(r2 + 2);
+          const uint32_t cnt = w * h;
+          const uint32_t inv_h = 65536u / h + 1u;
+          // A well-conditioned information matrix takes the short form
+          //   log2 L = q^T (-0.5 log2(e) I) q = qx (A qx + B qy) + (D qy) qy,
+          // whose rounding differs from the reference's by < 1e-7 absolute in the
+          // exponent when max|I| * cell^2 <= 1e7.  Anything stiffer (a cluster of
+          // near-identical points: |I| ~ 1e17, or inf / NaN) is evaluated with the
+          // reference's own grouping ((q^T I) q, ndt_model.cpp:113-114) and no FMA,
+          // so that it cancels exactly where the reference cancels.
+          const double mag = fmax(fmax(fabs(i0010.x), fabs(i0111.y)),
+              fmax(fabs(i0010.y), fabs(i0111.x)));
+          if (mag * cell2 <= 1.0e7) {
+            const double A = i0010.x * kLog2e, B = (i0010.y + i0111.x) * kLog2e,
+              D = i0111.y * kLog2e;
+            for (uint32_t k = lane; k < cnt; k += 32) {
+              const uint32_t ar = (k * inv_h) >> 16;
+              const uint32_t a = cx0 + ar, b = cy0 + (k - ar * h);
+              const double qx = xs[a] - mean.x, qy = ys[b] - mean.y;
+              const double e = qx * (A * qx + B * qy) + (D * qy) * qy;
+              acc[a * Rw + b] += static_cast<double>(ex2_ftz(static_cast<float>(e)));
+            }
+          } else {
+            for (uint32_t k = lane; k < cnt; k += 32) {
+              const uint32_t ar = (k * inv_h) >> 16;
+              const uint32_t a = cx0 + ar, b = cy0 + (k - ar * h);
+              const double qx = __dsub_rn(xs[a], mean.x), qy = __dsub_rn(ys[b], mean.y);
+              const double r0 = __dadd_rn(__dmul_rn(qx, i0010.x), __dmul_rn(qy, i0010.y));
+              const double r1 = __dadd_rn(__dmul_rn(qx, i0111.x), __dmul_rn(qy, i0111.y));
+              const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
+              acc[a * Rw + b] += static_cast<double>(exp2f(static_cast<float>(e * kLog2e)));
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- epilogue: per-candidate score, job partial
+    Best best{0.0, kNoIndex};
+    double sum[6] = {0, 0, 0, 0, 0, 0};
+    for (uint32_t k = lane; k < RR; k += 32) {
+      const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
+      if (a < nxc && b < nyc) {
+        const double score = -acc[k];
+        const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
+        const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
+          static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
+        if (scores) {scores[gi] = score;}
+        best_merge(best, score, static_cast<double>(gi));
+        sum[0] += score;
+        sum[1] += dx * score;
+        sum[2] += dy * score;
+        sum[3] += (dx * dx) * score;
+        sum[4] += (dx * dy) * score;
+        sum[5] += (dy * dy) * score;
+      }
+    }
+    warp_best(best);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {sum[k] = warp_sum(sum[k]);}
+    if (lane == 0) {
+      double * out = job_partials + static_cast<size_t>(job) * NDT2D_BLOCK_PARTIAL;
+      out[0] = best.score;
+      out[1] = best.index;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {out[2 + k] = sum[k];}
+      out[8] = sv.dth[itheta];
+    }
+    __syncwarp();
+  }
+}
+
+RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res)
+{
+  RegionPlan pl{};
+  // (Rw - 1) * step < cell keeps a region inside a 2 x 2 cell neighbourhood
+  uint32_t Rw = 1;
+  if (linear_res > 0.0 && g.cell_size > 0.0) {
+    const double ratio = g.cell_size / linear_res * (1.0 - 1e-9);
+    Rw = ratio >= static_cast<double>(kMaxRw) ? kMaxRw : static_cast<uint32_t>(ratio) + 1u;
+  }
+  if (Rw > kMaxRw) {Rw = kMaxRw;}
+  if (Rw > n_lin) {Rw = n_lin ? n_lin : 1u;}
+  // small searches: more, smaller regions so that every SM gets work
+  for (;;) {
+    const uint32_t q = (n_lin + Rw - 1) / Rw;
+    if (static_cast<uint64_t>(n_theta) * q * q >= kTargetJobs || Rw <= 6) {break;}
+    Rw = (Rw + 1) / 2;
+  }
+  pl.Rw = Rw;
+  pl.Q = (n_lin + Rw - 1) / Rw;
+  pl.n_jobs = n_theta * pl.Q * pl.Q;
+  pl.thr_doubles = g.size_x + 1 + g.size_y + 1;
+  const size_t d_bytes = (static_cast<size_t>(g.n_words) * 4 + 15) & ~size_t(15);
+  const size_t t_bytes = (static_cast<size_t>(pl.thr_doubles) * 8 + 15) & ~size_t(15);
+  pl.smem_tab = d_bytes + t_bytes <= kSmemTabBudget;
+  pl.tab_bytes = pl.smem_tab ? static_cast<uint32_t>(d_bytes + t_bytes) : 0u;
+  pl.smem_bytes = 16 + pl.tab_bytes + sizeof(double) * kWarpSmemDoubles * kWarps;
+  return pl;
+}
+
+template<bool S>
+int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
+  uint32_t theta_begin, double * d_job_partials, double * d_scores, uint32_t * d_counter,
+  cudaStream_t stream, Counters * ctr)
+{
+  auto kernel = search_region_kernel<S>;
+  NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static_cast<int>(pl.smem_bytes)));
+  int dev = 0, sms = 148, per_sm = 1;
+  NDT2D_CUDA_TRY(cudaGetDevice(&dev));
+  NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  NDT2D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32,
+    pl.smem_bytes));
+  if (per_sm < 1) {per_sm = 1;}
+  const uint32_t want = (pl.n_jobs + kWarps - 1) / kWarps;
+  pl.grid = min(want, static_cast<uint32_t>(sms * per_sm));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
+  const uint32_t d_bytes = pl.smem_tab ? ((mv.g.n_words * 4u + 15u) & ~15u) : 0u;
+  const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
+  kernel<<<pl.grid, kWarps * 32, pl.smem_bytes, stream>>>(
+    mv, sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, d_bytes, t_bytes, d_job_partials, d_scores,
+    d_counter);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}
+
+}  // namespace
+
+size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res)
+{
+  GridDesc g{};
+  g.cell_size = cell_size;
+  // the plan's region size shrinks with the number of theta slices searched; the
+  // scratch must hold the worst case of any theta sub-range: one slice
+  size_t worst = 0;
+  for (uint32_t nt : {1u, n_ang ? n_ang : 1u}) {
+    const RegionPlan pl = make_plan(g, nt, n_lin ? n_lin : 1, linear_res);
+    const size_t jobs = static_cast<size_t>(n_ang ? n_ang : 1) * pl.Q * pl.Q;
+    worst = jobs > worst ? jobs : worst;
+  }
+  return worst * NDT2D_BLOCK_PARTIAL + 8;
+}
+
+int ndt2d_launch_search_region(
+  const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
+  uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
+  cudaStream_t stream, Counters * ctr, uint32_t * n_jobs)
+{
+  RegionPlan pl = make_plan(mv.g, n_theta, sv.n_lin, linear_res);
+  *n_jobs = pl.n_jobs;
+  return pl.smem_tab
+         ? launch_one<true>(pl, mv, sv, theta_begin, d_job_partials, d_scores, d_counter, stream, ctr)
+         : launch_one<false>(pl, mv, sv, theta_begin, d_job_partials, d_scores, d_counter, stream,
+           ctr);
+}
