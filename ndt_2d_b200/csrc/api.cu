@@ -169,7 +169,7 @@ struct ndt2d_matcher
 
   bool has_model = false;
   GridDesc g{};
-  DeviceBuffer d_occ, d_occd, d_rec, d_thr, d_nvalid;
+  DeviceBuffer d_occ, d_occd, d_rec, d_rec_fast, d_thr, d_nvalid;
   uint32_t rec_cap = 0;
   uint32_t n_valid = 0;
 
@@ -197,6 +197,7 @@ ModelView model_view(const ndt2d_matcher * m)
   mv.occ = m->d_occ.as<uint2>();
   mv.occ_dilated = m->d_occd.as<uint32_t>();
   mv.rec = m->d_rec.as<double>();
+  mv.rec_fast = m->d_rec_fast.as<double>();
   mv.thr_x = m->d_thr.as<double>();
   mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 1);
   mv.n_valid_cap = m->rec_cap;
@@ -324,6 +325,7 @@ int add_scans_locked(
   const uint64_t cap64 = std::min<uint64_t>(n_cells64, n_points / 5) + 1;
   m->rec_cap = static_cast<uint32_t>(cap64);
   if ((rc = m->d_rec.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
+  if ((rc = m->d_rec_fast.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
 
   m->bs.wx = m->d_wx.as<double>();
   m->bs.wy = m->d_wy.as<double>();
@@ -350,7 +352,8 @@ int add_scans_locked(
 
   rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
       m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
-      m->d_rec.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st, &m->ctr, &m->sorted_buf);
+      m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st,
+      &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
   NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
   m->g = g;
@@ -601,7 +604,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
-    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_thr, &m->d_nvalid,
+    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter};

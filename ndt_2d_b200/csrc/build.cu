@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128) segment_moments_kernel(
   GridDesc g, const uint32_t * __restrict__ key, const uint32_t * __restrict__ val, size_t n,
   const uint32_t * __restrict__ seglen, const double * __restrict__ wx,
   const double * __restrict__ wy, const uint2 * __restrict__ occ, double * __restrict__ rec,
-  uint32_t rec_cap, uint32_t * __restrict__ n_valid)
+  double * __restrict__ rec_fast, uint32_t rec_cap, uint32_t * __restrict__ n_valid)
 {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i == 0) {
@@ -415,6 +415,16 @@ __global__ void __launch_bounds__(128) segment_moments_kernel(
   r[3] = -0.5 * c.info[2];  // (1,0)
   r[4] = -0.5 * c.info[1];  // (0,1)
   r[5] = -0.5 * c.info[3];  // (1,1)
+  // short-form record of the search kernel (ndt2d_internal.h, ModelView::rec_fast)
+  constexpr double kLog2e = 1.44269504088896340736;
+  double * f = rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
+  const double mag = fmax(fmax(fabs(c.info[0]), fabs(c.info[3])), fmax(fabs(c.info[1]), fabs(c.info[2])));
+  f[0] = c.mean[0];
+  f[1] = c.mean[1];
+  f[2] = r[2] * kLog2e;
+  f[3] = (r[3] + r[4]) * kLog2e;
+  f[4] = r[5] * kLog2e;
+  f[5] = (mag * (g.cell_size * g.cell_size) <= 1.0e7) ? 0.0 : 1.0;  // NaN -> stiff
 }
 
 // Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.
@@ -496,8 +506,8 @@ int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
   const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
-  double * d_rec, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr,
-  int * sorted_buf)
+  double * d_rec, double * d_rec_fast, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream,
+  Counters * ctr, int * sorted_buf)
 {
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint2), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ_dilated, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t), stream));
@@ -536,7 +546,7 @@ int ndt2d_launch_build(
   if (n_points > 0) {
     const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);
     segment_moments_kernel<<<nb, 128, 0, stream>>>(
-      g, s.key[cur], s.val[cur], n_points, s.seglen, s.wx, s.wy, d_occ, d_rec, rec_cap,
+      g, s.key[cur], s.val[cur], n_points, s.seglen, s.wx, s.wy, d_occ, d_rec, d_rec_fast, rec_cap,
       d_n_valid);
     NDT2D_LAUNCH_CHECK(ctr);
   }

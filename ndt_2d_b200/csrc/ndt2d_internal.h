@@ -33,6 +33,14 @@ struct GridDesc
 //   rec[r*6] = mean_x, mean_y, -0.5*I(0,0), -0.5*I(1,0), -0.5*I(0,1), -0.5*I(1,1)
 //              of the r-th occupied cell: what Cell::score (ndt_model.cpp:113-115)
 //              needs, 48 bytes
+//   rec_fast[r*6] = mean_x, mean_y, A, B, D, stiff  with
+//              A = -0.5 log2(e) I(0,0), B = -0.5 log2(e) (I(0,1) + I(1,0)),
+//              D = -0.5 log2(e) I(1,1): log2 of the likelihood is
+//              qx (A qx + B qy) + (D qy) qy.  stiff != 0 marks cells whose
+//              information matrix is too ill-conditioned for that form to stay
+//              within 1e-7 of the reference's grouping (max|I| cell^2 > 1e7, inf
+//              or NaN); the search then evaluates them from rec[] with the
+//              reference's own operation order.
 //   thr_x[k] = smallest double x whose reference grid_x is >= k  (k=0: origin)
 struct ModelView
 {
@@ -40,6 +48,7 @@ struct ModelView
   const uint2 * occ;
   const uint32_t * occ_dilated;  // D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1]
   const double * rec;
+  const double * rec_fast;  // 6 doubles per occupied cell, see below
   const double * thr_x;  // size_x + 1 entries
   const double * thr_y;  // size_y + 1 entries
   uint32_t n_valid_cap;
@@ -90,8 +99,8 @@ struct BuildScratch
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
   const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
-  double * d_rec, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream, Counters * ctr,
-  int * sorted_buf);
+  double * d_rec, double * d_rec_fast, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream,
+  Counters * ctr, int * sorted_buf);
 
 // Debug/parity: dense dump (16 doubles per reference cell) from the sorted
 // buffers of the last build.

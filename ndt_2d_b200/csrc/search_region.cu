@@ -99,6 +99,31 @@ __device__ __forceinline__ float ex2_ftz(float x)
   return y;
 }
 
+// Small integer tables (constant memory, warp-uniform reads).
+struct Tables
+{
+  uint8_t rounds[kMaxRw + 1][kMaxRw + 1];  // [n][m] = ceil(m / (32 / n)): rounds to cover m lines
+                                           // when the lane-fixed axis has n entries
+  uint8_t div32[33];                       // 32 / n
+  uint32_t inv[33];                        // 65536 / n + 1: (k * inv[n]) >> 16 == k / n, k < 1100
+};
+constexpr Tables make_tables()
+{
+  Tables t{};
+  for (uint32_t n = 1; n <= 32; ++n) {
+    t.div32[n] = static_cast<uint8_t>(32u / n);
+    t.inv[n] = 65536u / n + 1u;
+  }
+  for (uint32_t n = 1; n <= kMaxRw; ++n) {
+    for (uint32_t m = 0; m <= kMaxRw; ++m) {
+      const uint32_t lines = 32u / n;
+      t.rounds[n][m] = static_cast<uint8_t>((m + lines - 1) / lines);
+    }
+  }
+  return t;
+}
+__constant__ Tables kTab = make_tables();
+
 struct RegionPlan
 {
   uint32_t Rw;        // region side
@@ -169,7 +194,6 @@ search_region_kernel(
   const uint32_t pitch = mv.g.pitch;
   const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y;
   const double inv_cell = 1.0 / mv.g.cell_size;
-  const double cell2 = mv.g.cell_size * mv.g.cell_size;
   const double origin_x = mv.g.origin_x, origin_y = mv.g.origin_y;
   const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
   const uint32_t QQ = Q * Q;
@@ -246,31 +270,49 @@ search_region_kernel(
           const uint32_t bit = cidx & 31u;
           if (((ow.x >> bit) & 1u) == 0u) {continue;}
           const uint32_t rank = ow.y + __popc(ow.x & ((1u << bit) - 1u));
-          const double2 * r2 = reinterpret_cast<const double2 *>(
-            mv.rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
-          const double2 mean = __ldg(r2), i0010 = __ldg(r2 + 1), i0111 = __ldg(r2 + 2);
-          const uint32_t cnt = w * h;
-          const uint32_t inv_h = 65536u / h + 1u;
-          // A well-conditioned information matrix takes the short form
-          //   log2 L = q^T (-0.5 log2(e) I) q = qx (A qx + B qy) + (D qy) qy,
-          // whose rounding differs from the reference's by < 1e-7 absolute in the
-          // exponent when max|I| * cell^2 <= 1e7.  Anything stiffer (a cluster of
-          // near-identical points: |I| ~ 1e17, or inf / NaN) is evaluated with the
-          // reference's own grouping ((q^T I) q, ndt_model.cpp:113-114) and no FMA,
-          // so that it cancels exactly where the reference cancels.
-          const double mag = fmax(fmax(fabs(i0010.x), fabs(i0111.y)),
-              fmax(fabs(i0010.y), fabs(i0111.x)));
-          if (mag * cell2 <= 1.0e7) {
-            const double A = i0010.x * kLog2e, B = (i0010.y + i0111.x) * kLog2e,
-              D = i0111.y * kLog2e;
-            for (uint32_t k = lane; k < cnt; k += 32) {
-              const uint32_t ar = (k * inv_h) >> 16;
-              const uint32_t a = cx0 + ar, b = cy0 + (k - ar * h);
-              const double qx = xs[a] - mean.x, qy = ys[b] - mean.y;
-              const double e = qx * (A * qx + B * qy) + (D * qy) * qy;
-              acc[a * Rw + b] += static_cast<double>(ex2_ftz(static_cast<float>(e)));
+          const double2 * f2 = reinterpret_cast<const double2 *>(
+            mv.rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+          const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
+          if (Ds.y == 0.0) {
+            // ---- well-conditioned cell: log2 L = qx (A qx + B qy) + (D qy) qy.
+            // One axis of the sub-rectangle is laid over the lanes and stays fixed
+            // per lane (32 / n lines of it side by side), the other is iterated:
+            // per evaluation 1 subtract + 2 FMA + ex2 + the shared-memory add.
+            // The orientation with fewer rounds is taken (table lookup).
+            const bool colmode = kTab.rounds[h][w] <= kTab.rounds[w][h];
+            const uint32_t nU = colmode ? h : w, nV = colmode ? w : h;
+            const uint32_t u0 = colmode ? cy0 : cx0, v0 = colmode ? cx0 : cy0;
+            const double * us = colmode ? ys : xs;
+            const double * vs = colmode ? xs : ys;
+            const double mean_u = colmode ? mean.y : mean.x, mean_v = colmode ? mean.x : mean.y;
+            const double Cu = colmode ? Ds.x : AB.x, Cv = colmode ? AB.x : Ds.x;
+            const uint32_t stride_u = colmode ? 1u : Rw, stride_v = colmode ? Rw : 1u;
+            const uint32_t lines = kTab.div32[nU];
+            const uint32_t lv = (lane * kTab.inv[nU]) >> 16, lu = lane - lv * nU;
+            if (lv < lines) {
+              const double qu = us[u0 + lu] - mean_u;
+              const double Bqu = AB.y * qu, Cqu2 = (Cu * qu) * qu;
+              double * ap = acc + (u0 + lu) * stride_u + (v0 + lv) * stride_v;
+              const double * vp = vs + v0 + lv;
+              const uint32_t ap_step = lines * stride_v;
+              for (uint32_t v = lv; v < nV; v += lines) {
+                const double qv = *vp - mean_v;
+                const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
+                *ap += static_cast<double>(ex2_ftz(static_cast<float>(e)));
+                vp += lines;
+                ap += ap_step;
+              }
             }
           } else {
+            // ---- stiff cell (a cluster of near-identical points: |I| ~ 1e17, or
+            // inf / NaN): the reference's own grouping ((q^T I) q,
+            // ndt_model.cpp:113-114) and no FMA, so that it cancels exactly where
+            // the reference cancels.
+            const double2 * r2 = reinterpret_cast<const double2 *>(
+              mv.rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+            const double2 i0010 = __ldg(r2 + 1), i0111 = __ldg(r2 + 2);
+            const uint32_t cnt = w * h;
+            const uint32_t inv_h = kTab.inv[h];
             for (uint32_t k = lane; k < cnt; k += 32) {
               const uint32_t ar = (k * inv_h) >> 16;
               const uint32_t a = cx0 + ar, b = cy0 + (k - ar * h);

@@ -18,6 +18,9 @@ N_OBSTACLES = 400
 SIDE_MIN, SIDE_MAX = 0.5, 4.0
 WORLD_SEED = 42
 NOISE_SIGMA = 0.01
+# order of the matcher parameters wherever they are stored as a flat vector
+PARAM_KEYS = ("ndt_resolution", "search_angular_resolution", "search_angular_size",
+              "search_linear_resolution", "search_linear_size", "laser_max_beams", "range_max")
 
 
 def uniform(seed: int, n: int) -> np.ndarray:
