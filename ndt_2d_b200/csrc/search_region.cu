@@ -48,12 +48,13 @@ namespace
 using namespace ndt2d_dev;
 
 constexpr uint32_t kMaxRw = 25;                 // region side (candidates)
-constexpr uint32_t kWarps = 8;                  // warps per CTA
-constexpr uint32_t kAccDoubles = kMaxRw * kMaxRw;
-constexpr uint32_t kWarpSmemDoubles = kAccDoubles + 64 + 7;  // acc + xs[32] + ys[32] (+ pad)
-constexpr size_t kSmemTabBudget = 96 * 1024;    // D + thresholds in shared memory up to this
-constexpr uint32_t kCtasPerSm = 4;
-constexpr uint32_t kTargetJobs = 148 * kWarps * 2;  // shrink regions of small searches
+constexpr uint32_t kWarps = 24;                 // warps per CTA; one persistent CTA per SM
+constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
+// per warp: double totals, xs[32], ys[32], float block sums (16-byte rounded)
+constexpr uint32_t kWarpSmemBytes = ((kAccEntries * 8 + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
+constexpr size_t kSmemTabBudget = 32 * 1024;    // D + thresholds in shared memory up to this
+constexpr uint32_t kFlushSteps = 2;             // 32-point steps per float accumulation block
+constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
@@ -153,8 +154,55 @@ __device__ __forceinline__ uint32_t padded_coord(
   return pc;
 }
 
+// Evaluates one occupied cell for the candidates of its sub-rectangle
+// [cx0, cx0 + w) x [cy0, cy0 + h) of the region.  Well-conditioned cells only:
+//   log2 L = qx (A qx + B qy) + (D qy) qy.
+// One axis of the sub-rectangle (U: rows if COL, else columns) is laid over the
+// lanes and stays fixed per lane, 32 / nU lines of it side by side; the other
+// (V) is iterated.  Per evaluation: 1 subtract + 2 FMA in double, ex2 and the
+// shared-memory add in float.
+template<bool COL>
+__device__ __forceinline__ void eval_cell(
+  float * __restrict__ acc_f, const double * __restrict__ xs, const double * __restrict__ ys,
+  uint32_t Rw, uint32_t cx0, uint32_t w, uint32_t cy0, uint32_t h, double2 mean, double2 AB,
+  double Dv, uint32_t lane)
+{
+  const uint32_t nU = COL ? h : w, nV = COL ? w : h;
+  const uint32_t u0 = COL ? cy0 : cx0, v0 = COL ? cx0 : cy0;
+  const double * us = COL ? ys : xs;
+  const double * vs = COL ? xs : ys;
+  const double mean_u = COL ? mean.y : mean.x, mean_v = COL ? mean.x : mean.y;
+  const double Cu = COL ? Dv : AB.x, Cv = COL ? AB.x : Dv;
+  const uint32_t lines = kTab.div32[nU];
+  const uint32_t lv = (lane * kTab.inv[nU]) >> 16, lu = lane - lv * nU;
+  if (lv < lines) {
+    const double qu = us[u0 + lu] - mean_u;
+    const double Bqu = AB.y * qu, Cqu2 = (Cu * qu) * qu;
+    float * ap = acc_f + (COL ? (u0 + lu) + (v0 + lv) * Rw : (u0 + lu) * Rw + (v0 + lv));
+    const double * vp = vs + v0 + lv;
+    const uint32_t ap_step = COL ? lines * Rw : lines;
+    for (uint32_t v = lv; v < nV; v += lines) {
+      const double qv = *vp - mean_v;
+      const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
+      *ap += ex2_ftz(static_cast<float>(e));
+      vp += lines;
+      ap += ap_step;
+    }
+  }
+}
+
+// acc_d += acc_f; acc_f = 0  (per-warp, lanes stride over the region)
+__device__ __forceinline__ void flush_block(
+  double * __restrict__ acc_d, float * __restrict__ acc_f, uint32_t RR, uint32_t lane)
+{
+  for (uint32_t k = lane; k < RR; k += 32) {
+    acc_d[k] += static_cast<double>(acc_f[k]);
+    acc_f[k] = 0.0f;
+  }
+}
+
 template<bool SMEM_TAB>
-__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+__global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
   uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
@@ -164,7 +212,7 @@ search_region_kernel(
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
-  // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc / xs / ys]
+  // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc_d / xs / ys / acc_f]
   const uint32_t * occd;
   const double * thr_x;
   const double * thr_y;
@@ -186,9 +234,10 @@ search_region_kernel(
     thr_x = mv.thr_x;
     thr_y = mv.thr_y;
   }
-  double * acc = reinterpret_cast<double *>(sp) + static_cast<size_t>(warp) * kWarpSmemDoubles;
-  double * xs = acc + kAccDoubles;
+  double * acc_d = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
+  double * xs = acc_d + kAccEntries;
   double * ys = xs + 32;
+  float * acc_f = reinterpret_cast<float *>(ys + 32);
 
   const uint32_t n_lin = sv.n_lin;
   const uint32_t pitch = mv.g.pitch;
@@ -221,13 +270,17 @@ search_region_kernel(
     const double dlx0 = __shfl_sync(0xffffffffu, my_dlx, 0);
     const double dly0 = __shfl_sync(0xffffffffu, my_dly, 0);
 
-    for (uint32_t k = lane; k < RR; k += 32) {acc[k] = 0.0;}
+    for (uint32_t k = lane; k < RR; k += 32) {
+      acc_d[k] = 0.0;
+      acc_f[k] = 0.0f;
+    }
     __syncwarp();
 
+    uint32_t dirty_steps = 0;  // steps with hits since the last flush
     for (uint32_t p0 = 0; p0 < sv.n_pts; p0 += 32) {
       const uint32_t i = p0 + lane;
       double ox = 0.0, oy = 0.0;
-      uint32_t pcx = 0, pcy = 0, idx = 0;
+      uint32_t pcx = 0, pcy = 0;
       bool hit = false;
       if (i < sv.n_pts) {
         const double2 p = sv.pts[i];
@@ -236,10 +289,11 @@ search_region_kernel(
         oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
         pcx = padded_coord<SMEM_TAB>(__dadd_rn(ox, dlx0), thr_x, size_x, origin_x, inv_cell);
         pcy = padded_coord<SMEM_TAB>(__dadd_rn(oy, dly0), thr_y, size_y, origin_y, inv_cell);
-        idx = pcy * pitch + pcx;
+        const uint32_t idx = pcy * pitch + pcx;
         hit = ((occd[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      if (mask) {++dirty_steps;}
       while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1u;
@@ -248,7 +302,6 @@ search_region_kernel(
         const double poy = __shfl_sync(0xffffffffu, oy, src);
         const uint32_t bx = __shfl_sync(0xffffffffu, pcx, src);
         const uint32_t by = __shfl_sync(0xffffffffu, pcy, src);
-        const uint32_t base = by * pitch + bx;
         // exact candidate coordinates (scan_matcher_ndt.cpp:123-124), lane = column / row
         const double xa = __dadd_rn(pox, my_dlx), ya = __dadd_rn(poy, my_dly);
         // columns / rows still in the first cell: below the next threshold
@@ -258,50 +311,39 @@ search_region_kernel(
         const uint32_t ny = __popc(__ballot_sync(0xffffffffu, lane < nyc && in_y0));
         xs[lane] = xa;
         ys[lane] = ya;
-        __syncwarp();
-#pragma unroll
-        for (uint32_t v = 0; v < 4; ++v) {
+        // the 2 x 2 cells are probed by lanes 0..3 in parallel: occupancy + record rank
+        bool occ_l = false;
+        uint32_t rank_l = 0;
+        {
+          const uint32_t pvx = lane & 1u, pvy = (lane >> 1) & 1u;
+          const uint32_t w_l = pvx ? nxc - nx : nx, h_l = pvy ? nyc - ny : ny;
+          if (lane < 4u && w_l != 0u && h_l != 0u) {
+            const uint32_t cidx = by * pitch + bx + pvx + pvy * pitch;
+            const uint2 ow = __ldg(mv.occ + (cidx >> 5));
+            const uint32_t bit = cidx & 31u;
+            occ_l = ((ow.x >> bit) & 1u) != 0u;
+            rank_l = ow.y + __popc(ow.x & ((1u << bit) - 1u));
+          }
+        }
+        const uint32_t cmask0 = __ballot_sync(0xffffffffu, occ_l);
+        __syncwarp();  // xs / ys visible to every lane
+        uint32_t cmask = cmask0;
+        while (cmask) {
+          const uint32_t v = __ffs(cmask) - 1;
+          cmask &= cmask - 1u;
+          const uint32_t rank = __shfl_sync(0xffffffffu, rank_l, v);
           const uint32_t vx = v & 1u, vy = v >> 1;
           const uint32_t cx0 = vx ? nx : 0u, w = vx ? nxc - nx : nx;
           const uint32_t cy0 = vy ? ny : 0u, h = vy ? nyc - ny : ny;
-          if (w == 0u || h == 0u) {continue;}
-          const uint32_t cidx = base + vx + vy * pitch;
-          const uint2 ow = __ldg(mv.occ + (cidx >> 5));
-          const uint32_t bit = cidx & 31u;
-          if (((ow.x >> bit) & 1u) == 0u) {continue;}
-          const uint32_t rank = ow.y + __popc(ow.x & ((1u << bit) - 1u));
           const double2 * f2 = reinterpret_cast<const double2 *>(
             mv.rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
           const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
           if (Ds.y == 0.0) {
-            // ---- well-conditioned cell: log2 L = qx (A qx + B qy) + (D qy) qy.
-            // One axis of the sub-rectangle is laid over the lanes and stays fixed
-            // per lane (32 / n lines of it side by side), the other is iterated:
-            // per evaluation 1 subtract + 2 FMA + ex2 + the shared-memory add.
-            // The orientation with fewer rounds is taken (table lookup).
-            const bool colmode = kTab.rounds[h][w] <= kTab.rounds[w][h];
-            const uint32_t nU = colmode ? h : w, nV = colmode ? w : h;
-            const uint32_t u0 = colmode ? cy0 : cx0, v0 = colmode ? cx0 : cy0;
-            const double * us = colmode ? ys : xs;
-            const double * vs = colmode ? xs : ys;
-            const double mean_u = colmode ? mean.y : mean.x, mean_v = colmode ? mean.x : mean.y;
-            const double Cu = colmode ? Ds.x : AB.x, Cv = colmode ? AB.x : Ds.x;
-            const uint32_t stride_u = colmode ? 1u : Rw, stride_v = colmode ? Rw : 1u;
-            const uint32_t lines = kTab.div32[nU];
-            const uint32_t lv = (lane * kTab.inv[nU]) >> 16, lu = lane - lv * nU;
-            if (lv < lines) {
-              const double qu = us[u0 + lu] - mean_u;
-              const double Bqu = AB.y * qu, Cqu2 = (Cu * qu) * qu;
-              double * ap = acc + (u0 + lu) * stride_u + (v0 + lv) * stride_v;
-              const double * vp = vs + v0 + lv;
-              const uint32_t ap_step = lines * stride_v;
-              for (uint32_t v = lv; v < nV; v += lines) {
-                const double qv = *vp - mean_v;
-                const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
-                *ap += static_cast<double>(ex2_ftz(static_cast<float>(e)));
-                vp += lines;
-                ap += ap_step;
-              }
+            // orientation with fewer rounds (table lookup)
+            if (kTab.rounds[h][w] <= kTab.rounds[w][h]) {
+              eval_cell<true>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
+            } else {
+              eval_cell<false>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
             }
           } else {
             // ---- stiff cell (a cluster of near-identical points: |I| ~ 1e17, or
@@ -320,12 +362,23 @@ search_region_kernel(
               const double r0 = __dadd_rn(__dmul_rn(qx, i0010.x), __dmul_rn(qy, i0010.y));
               const double r1 = __dadd_rn(__dmul_rn(qx, i0111.x), __dmul_rn(qy, i0111.y));
               const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
-              acc[a * Rw + b] += static_cast<double>(exp2f(static_cast<float>(e * kLog2e)));
+              acc_f[a * Rw + b] += exp2f(static_cast<float>(e * kLog2e));
             }
           }
         }
         __syncwarp();
       }
+      // float block sums go to the double totals every kFlushSteps steps with hits:
+      // a block sum stays below 32 * kFlushSteps, so its rounding stays ~1e-8 of a score
+      if (dirty_steps == kFlushSteps) {
+        flush_block(acc_d, acc_f, RR, lane);
+        dirty_steps = 0;
+        __syncwarp();
+      }
+    }
+    if (dirty_steps) {
+      flush_block(acc_d, acc_f, RR, lane);
+      __syncwarp();
     }
 
     // ---- epilogue: per-candidate score, job partial
@@ -334,7 +387,7 @@ search_region_kernel(
     for (uint32_t k = lane; k < RR; k += 32) {
       const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
       if (a < nxc && b < nyc) {
-        const double score = -acc[k];
+        const double score = -acc_d[k];
         const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
         const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
           static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
@@ -388,7 +441,7 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
   const size_t t_bytes = (static_cast<size_t>(pl.thr_doubles) * 8 + 15) & ~size_t(15);
   pl.smem_tab = d_bytes + t_bytes <= kSmemTabBudget;
   pl.tab_bytes = pl.smem_tab ? static_cast<uint32_t>(d_bytes + t_bytes) : 0u;
-  pl.smem_bytes = 16 + pl.tab_bytes + sizeof(double) * kWarpSmemDoubles * kWarps;
+  pl.smem_bytes = 16 + pl.tab_bytes + static_cast<size_t>(kWarpSmemBytes) * kWarps;
   return pl;
 }
 
@@ -400,14 +453,12 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   auto kernel = search_region_kernel<S>;
   NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
     static_cast<int>(pl.smem_bytes)));
-  int dev = 0, sms = 148, per_sm = 1;
+  int dev = 0, sms = 148;
   NDT2D_CUDA_TRY(cudaGetDevice(&dev));
   NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  NDT2D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32,
-    pl.smem_bytes));
-  if (per_sm < 1) {per_sm = 1;}
-  const uint32_t want = (pl.n_jobs + kWarps - 1) / kWarps;
-  pl.grid = min(want, static_cast<uint32_t>(sms * per_sm));
+  // one persistent CTA per SM; small searches still spread over all SMs (the
+  // warps of every CTA draw jobs from the same counter)
+  pl.grid = min(pl.n_jobs, static_cast<uint32_t>(sms));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
   const uint32_t d_bytes = pl.smem_tab ? ((mv.g.n_words * 4u + 15u) & ~15u) : 0u;
   const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
