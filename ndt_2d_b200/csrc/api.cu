@@ -821,7 +821,7 @@ NDT2D_API int ndt2d_combine_partials(
       }
     }
   }
-  if (out_score) {*out_score = best / npts;}
+  if (out_score) {*out_score = (written ? best : 0.0) / npts;}
   return NDT2D_OK;
 }
 

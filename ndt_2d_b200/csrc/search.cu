@@ -128,7 +128,9 @@ __device__ void finish_record(double * rec, const double * dth, const double * d
       rec[20 + r * 3 + c] = inv_s * k[r * 3 + c] + (inv_s2 * u[r]) * u[c];
     }
   }
-  rec[29] = best / n;  // :148 (n == 0 -> NaN, as in the reference)
+  // :148 (n == 0 -> NaN, as in the reference); `best` stays the +0.0 it was
+  // initialised with when no candidate scored below zero (:83,128)
+  rec[29] = (written ? best : 0.0) / n;
   rec[30] = rec[31] = 0.0;
 }
 

@@ -1,0 +1,271 @@
+// plugin_parity.cpp -- drives the REFERENCE plugin and the B200 plugin through the
+// same abstract interface (ndt_2d::ScanMatcher, scan_matcher.hpp:42-91) on identical
+// synthetic inputs, the way Mapper::laserCallback does (ndt_mapper.cpp:508-515), and
+// ndt_2d::ParticleFilter next to ndt_2d_b200::ParticleFilter.
+//
+// TEST INFRASTRUCTURE.  Built by oracle/Makefile (target plugin_parity) only where
+// /root/reference exists: the reference's sources are compiled in place, unmodified,
+// against oracle/ref_shim; the binary lands in oracle/_ref/ and travels to the GPU box.
+//
+//   plugin_parity            full comparison (needs a CUDA device), exit 0 = parity
+//   plugin_parity --no-gpu   checks that the B200 plugin fails loudly without a device
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define private public
+#include <ndt_2d/particle_filter.hpp>
+#undef private
+#include <ndt_2d/motion_model.hpp>
+#include <ndt_2d/scan_matcher_ndt.hpp>
+
+#include <ndt_2d_b200/particle_filter.hpp>
+#include <ndt_2d_b200/scan_matcher_ndt.hpp>
+
+namespace
+{
+
+int g_failures = 0;
+
+void expect(bool ok, const char * what)
+{
+  if (!ok) {
+    ++g_failures;
+    std::printf("FAIL: %s\n", what);
+  }
+}
+
+bool close_rel(double a, double b, double rtol, double atol = 0.0)
+{
+  if (std::isnan(a) || std::isnan(b)) {return std::isnan(a) && std::isnan(b);}
+  return std::fabs(a - b) <= atol + rtol * std::fabs(b);
+}
+
+const double kPi = 3.14159265358979323846;
+
+struct World
+{
+  std::vector<double> rects;
+  int n_rects = 60;
+  double arena = 100.0;
+};
+
+std::vector<ndt_2d::ScanPtr> make_scans(
+  const World & w, const std::vector<double> & poses3, int beams, double range_max, uint64_t seed)
+{
+  const size_t n = poses3.size() / 3;
+  std::vector<uint64_t> offsets(n + 1);
+  std::vector<double> pts(2 * static_cast<size_t>(beams) * n);
+  ndt2d_synth_scans(w.rects.data(), w.n_rects, w.arena, poses3.data(), n, beams, range_max, 0.01,
+    seed, offsets.data(), pts.data());
+  std::vector<ndt_2d::ScanPtr> out;
+  for (size_t k = 0; k < n; ++k) {
+    ndt_2d::ScanPtr scan(new ndt_2d::Scan(k));
+    scan->setPose(ndt_2d::Pose2d(poses3[3 * k], poses3[3 * k + 1], poses3[3 * k + 2]));
+    std::vector<ndt_2d::Point> points;
+    for (uint64_t i = offsets[k]; i < offsets[k + 1]; ++i) {
+      points.emplace_back(pts[2 * i], pts[2 * i + 1]);
+    }
+    scan->setPoints(points);
+    out.push_back(scan);
+  }
+  return out;
+}
+
+void compare_match(
+  const ndt_2d::ScanMatcherPtr & ref, const ndt_2d::ScanMatcherPtr & dev, const ndt_2d::ScanPtr & scan,
+  const char * label)
+{
+  // both start from a default pose and an "uninitialised" covariance, as the node's callers do
+  ndt_2d::Pose2d pr, pd;
+  Eigen::Matrix3d cr, cd;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {cr(r, c) = cd(r, c) = 7.0;}
+  }
+  const double sr = ref->matchScan(scan, pr, cr);
+  const double sd = dev->matchScan(scan, pd, cd);
+  std::printf("%s: matchScan ref %.12g dev %.12g  pose ref (%.6f %.6f %.6f) dev (%.6f %.6f %.6f)\n",
+    label, sr, sd, pr.x, pr.y, pr.theta, pd.x, pd.y, pd.theta);
+  expect(close_rel(sd, sr, 1e-5, 1e-30), "matchScan score within 1e-5");
+  expect(pr.x == pd.x && pr.y == pd.y && pr.theta == pd.theta, "matchScan pose identical");
+  double cmax = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      if (std::isfinite(cr(r, c))) {cmax = std::fmax(cmax, std::fabs(cr(r, c)));}
+    }
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      expect(close_rel(cd(r, c), cr(r, c), 1e-5, 1e-5 * cmax), "matchScan covariance within 1e-5");
+    }
+  }
+  const double qr = ref->scoreScan(scan), qd = dev->scoreScan(scan);
+  expect(close_rel(qd, qr, 1e-5, 1e-30), "scoreScan within 1e-5");
+}
+
+int run_no_gpu()
+{
+  rclcpp::Node node;
+  ndt_2d_b200::ScanMatcherNDT m;
+  bool threw = false;
+  try {
+    m.initialize("local_scan_matcher", &node, 10.0);
+  } catch (const std::runtime_error & e) {
+    threw = true;
+    std::printf("initialize without a device: %s\n", e.what());
+  }
+  if (ndt2d_device_count() > 0) {
+    std::printf("a CUDA device is visible; --no-gpu check not applicable\n");
+    return 0;
+  }
+  return threw ? 0 : 1;
+}
+
+}  // namespace
+
+int main(int argc, char ** argv)
+{
+  if (argc > 1 && !std::strcmp(argv[1], "--no-gpu")) {return run_no_gpu();}
+
+  World w;
+  w.rects.resize(4 * w.n_rects);
+  ndt2d_synth_world(42, w.arena, w.n_rects, 1.0, 8.0, w.rects.data());
+
+  // ---- mapping: rolling window of 10 scans + the 11th matched against it -----------
+  std::vector<double> poses;
+  for (int k = 0; k < 11; ++k) {
+    poses.push_back(50.0 + 0.2 * k);
+    poses.push_back(50.0);
+    poses.push_back(0.01 * ((k * 7) % 11 - 5));
+  }
+  std::vector<ndt_2d::ScanPtr> scans = make_scans(w, poses, 360, 10.0, 43);
+  ndt_2d::ScanPtr query = scans.back();
+  scans.pop_back();
+  const ndt_2d::Pose2d truth = query->getPose();
+  query->setPose(ndt_2d::Pose2d(truth.x - 0.12, truth.y + 0.07, truth.theta - 0.06));
+
+  rclcpp::Node node;  // the params file: config 1 of BASELINE.json
+  node.overrides["local_scan_matcher.ndt_resolution"] = 0.25;
+  node.overrides["local_scan_matcher.search_linear_size"] = 0.25;
+  node.overrides["local_scan_matcher.search_linear_resolution"] = 0.05;
+  node.overrides["local_scan_matcher.search_angular_size"] = 0.25;
+  node.overrides["local_scan_matcher.search_angular_resolution"] = 0.0025;
+  node.overrides["local_scan_matcher.laser_max_beams"] = 360;
+
+  ndt_2d::ScanMatcherPtr ref(new ndt_2d::ScanMatcherNDT());
+  ndt_2d::ScanMatcherPtr dev(new ndt_2d_b200::ScanMatcherNDT());
+  for (auto & m : {ref, dev}) {
+    m->initialize("local_scan_matcher", &node, 10.0);
+  }
+
+  // no map yet: 0.0 and outputs untouched (scan_matcher_ndt.cpp:80,159)
+  {
+    ndt_2d::Pose2d p(1.0, 2.0, 3.0);
+    Eigen::Matrix3d c;
+    for (int r = 0; r < 3; ++r) {for (int q = 0; q < 3; ++q) {c(r, q) = 7.0;}}
+    const double s = dev->matchScan(query, p, c);
+    expect(s == 0.0 && p.x == 1.0 && p.y == 2.0 && p.theta == 3.0 && c(1, 1) == 7.0,
+      "no map: matchScan returns 0.0 and leaves pose / covariance untouched");
+    expect(dev->scoreScan(query) == 0.0 && ref->scoreScan(query) == 0.0, "no map: scoreScan 0.0");
+  }
+
+  for (auto & m : {ref, dev}) {
+    m->reset();
+    m->addScans(scans.begin(), scans.end());   // ndt_mapper.cpp:508-509
+  }
+  compare_match(ref, dev, query, "config1");
+
+  // a scan nowhere near the map: every candidate scores 0, pose untouched, NaN covariance
+  {
+    ndt_2d::ScanPtr far(new ndt_2d::Scan(99));
+    far->setPose(ndt_2d::Pose2d(500.0, 500.0, 0.0));
+    far->setPoints(query->getPoints());
+    compare_match(ref, dev, far, "far scan");
+  }
+
+  // plugin defaults (no overrides): 21 x 21 x 80 candidates, 100 beams
+  {
+    rclcpp::Node defaults;
+    ndt_2d::ScanMatcherPtr r2(new ndt_2d::ScanMatcherNDT()), d2(new ndt_2d_b200::ScanMatcherNDT());
+    for (auto & m : {r2, d2}) {
+      m->initialize("global_scan_matcher", &defaults, 10.0);
+      m->addScans(scans.begin(), scans.end());
+    }
+    ndt_2d::ScanPtr q2(new ndt_2d::Scan(100));
+    q2->setPose(ndt_2d::Pose2d(truth.x - 0.02, truth.y + 0.03, truth.theta - 0.04));
+    q2->setPoints(query->getPoints());
+    compare_match(r2, d2, q2, "plugin defaults");
+  }
+
+  // ---- scorePoints at assorted poses ------------------------------------------------
+  const std::vector<ndt_2d::Point> qpts = query->getPoints();
+  for (int k = 0; k < 8; ++k) {
+    ndt_2d::Pose2d p(truth.x + 0.03 * k - 0.1, truth.y - 0.02 * k, truth.theta + 0.01 * k);
+    expect(close_rel(dev->scorePoints(qpts, p), ref->scorePoints(qpts, p), 1e-5, 1e-30),
+      "scorePoints within 1e-5");
+  }
+
+  // ---- particle filter: measure + statistics ------------------------------------------
+  {
+    const size_t P = 600;
+    std::vector<double> u(3 * P), particles(3 * P), weights(P, 1.0 / P);
+    ndt2d_synth_normal(7, 3 * P, u.data());
+    for (size_t i = 0; i < P; ++i) {
+      particles[3 * i] = truth.x + 0.3 * u[3 * i];
+      particles[3 * i + 1] = truth.y + 0.3 * u[3 * i + 1];
+      particles[3 * i + 2] = truth.theta + 0.1 * u[3 * i + 2];
+    }
+    ndt_2d::MotionModelPtr rmm(new ndt_2d::MotionModel(0.2, 0.2, 0.2, 0.2, 0.2));
+    ndt_2d::ParticleFilter rf(100, P, rmm);
+    rf.particles_.clear();
+    for (size_t i = 0; i < P; ++i) {
+      rf.particles_.emplace_back(particles[3 * i], particles[3 * i + 1], particles[3 * i + 2]);
+    }
+    rf.weights_.assign(P, 1.0 / P);
+    rf.cov_ = Eigen::Matrix3d::Zero();
+    rf.measure(ref, query);
+
+    ndt_2d_b200::MotionModelPtr dmm(new ndt_2d_b200::MotionModel(0.2, 0.2, 0.2, 0.2, 0.2));
+    ndt_2d_b200::ParticleFilter df(100, P, dmm);
+    expect(df.size() == 100, "filter starts with min_particles particles");
+    df.setParticles(particles, weights);
+    df.measure(dev, query);
+    std::vector<double> dp, dw;
+    df.getParticles(dp, dw);
+    bool w_ok = dw.size() == P;
+    for (size_t i = 0; w_ok && i < P; ++i) {w_ok = close_rel(dw[i], rf.weights_[i], 1e-5, 1e-30);}
+    expect(w_ok, "measure: normalised weights within 1e-5");
+    const Eigen::Vector3d mr = rf.getMean(), md = df.getMean();
+    const Eigen::Matrix3d cr = rf.getCovariance(), cd = df.getCovariance();
+    std::printf("filter mean ref (%.9f %.9f %.9f) dev (%.9f %.9f %.9f)\n", mr(0), mr(1), mr(2),
+      md(0), md(1), md(2));
+    for (int k = 0; k < 3; ++k) {expect(close_rel(md(k), mr(k), 1e-5, 1e-9), "filter mean");}
+    double cmax = 0.0;
+    for (int r = 0; r < 3; ++r) {for (int c = 0; c < 3; ++c) {cmax = std::fmax(cmax, std::fabs(cr(r, c)));}}
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {expect(close_rel(cd(r, c), cr(r, c), 1e-5, 1e-5 * cmax), "filter covariance");}
+    }
+    geometry_msgs::msg::PoseArray msg;
+    df.getMsg(msg);
+    expect(msg.poses.size() == P && msg.poses[3].position.x == particles[9], "getMsg");
+    // a foreign matcher cannot be scored on the device: loud failure, no host path
+    bool threw = false;
+    try {
+      df.measure(ref, query);
+    } catch (const std::invalid_argument &) {
+      threw = true;
+    }
+    expect(threw, "measure with a non-B200 matcher throws");
+    df.resample(0.01, 2.3);
+    expect(df.size() >= 100 && df.size() <= P, "resample keeps min <= n <= max");
+    (void)kPi;
+  }
+
+  std::printf("{\"plugin_parity\": \"%s\", \"failures\": %d}\n", g_failures ? "FAILED" : "ok",
+    g_failures);
+  return g_failures ? 1 : 0;
+}
