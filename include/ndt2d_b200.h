@@ -182,6 +182,17 @@ NDT2D_API int ndt2d_combine_partials(
   const ndt2d_matcher * m, const double * partials, size_t n_partials,
   double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
 
+/* The same reduction without a handle (pure host arithmetic, usable on a machine
+ * without a device): dth / dlin are the replayed lattices (ndt2d_search_lattice). */
+NDT2D_API int ndt2d_combine_partials_host(
+  const double * dth, size_t n_ang, const double * dlin, size_t n_lin, const double * partials,
+  size_t n_partials, double * out_delta3, int * delta_written, double * out_cov9,
+  double * out_score);
+/* Replays `for (v = -size; v < size; v += resolution)` (scan_matcher_ndt.cpp:103,117,
+ * 119) on the host: *n values; copied to out if out != NULL (cap entries). */
+NDT2D_API int ndt2d_search_lattice(double size, double resolution, double * out, size_t cap,
+  size_t * n);
+
 /* Same reduction on the device: d_partials points at n records in device
  * memory (e.g. the all-gather output); result fetched to the host. */
 NDT2D_API int ndt2d_matcher_combine_device(
@@ -207,6 +218,13 @@ NDT2D_API int ndt2d_matcher_dump_scores(
 /* Counters: [0] kernels launched by this handle so far, [1] H2D bytes,
  * [2] D2H bytes, [3] valid (n>=5) cells in the current model. */
 NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4);
+/* Work statistics of the last search launch of the production kernel:
+ * [0] (candidate, point) evaluations that reached an occupied cell (the Gaussians
+ *     the reference evaluates with a non-zero result), [1] (scan point, candidate
+ *     region) pairs that passed the dilated-occupancy test, [2] job counter at
+ *     exit, [3] duration of the search kernel alone in nanoseconds (CUDA events
+ *     recorded around it on the handle's stream). */
+NDT2D_API int ndt2d_matcher_search_stats(ndt2d_matcher * m, uint64_t * out4);
 /* cudaStream_t the handle runs on. */
 NDT2D_API void * ndt2d_matcher_stream(ndt2d_matcher * m);
 
@@ -264,6 +282,16 @@ NDT2D_API int ndt2d_filter_stats(ndt2d_filter * f, double * mean3, double * cov9
 NDT2D_API int ndt2d_filter_set_cov(ndt2d_filter * f, const double * cov9);
 /* Indices drawn by the last resample (out must hold size() entries). */
 NDT2D_API int ndt2d_filter_last_draws(ndt2d_filter * f, uint64_t * out);
+
+/* ------------------------------------------------------------------------
+ * Roofline probes (bench.py): measured on the device the bench runs on.
+ * ---------------------------------------------------------------------- */
+
+/* GB/s of random 32-byte record reads from a table of table_bytes (L1-, L2- or
+ * HBM-resident depending on its size): the gather roofline of SURVEY.md 8(d). */
+NDT2D_API int ndt2d_probe_gather(int device, size_t table_bytes, double * out_gbps);
+/* GB/s (read + write) of a plain device-to-device copy of `bytes`. */
+NDT2D_API int ndt2d_probe_copy(int device, size_t bytes, double * out_gbps);
 
 /* ------------------------------------------------------------------------
  * Synthetic laser world (host code; shared by tests and bench so that the

@@ -72,13 +72,19 @@ SIGNATURES = {
     "ndt2d_matcher_search_staged": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "ndt2d_matcher_fetch_partial": (C.c_int, [_vp, _dp]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
+    "ndt2d_combine_partials_host": (
+        C.c_int, [_dp, C.c_size_t, _dp, C.c_size_t, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
+    "ndt2d_search_lattice": (C.c_int, [C.c_double, C.c_double, _dp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ndt2d_matcher_combine_device": (C.c_int, [_vp, _vp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_matcher_grid_info": (C.c_int, [_vp, _dp]),
     "ndt2d_matcher_dump_cells": (C.c_int, [_vp, _dp]),
     "ndt2d_matcher_dump_keys": (C.c_int, [_vp, _i32p, C.c_size_t]),
     "ndt2d_matcher_dump_scores": (C.c_int, [_vp, _dp, _dp, C.c_size_t, _dp, C.c_size_t]),
     "ndt2d_matcher_counters": (C.c_int, [_vp, _u64p]),
+    "ndt2d_matcher_search_stats": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_stream": (_vp, [_vp]),
+    "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
+    "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_filter_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, _vp, C.POINTER(_vp)]),
     "ndt2d_filter_destroy": (C.c_int, [_vp]),
     "ndt2d_filter_set_particles": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),

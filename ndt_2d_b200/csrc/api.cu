@@ -185,6 +185,8 @@ struct ndt2d_matcher
   uint32_t n_pts = 0;
 
   PinnedBuffer h_stage, h_result;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the last search kernel
+  bool ev_valid = false;
 };
 
 namespace
@@ -439,8 +441,9 @@ int match_scan_locked(
   if (rc) {return rc;}
   rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(m->dth.size()),
       m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(), nullptr,
-      m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
+      m->d_counter.as<uint32_t>(), m->stream, &m->ctr, m->ev_begin, m->ev_end);
   if (rc) {return rc;}
+  m->ev_valid = true;
   double r32[32];
   if ((rc = fetch_result_locked(m, r32))) {return rc;}
   unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
@@ -578,6 +581,10 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
     }
     m->own_stream = true;
   }
+  if (cudaEventCreate(&m->ev_begin) != cudaSuccess || cudaEventCreate(&m->ev_end) != cudaSuccess) {
+    m->ev_begin = m->ev_end = nullptr;  // timing is optional
+    cudaGetLastError();
+  }
   const size_t na = m->dth.size(), nl = m->dlin.size();
   rc = m->d_dth.ensure((na ? na : 1) * sizeof(double));
   if (!rc) {rc = m->d_dlin.ensure((nl ? nl : 1) * sizeof(double));}
@@ -611,6 +618,8 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();
+    if (m->ev_begin) {cudaEventDestroy(m->ev_begin);}
+    if (m->ev_end) {cudaEventDestroy(m->ev_end);}
     if (m->own_stream && m->stream) {cudaStreamDestroy(m->stream);}
   }
   delete m;
@@ -764,8 +773,10 @@ NDT2D_API int ndt2d_matcher_search_staged(
   DeviceGuard guard(m->device);
   int rc = ndt2d_launch_search(model_view(m), search_view(m), static_cast<uint32_t>(theta_begin),
       static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
-      m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
+      m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr,
+      m->ev_begin, m->ev_end);
   if (rc) {return rc;}
+  m->ev_valid = theta_end > theta_begin;
   if (d_partial) {
     NDT2D_CUDA_TRY(cudaMemcpyAsync(d_partial, m->d_partial.p,
       NDT2D_PARTIAL_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
@@ -786,11 +797,28 @@ NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16)
   return NDT2D_OK;
 }
 
-NDT2D_API int ndt2d_combine_partials(
-  const ndt2d_matcher * m, const double * partials, size_t n_partials,
-  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+NDT2D_API int ndt2d_search_lattice(double size, double resolution, double * out, size_t cap,
+  size_t * n)
 {
-  if (!m || (n_partials && !partials)) {return NDT2D_ERR_INVALID;}
+  // `for (v = -size; v < size; v += resolution)` replayed (scan_matcher_ndt.cpp:103,117,119)
+  if (!n) {return NDT2D_ERR_INVALID;}
+  std::vector<double> v;
+  const int rc = replay_loop(size, resolution, 1u << 24, v);
+  if (rc) {return rc;}
+  *n = v.size();
+  if (out) {
+    if (cap < v.size()) {return NDT2D_ERR_SIZE;}
+    memcpy(out, v.data(), v.size() * sizeof(double));
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_combine_partials_host(
+  const double * dth, size_t n_ang, const double * dlin, size_t n_lin, const double * partials,
+  size_t n_partials, double * out_delta3, int * delta_written, double * out_cov9,
+  double * out_score)
+{
+  if ((n_partials && !partials) || (n_ang && !dth) || (n_lin && !dlin)) {return NDT2D_ERR_INVALID;}
   double best = 0.0, best_idx = 1.0e300, s[10] = {0}, npts = 0.0;
   for (size_t r = 0; r < n_partials; ++r) {
     const double * p = partials + r * NDT2D_PARTIAL_DOUBLES;
@@ -804,14 +832,16 @@ NDT2D_API int ndt2d_combine_partials(
   const bool written = best < 0.0;
   if (delta_written) {*delta_written = written ? 1 : 0;}
   if (written && out_delta3) {
-    const uint64_t n_lin = m->dlin.size(), n_cand = n_lin * n_lin;
+    const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
     const uint64_t idx = static_cast<uint64_t>(best_idx);
     const uint64_t it = idx / n_cand, rem = idx - it * n_cand;
-    out_delta3[0] = m->dlin[rem / n_lin];
-    out_delta3[1] = m->dlin[rem % n_lin];
-    out_delta3[2] = m->dth[it];
+    if (it >= n_ang) {return NDT2D_ERR_INVALID;}
+    out_delta3[0] = dlin[rem / n_lin];
+    out_delta3[1] = dlin[rem % n_lin];
+    out_delta3[2] = dth[it];
   }
   if (out_cov9) {
+    // covariance = (1/s) k + ((1/(s*s)) u) u^T      (scan_matcher_ndt.cpp:146)
     const double sum = s[9], inv_s = 1.0 / sum, inv_s2 = 1.0 / (sum * sum);
     const double k[9] = {s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]};
     const double u[3] = {s[6], s[7], s[8]};
@@ -823,6 +853,15 @@ NDT2D_API int ndt2d_combine_partials(
   }
   if (out_score) {*out_score = (written ? best : 0.0) / npts;}
   return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_combine_partials(
+  const ndt2d_matcher * m, const double * partials, size_t n_partials,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  return ndt2d_combine_partials_host(m->dth.data(), m->dth.size(), m->dlin.data(), m->dlin.size(),
+           partials, n_partials, out_delta3, delta_written, out_cov9, out_score);
 }
 
 NDT2D_API int ndt2d_matcher_combine_device(
@@ -951,6 +990,30 @@ NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4)
     uint32_t nv = 0;
     if (cudaMemcpy(&nv, m->d_nvalid.p, sizeof(nv), cudaMemcpyDeviceToHost) == cudaSuccess) {
       out4[3] = nv;
+    }
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_search_stats(ndt2d_matcher * m, uint64_t * out4)
+{
+  if (!m || !out4) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  if (!m->d_counter.p) {return NDT2D_ERR_STATE;}
+  DeviceGuard guard(m->device);
+  uint64_t h[4] = {0, 0, 0, 0};
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  NDT2D_CUDA_TRY(cudaMemcpy(h, m->d_counter.p, 32, cudaMemcpyDeviceToHost));
+  out4[0] = h[1];                  // useful evaluations
+  out4[1] = h[2];                  // (point, region) items
+  out4[2] = h[0] & 0xffffffffu;    // job counter at exit (>= jobs)
+  if (m->ev_valid && m->ev_begin && m->ev_end) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end) == cudaSuccess) {
+      out4[3] = static_cast<uint64_t>(static_cast<double>(ms) * 1.0e6);  // search kernel, ns
+    } else {
+      cudaGetLastError();
     }
   }
   return NDT2D_OK;

@@ -137,7 +137,8 @@ int ndt2d_launch_search_region(
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
-  uint32_t * d_counter, cudaStream_t stream, Counters * ctr);
+  uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin = nullptr,
+  cudaEvent_t ev_end = nullptr);  // events (optional) bracket the search kernel alone
 
 // Combine n 16-double partial records (device) into one 32-double record
 // (device): [0..15] partial, [16..18] delta, [19] delta_written,

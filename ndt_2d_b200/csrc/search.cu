@@ -275,7 +275,8 @@ size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
-  uint32_t * d_counter, cudaStream_t stream, Counters * ctr)
+  uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin,
+  cudaEvent_t ev_end)
 {
   if (theta_end <= theta_begin || sv.n_lin == 0) {
     empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
@@ -286,9 +287,11 @@ int ndt2d_launch_search(
   const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
   if (variant != 1 && variant != 2) {
     uint32_t n_jobs = 0;
+    if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
     const int rc = ndt2d_launch_search_region(mv, sv, sv.linear_res, theta_begin, n_theta,
         d_block_partials, d_scores, d_counter, stream, ctr, &n_jobs);
     if (rc != NDT2D_OK) {return rc;}
+    if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_jobs, sv, n_candidates,
       d_partial32);
     NDT2D_LAUNCH_CHECK(ctr);
@@ -296,9 +299,11 @@ int ndt2d_launch_search(
   }
   if (variant == 2) {
     uint32_t n_blocks = 0;
+    if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
     const int rc = ndt2d_launch_search_tiled(mv, sv, sv.linear_res, theta_begin, n_theta,
         d_block_partials, d_scores, stream, ctr, &n_blocks);
     if (rc != NDT2D_OK) {return rc;}
+    if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_blocks, sv, n_candidates,
       d_partial32);
     NDT2D_LAUNCH_CHECK(ctr);
@@ -307,6 +312,7 @@ int ndt2d_launch_search(
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
   uint32_t done = 0;
+  if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
   while (done < n_theta) {
     const uint32_t ny = min(n_theta - done, 65535u);
     dim3 grid(bx, ny);
@@ -316,6 +322,7 @@ int ndt2d_launch_search(
     NDT2D_LAUNCH_CHECK(ctr);
     done += ny;
   }
+  if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   search_final_kernel<<<1, 256, 0, stream>>>(
     d_block_partials, n_theta * bx, sv, n_candidates, d_partial32);
   NDT2D_LAUNCH_CHECK(ctr);

@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
   uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
-  double * __restrict__ scores, uint32_t * __restrict__ job_counter)
+  double * __restrict__ scores, uint32_t * __restrict__ job_counter,
+  unsigned long long * __restrict__ stats)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned long long n_useful = 0, n_items = 0;  // warp-uniform tallies (lane 0 reports)
 
   // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc_d / xs / ys / acc_f]
   const uint32_t * occd;
@@ -297,6 +299,7 @@ search_region_kernel(
       while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1u;
+        ++n_items;
         // ---- item: scan point (p0 + src) against this region
         const double pox = __shfl_sync(0xffffffffu, ox, src);
         const double poy = __shfl_sync(0xffffffffu, oy, src);
@@ -335,6 +338,7 @@ search_region_kernel(
           const uint32_t vx = v & 1u, vy = v >> 1;
           const uint32_t cx0 = vx ? nx : 0u, w = vx ? nxc - nx : nx;
           const uint32_t cy0 = vy ? ny : 0u, h = vy ? nyc - ny : ny;
+          n_useful += w * h;
           const double2 * f2 = reinterpret_cast<const double2 *>(
             mv.rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
           const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
@@ -414,6 +418,10 @@ search_region_kernel(
     }
     __syncwarp();
   }
+  if (lane == 0 && stats) {
+    atomicAdd(stats, n_useful);      // (candidate, point) evaluations that reached an occupied cell
+    atomicAdd(stats + 1, n_items);   // (point, region) pairs that passed the dilated-bitmap test
+  }
 }
 
 RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res)
@@ -459,12 +467,13 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   // one persistent CTA per SM; small searches still spread over all SMs (the
   // warps of every CTA draw jobs from the same counter)
   pl.grid = min(pl.n_jobs, static_cast<uint32_t>(sms));
-  NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
+  // d_counter: [0] job counter (u32, + pad), [1..2] u64 statistics of this launch
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 32, stream));
   const uint32_t d_bytes = pl.smem_tab ? ((mv.g.n_words * 4u + 15u) & ~15u) : 0u;
   const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
   kernel<<<pl.grid, kWarps * 32, pl.smem_bytes, stream>>>(
     mv, sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, d_bytes, t_bytes, d_job_partials, d_scores,
-    d_counter);
+    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
 }

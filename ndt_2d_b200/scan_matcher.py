@@ -301,5 +301,12 @@ class ScanMatcherNDT:
         return dict(launches=int(out[0]), h2d_bytes=int(out[1]), d2h_bytes=int(out[2]),
                     valid_cells=int(out[3]))
 
+    def search_stats(self) -> dict:
+        """Work done by the last search launch (ndt2d_matcher_search_stats)."""
+        out = np.zeros(4, dtype=np.uint64)
+        L.check(L.lib.ndt2d_matcher_search_stats(self.handle, L.u64ptr(out)), "search_stats")
+        return dict(useful_evaluations=int(out[0]), items=int(out[1]), jobs_drawn=int(out[2]),
+                    kernel_ms=float(out[3]) * 1e-6)
+
     def stream(self) -> int:
         return int(L.lib.ndt2d_matcher_stream(self.handle) or 0)

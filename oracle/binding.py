@@ -75,6 +75,7 @@ class OracleLib:
                 "matcher_match_scan_window": (
                     C.c_double, [_vp, _dp, _dp, C.c_size_t, _dp, C.POINTER(C.c_int), _dp, _dp,
                                  C.c_size_t, C.c_size_t, _u64p]),
+                "matcher_partial": (None, [_vp, _dp, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _dp]),
                 "pf_measure": (None, [_vp, _dp, C.c_size_t, _dp, C.c_size_t, _dp]),
                 "pf_update_statistics": (None, [_dp, _dp, C.c_size_t, _dp, _dp]),
                 "pf_resample": (C.c_size_t, [_dp, _dp, C.c_size_t, C.c_size_t, C.c_size_t,
@@ -194,6 +195,14 @@ class Matcher:
                                              _d(delta), C.byref(written), _d(cov), None,
                                              theta_lo, theta_hi, C.byref(ncand))
         return s, int(ncand.value), delta, bool(written.value), cov
+
+    def partial(self, pose, points, theta_lo: int, theta_hi: int) -> np.ndarray:
+        """16-double partial record of the theta range (oracle only)."""
+        pose = _f64(pose).reshape(3)
+        points = _f64(points).reshape(-1, 2)
+        out = np.zeros(16)
+        self.o.matcher_partial(self.h, _d(pose), _d(points), points.shape[0], theta_lo, theta_hi, _d(out))
+        return out
 
     def score_points(self, points, pose) -> float:
         pose = _f64(pose).reshape(3)

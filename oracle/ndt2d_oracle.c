@@ -430,12 +430,42 @@ ORC_API size_t orc_loop_values(double size, double res, double * out, size_t cap
  *               the CPU baseline can time a bounded sample of a huge search;
  *               the loop variable is still replayed from -angular_size.
  * returns best_score / n  (0.0 and nothing written when there is no NDT). */
+static double match_scan_window_ex(
+  void * mv, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta, int * delta_written, double * out_cov, double * all_scores,
+  size_t theta_lo, size_t theta_hi, uint64_t * n_candidates, double * partial16);
+
 ORC_API double orc_matcher_match_scan_window(
   void * mv, const double * pose3, const double * pts_xy, size_t npts,
   double * out_delta, int * delta_written, double * out_cov, double * all_scores,
   size_t theta_lo, size_t theta_hi, uint64_t * n_candidates)
 {
+  return match_scan_window_ex(mv, pose3, pts_xy, npts, out_delta, delta_written, out_cov,
+           all_scores, theta_lo, theta_hi, n_candidates, NULL);
+}
+
+/* The sequential search restricted to theta indices [theta_lo, theta_hi), reported as
+ * the 16-double partial record of include/ndt2d_b200.h (ndt2d_matcher_search_staged):
+ * what one rank of a theta-sliced search contributes.  Test infrastructure for the
+ * multi-rank host logic (tests/test_multi_rank.py). */
+ORC_API void orc_matcher_partial(
+  void * mv, const double * pose3, const double * pts_xy, size_t npts,
+  size_t theta_lo, size_t theta_hi, double * partial16)
+{
+  match_scan_window_ex(mv, pose3, pts_xy, npts, NULL, NULL, NULL, NULL, theta_lo, theta_hi, NULL,
+    partial16);
+}
+
+static double match_scan_window_ex(
+  void * mv, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta, int * delta_written, double * out_cov, double * all_scores,
+  size_t theta_lo, size_t theta_hi, uint64_t * n_candidates, double * partial16)
+{
   orc_matcher * m = (orc_matcher *)mv;
+  if (partial16) {
+    memset(partial16, 0, 16 * sizeof(double));
+    partial16[1] = 1.0e300;
+  }
   if (delta_written) {*delta_written = 0;}
   if (n_candidates) {*n_candidates = 0;}
   if (!m->ndt) {
@@ -458,10 +488,14 @@ ORC_API double orc_matcher_match_scan_window(
 
   uint64_t cand = 0;
   size_t ith = 0;
+  size_t n_lin = 0;
+  for (double d = -m->linear_size; d < m->linear_size; d += m->linear_res) {++n_lin;}
+  double best_index = 1.0e300;
   for (double dth = -m->angular_size; dth < m->angular_size; dth += m->angular_res, ++ith) {
     if (ith < theta_lo || ith >= theta_hi) {
       continue;
     }
+    uint64_t in_slice = 0;
     const double costh = cos(scan_pose[2] + dth); /* :106-107 */
     const double sinth = sin(scan_pose[2] + dth);
     for (size_t i = 0; i < scan_points_to_use; ++i) {
@@ -478,6 +512,7 @@ ORC_API double orc_matcher_match_scan_window(
         const double score = -orc_ndt_likelihood_points(m->ndt, inner, scan_points_to_use);
         if (score < best_score) { /* :128 strict <, first wins */
           best_score = score;
+          best_index = (double)((uint64_t)ith * n_lin * n_lin + in_slice);
           if (out_delta) {
             out_delta[0] = dx;
             out_delta[1] = dy;
@@ -496,8 +531,19 @@ ORC_API double orc_matcher_match_scan_window(
         s += score;
         if (all_scores) {all_scores[cand] = score;}
         ++cand;
+        ++in_slice;
       }
     }
+  }
+  if (partial16) {
+    partial16[0] = best_score;
+    partial16[1] = best_index;
+    partial16[2] = k[0]; partial16[3] = k[1]; partial16[4] = k[2];
+    partial16[5] = k[4]; partial16[6] = k[5]; partial16[7] = k[8];
+    partial16[8] = u[0]; partial16[9] = u[1]; partial16[10] = u[2];
+    partial16[11] = s;
+    partial16[12] = (double)cand;
+    partial16[13] = (double)scan_points_to_use;
   }
   /* :146  covariance = (1/s) * k + ((1/(s*s)) * u) * u^T   (note the '+') */
   if (out_cov) {
