@@ -171,6 +171,13 @@ NDT2D_API int ndt2d_matcher_stage_scan(
 NDT2D_API int ndt2d_matcher_search_staged(
   ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial);
 
+/* The same over theta indices theta_begin, theta_begin + stride, ... (< theta_end).
+ * Interleaving the slices of N ranks (begin = rank, stride = N) balances the work:
+ * how much of the scan overlaps the map varies smoothly with theta. */
+NDT2D_API int ndt2d_matcher_search_staged_strided(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, uint64_t theta_stride,
+  void * d_partial);
+
 /* Synchronises the stream and copies the handle-held partial record out. */
 NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16);
 

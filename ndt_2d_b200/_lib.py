@@ -70,6 +70,7 @@ SIGNATURES = {
     "ndt2d_matcher_search_values": (C.c_int, [_vp, _dp, _dp]),
     "ndt2d_matcher_stage_scan": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),
     "ndt2d_matcher_search_staged": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "ndt2d_matcher_search_staged_strided": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]),
     "ndt2d_matcher_fetch_partial": (C.c_int, [_vp, _dp]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_combine_partials_host": (

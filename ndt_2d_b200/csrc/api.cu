@@ -180,7 +180,7 @@ struct ndt2d_matcher
   int sorted_buf = 0;
 
   bool staged = false;
-  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter;
+  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter, d_coords;
   double pose_x = 0, pose_y = 0;
   uint32_t n_pts = 0;
 
@@ -219,6 +219,9 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.n_pts = m->n_pts;
   sv.n_ang = static_cast<uint32_t>(m->dth.size());
   sv.n_lin = static_cast<uint32_t>(m->dlin.size());
+  sv.theta_stride = 1;
+  sv.coords = m->d_coords.as<uint16_t>();
+  sv.coords_cap_bytes = m->d_coords.cap;
   return sv;
 }
 
@@ -401,6 +404,13 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   if ((rc = m->d_blockpart.ensure(scratch * sizeof(double)))) {return rc;}
   if ((rc = m->d_partial.ensure(32 * sizeof(double)))) {return rc;}
   if ((rc = m->d_counter.ensure(64))) {return rc;}
+  {
+    // coordinate pre-pass table of the search kernel (skipped above 512 MiB)
+    const size_t cb = ndt2d_region_coords_bytes(m->prm.ndt_resolution, static_cast<uint32_t>(n_ang),
+        static_cast<uint32_t>(m->dlin.size()), m->prm.search_linear_resolution,
+        static_cast<uint32_t>(n_use), size_t(512) << 20);
+    if (cb && (rc = m->d_coords.ensure(cb))) {return rc;}
+  }
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
   // the pinned staging area is reused by the next call: wait for the copies
   NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
@@ -614,7 +624,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
-      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter};
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();
@@ -761,17 +771,20 @@ NDT2D_API int ndt2d_matcher_stage_scan(
   return stage_scan_locked(m, pose3, pts_xy, npts);
 }
 
-NDT2D_API int ndt2d_matcher_search_staged(
-  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial)
+NDT2D_API int ndt2d_matcher_search_staged_strided(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, uint64_t theta_stride,
+  void * d_partial)
 {
-  if (!m) {return NDT2D_ERR_INVALID;}
+  if (!m || theta_stride == 0 || theta_stride > 0xffffffffull) {return NDT2D_ERR_INVALID;}
   std::lock_guard<std::mutex> lock(m->mu);
   if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
   if (!m->staged) {return NDT2D_ERR_STATE;}
   const uint64_t n_ang = m->dth.size();
   if (theta_begin > theta_end || theta_end > n_ang) {return NDT2D_ERR_INVALID;}
   DeviceGuard guard(m->device);
-  int rc = ndt2d_launch_search(model_view(m), search_view(m), static_cast<uint32_t>(theta_begin),
+  SearchView sv = search_view(m);
+  sv.theta_stride = static_cast<uint32_t>(theta_stride);
+  int rc = ndt2d_launch_search(model_view(m), sv, static_cast<uint32_t>(theta_begin),
       static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
       m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr,
       m->ev_begin, m->ev_end);
@@ -782,6 +795,12 @@ NDT2D_API int ndt2d_matcher_search_staged(
       NDT2D_PARTIAL_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   }
   return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_search_staged(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial)
+{
+  return ndt2d_matcher_search_staged_strided(m, theta_begin, theta_end, 1, d_partial);
 }
 
 NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16)

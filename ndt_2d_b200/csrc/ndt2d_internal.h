@@ -66,6 +66,9 @@ struct SearchView
   double pose_x, pose_y;
   double linear_res;     // search_linear_resolution (patch sizing of the tiled kernel)
   uint32_t n_pts, n_ang, n_lin;
+  uint16_t * coords;        // scratch of the coordinate pre-pass (may be null)
+  size_t coords_cap_bytes;
+  uint32_t theta_stride;  // a search covers theta_begin, theta_begin + stride, ... (< theta_end)
 };
 
 // Per-block partial of the search (8 doubles):
@@ -130,10 +133,14 @@ int ndt2d_launch_search_tiled(
 // (theta, region of candidates) job, jobs handed out through *d_counter.
 size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res);
+// Bytes of the coordinate pre-pass table for a search of this shape (0 if above cap).
+size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res, uint32_t n_pts, size_t cap_bytes);
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
-  cudaStream_t stream, Counters * ctr, uint32_t * n_jobs);
+  uint16_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
+  uint32_t * n_jobs);
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kPlainThreads) search_plain_kernel(
   double * __restrict__ scores)
 {
   __shared__ double2 outer[kPlainChunk];
-  const uint32_t itheta = theta_begin + blockIdx.y;
+  const uint32_t itheta = theta_begin + blockIdx.y * sv.theta_stride;
   const double2 cs = sv.trig[itheta];
   const double dth = sv.dth[itheta];
   const uint32_t n_lin = sv.n_lin;
@@ -134,28 +134,18 @@ __device__ void finish_record(double * rec, const double * dth, const double * d
   rec[30] = rec[31] = 0.0;
 }
 
-// Reduce the per-block partials of one launch into the 32-double record.
-__global__ void __launch_bounds__(256) search_final_kernel(
-  const double * __restrict__ block_partials, uint32_t n_blocks, SearchView sv,
-  double n_candidates, double * __restrict__ out32)
+// Reduction of the per-job partials of one launch, two deterministic stages:
+//   stage 1  search_reduce_kernel  block b folds the jobs of its contiguous chunk into
+//            one 12-double record {best, index, kxx kxy kxt kyy kyt ktt ux uy ut s}
+//            (the job's dtheta is folded into the theta terms here)
+//   stage 2  search_finish_kernel  one block folds the <= kReduceBlocks records and
+//            writes the 32-double result record.
+constexpr uint32_t kReduceBlocks = 592;
+constexpr int kStage1Doubles = 12;
+
+__device__ __forceinline__ void block_fold_12(
+  Best best, double (&acc)[10], double * __restrict__ out12)
 {
-  Best best{0.0, kNoIndex};
-  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // kxx kxy kxt kyy kyt ktt ux uy ut s
-  for (uint32_t b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-    const double * p = block_partials + static_cast<size_t>(b) * NDT2D_BLOCK_PARTIAL;
-    best_merge(best, p[0], p[1]);
-    const double S = p[2], Sx = p[3], Sy = p[4], Sxx = p[5], Sxy = p[6], Syy = p[7], t = p[8];
-    acc[0] += Sxx;
-    acc[1] += Sxy;
-    acc[2] += t * Sx;
-    acc[3] += Syy;
-    acc[4] += t * Sy;
-    acc[5] += (t * t) * S;
-    acc[6] += Sx;
-    acc[7] += Sy;
-    acc[8] += t * S;
-    acc[9] += S;
-  }
   __shared__ double red[8][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   warp_best(best);
@@ -176,14 +166,72 @@ __global__ void __launch_bounds__(256) search_final_kernel(
       best_merge(t, red[w][0], red[w][1]);
       for (int k = 0; k < 10; ++k) {s[k] += red[w][2 + k];}
     }
-    out32[0] = t.score;
-    out32[1] = t.index;
-    for (int k = 0; k < 10; ++k) {out32[2 + k] = s[k];}
+    out12[0] = t.score;
+    out12[1] = t.index;
+    for (int k = 0; k < 10; ++k) {out12[2 + k] = s[k];}
+  }
+}
+
+__global__ void __launch_bounds__(256) search_reduce_kernel(
+  const double * __restrict__ block_partials, uint32_t n_blocks, double * __restrict__ stage1)
+{
+  const uint32_t chunk = (n_blocks + gridDim.x - 1) / gridDim.x;
+  const uint32_t lo = blockIdx.x * chunk, hi = min(n_blocks, lo + chunk);
+  Best best{0.0, kNoIndex};
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // kxx kxy kxt kyy kyt ktt ux uy ut s
+  for (uint32_t b = lo + threadIdx.x; b < hi; b += blockDim.x) {
+    const double * p = block_partials + static_cast<size_t>(b) * NDT2D_BLOCK_PARTIAL;
+    best_merge(best, p[0], p[1]);
+    const double S = p[2], Sx = p[3], Sy = p[4], Sxx = p[5], Sxy = p[6], Syy = p[7], t = p[8];
+    acc[0] += Sxx;
+    acc[1] += Sxy;
+    acc[2] += t * Sx;
+    acc[3] += Syy;
+    acc[4] += t * Sy;
+    acc[5] += (t * t) * S;
+    acc[6] += Sx;
+    acc[7] += Sy;
+    acc[8] += t * S;
+    acc[9] += S;
+  }
+  block_fold_12(best, acc, stage1 + static_cast<size_t>(blockIdx.x) * kStage1Doubles);
+}
+
+__global__ void __launch_bounds__(256) search_finish_kernel(
+  const double * __restrict__ stage1, uint32_t n_records, SearchView sv, double n_candidates,
+  double * __restrict__ out32)
+{
+  Best best{0.0, kNoIndex};
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t b = threadIdx.x; b < n_records; b += blockDim.x) {
+    const double * p = stage1 + static_cast<size_t>(b) * kStage1Doubles;
+    best_merge(best, p[0], p[1]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {acc[k] += p[2 + k];}
+  }
+  __shared__ double folded[12];
+  block_fold_12(best, acc, folded);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 12; ++k) {out32[k] = folded[k];}
     out32[12] = n_candidates;
     out32[13] = static_cast<double>(sv.n_pts);
     out32[14] = out32[15] = 0.0;
     finish_record(out32, sv.dth, sv.dlin, sv.n_lin);
   }
+}
+
+// block_partials: n_blocks records of NDT2D_BLOCK_PARTIAL doubles, followed by room for
+// kReduceBlocks stage-1 records (ndt2d_search_scratch_doubles accounts for it).
+int launch_final(const double * d_block_partials, uint32_t n_blocks, double * d_stage1,
+  const SearchView & sv, double n_candidates, double * d_partial32, cudaStream_t stream,
+  Counters * ctr)
+{
+  const uint32_t nb = min(kReduceBlocks, max(1u, (n_blocks + 255u) / 256u));
+  search_reduce_kernel<<<nb, 256, 0, stream>>>(d_block_partials, n_blocks, d_stage1);
+  NDT2D_LAUNCH_CHECK(ctr);
+  search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, sv, n_candidates, d_partial32);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
 }
 
 // Lexicographic min + sums over n partial records (one per GPU / theta range).
@@ -269,7 +317,7 @@ size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_
   const size_t tiled = ndt2d_tiled_scratch_doubles(g, n_ang, n_lin, linear_res);
   const size_t region = ndt2d_region_scratch_doubles(cell_size, n_ang, n_lin, linear_res);
   const size_t a = plain > tiled ? plain : tiled;
-  return a > region ? a : region;
+  return (a > region ? a : region) + static_cast<size_t>(kReduceBlocks) * kStage1Doubles;
 }
 
 int ndt2d_launch_search(
@@ -283,19 +331,22 @@ int ndt2d_launch_search(
     NDT2D_LAUNCH_CHECK(ctr);
     return NDT2D_OK;
   }
-  const uint32_t n_theta = theta_end - theta_begin;
+  // stage-1 records of the final reduction live at the end of the scratch buffer
+  const size_t stage1_offset = ndt2d_search_scratch_doubles(sv.n_ang, sv.n_lin, mv.g.cell_size,
+      sv.linear_res) - static_cast<size_t>(kReduceBlocks) * kStage1Doubles;
+  const uint32_t stride = sv.theta_stride ? sv.theta_stride : 1u;
+  const uint32_t n_theta = (theta_end - theta_begin + stride - 1u) / stride;
   const double n_candidates = static_cast<double>(n_theta) * sv.n_lin * sv.n_lin;
   if (variant != 1 && variant != 2) {
     uint32_t n_jobs = 0;
     if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
     const int rc = ndt2d_launch_search_region(mv, sv, sv.linear_res, theta_begin, n_theta,
-        d_block_partials, d_scores, d_counter, stream, ctr, &n_jobs);
+        d_block_partials, d_scores, d_counter, sv.coords, sv.coords_cap_bytes, stream, ctr,
+        &n_jobs);
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
-    search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_jobs, sv, n_candidates,
-      d_partial32);
-    NDT2D_LAUNCH_CHECK(ctr);
-    return NDT2D_OK;
+    return launch_final(d_block_partials, n_jobs, d_block_partials + stage1_offset, sv,
+             n_candidates, d_partial32, stream, ctr);
   }
   if (variant == 2) {
     uint32_t n_blocks = 0;
@@ -304,10 +355,8 @@ int ndt2d_launch_search(
         d_block_partials, d_scores, stream, ctr, &n_blocks);
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
-    search_final_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_blocks, sv, n_candidates,
-      d_partial32);
-    NDT2D_LAUNCH_CHECK(ctr);
-    return NDT2D_OK;
+    return launch_final(d_block_partials, n_blocks, d_block_partials + stage1_offset, sv,
+             n_candidates, d_partial32, stream, ctr);
   }
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
@@ -317,16 +366,14 @@ int ndt2d_launch_search(
     const uint32_t ny = min(n_theta - done, 65535u);
     dim3 grid(bx, ny);
     search_plain_kernel<<<grid, kPlainThreads, 0, stream>>>(
-      mv, sv, theta_begin + done,
+      mv, sv, theta_begin + done * stride,
       d_block_partials + static_cast<size_t>(done) * bx * NDT2D_BLOCK_PARTIAL, d_scores);
     NDT2D_LAUNCH_CHECK(ctr);
     done += ny;
   }
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
-  search_final_kernel<<<1, 256, 0, stream>>>(
-    d_block_partials, n_theta * bx, sv, n_candidates, d_partial32);
-  NDT2D_LAUNCH_CHECK(ctr);
-  return NDT2D_OK;
+  return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
+           n_candidates, d_partial32, stream, ctr);
 }
 
 int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,

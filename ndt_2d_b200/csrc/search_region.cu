@@ -201,13 +201,43 @@ __device__ __forceinline__ void flush_block(
   }
 }
 
-template<bool SMEM_TAB>
+// Pre-pass of the search: for every (theta slice, scan point) the padded cell
+// coordinate of the FIRST column of each of the Q region columns (x) and of the
+// first row of each of the Q region rows (y).  The Q*Q regions of a slice share
+// them, so computing them here instead of inside every job removes a factor Q
+// of threshold lookups.  Layout: coords[((it * 2 + axis) * Q + q) * n_pts_pad + i], u16.
+__global__ void __launch_bounds__(128) region_coords_kernel(
+  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t Rw, uint32_t Q,
+  uint32_t n_pts_pad, uint16_t * __restrict__ coords)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sv.n_pts) {return;}
+  const double2 p = sv.pts[i];
+  const double inv_cell = 1.0 / mv.g.cell_size;
+  for (uint32_t it = blockIdx.y; it < n_theta; it += gridDim.y) {
+    const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
+    const double ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
+    const double oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
+    uint16_t * cx = coords + (static_cast<size_t>(it) * 2 * Q) * n_pts_pad + i;
+    uint16_t * cy = cx + static_cast<size_t>(Q) * n_pts_pad;
+    for (uint32_t q = 0; q < Q; ++q) {
+      const double dl = sv.dlin[q * Rw];
+      cx[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
+          __dadd_rn(ox, dl), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell));
+      cy[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
+          __dadd_rn(oy, dl), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell));
+    }
+  }
+}
+
+template<bool SMEM_TAB, bool PRE>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
   uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
   double * __restrict__ scores, uint32_t * __restrict__ job_counter,
-  unsigned long long * __restrict__ stats)
+  unsigned long long * __restrict__ stats, const uint16_t * __restrict__ coords,
+  uint32_t n_pts_pad)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -263,7 +293,7 @@ search_region_kernel(
     if (job >= n_jobs) {break;}
     const uint32_t it = job / QQ, rr = job - it * QQ;
     const uint32_t rx = rr / Q, ry = rr - rx * Q;
-    const uint32_t itheta = theta_begin + it;
+    const uint32_t itheta = theta_begin + it * sv.theta_stride;
     const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
     const uint32_t nxc = min(Rw, n_lin - jx0), nyc = min(Rw, n_lin - jy0);  // columns / rows
     const double2 cs = sv.trig[itheta];
@@ -271,6 +301,12 @@ search_region_kernel(
     const double my_dly = sv.dlin[jy0 + min(lane, nyc - 1u)];
     const double dlx0 = __shfl_sync(0xffffffffu, my_dlx, 0);
     const double dly0 = __shfl_sync(0xffffffffu, my_dly, 0);
+    const uint16_t * cx_tab = nullptr;
+    const uint16_t * cy_tab = nullptr;
+    if (PRE) {
+      cx_tab = coords + (static_cast<size_t>(it) * 2 * Q + rx) * n_pts_pad;
+      cy_tab = coords + (static_cast<size_t>(it) * 2 * Q + Q + ry) * n_pts_pad;
+    }
 
     for (uint32_t k = lane; k < RR; k += 32) {
       acc_d[k] = 0.0;
@@ -284,7 +320,20 @@ search_region_kernel(
       double ox = 0.0, oy = 0.0;
       uint32_t pcx = 0, pcy = 0;
       bool hit = false;
-      if (i < sv.n_pts) {
+      if (PRE) {
+        // coordinates of the region's first column / row from the pre-pass table
+        if (i < sv.n_pts) {
+          pcx = cx_tab[i];
+          pcy = cy_tab[i];
+          const uint32_t idx = pcy * pitch + pcx;
+          hit = ((occd[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
+        }
+        if (hit) {
+          const double2 p = sv.pts[i];
+          ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
+          oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
+        }
+      } else if (i < sv.n_pts) {
         const double2 p = sv.pts[i];
         // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
         ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
@@ -453,12 +502,12 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
   return pl;
 }
 
-template<bool S>
+template<bool S, bool PRE>
 int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
-  uint32_t theta_begin, double * d_job_partials, double * d_scores, uint32_t * d_counter,
-  cudaStream_t stream, Counters * ctr)
+  uint32_t theta_begin, uint32_t n_theta, double * d_job_partials, double * d_scores,
+  uint32_t * d_counter, uint16_t * d_coords, cudaStream_t stream, Counters * ctr)
 {
-  auto kernel = search_region_kernel<S>;
+  auto kernel = search_region_kernel<S, PRE>;
   NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
     static_cast<int>(pl.smem_bytes)));
   int dev = 0, sms = 148;
@@ -469,13 +518,26 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   pl.grid = min(pl.n_jobs, static_cast<uint32_t>(sms));
   // d_counter: [0] job counter (u32, + pad), [1..2] u64 statistics of this launch
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 32, stream));
+  const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
+  if (PRE) {
+    dim3 grid((sv.n_pts + 127u) / 128u, min(n_theta, 65535u));
+    region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.Rw, pl.Q,
+      n_pts_pad, d_coords);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
   const uint32_t d_bytes = pl.smem_tab ? ((mv.g.n_words * 4u + 15u) & ~15u) : 0u;
   const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
   kernel<<<pl.grid, kWarps * 32, pl.smem_bytes, stream>>>(
     mv, sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, d_bytes, t_bytes, d_job_partials, d_scores,
-    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1);
+    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1, d_coords, n_pts_pad);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
+}
+
+size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
+{
+  const size_t n_pts_pad = (static_cast<size_t>(n_pts) + 31u) & ~size_t(31);
+  return static_cast<size_t>(n_theta) * 2 * pl.Q * n_pts_pad * sizeof(uint16_t);
 }
 
 }  // namespace
@@ -485,26 +547,51 @@ size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n
 {
   GridDesc g{};
   g.cell_size = cell_size;
-  // the plan's region size shrinks with the number of theta slices searched; the
-  // scratch must hold the worst case of any theta sub-range: one slice
+  // the plan's region size shrinks with the number of theta slices searched (more,
+  // smaller regions for small searches); bound the job count of any sub-range
+  // [nt, 2 nt) by the plan of nt slices applied to 2 nt slices
+  const uint32_t na = n_ang ? n_ang : 1;
   size_t worst = 0;
-  for (uint32_t nt : {1u, n_ang ? n_ang : 1u}) {
-    const RegionPlan pl = make_plan(g, nt, n_lin ? n_lin : 1, linear_res);
-    const size_t jobs = static_cast<size_t>(n_ang ? n_ang : 1) * pl.Q * pl.Q;
+  for (uint64_t nt = 1;; nt *= 2) {
+    const uint32_t t = static_cast<uint32_t>(nt < na ? nt : na);
+    const RegionPlan pl = make_plan(g, t, n_lin ? n_lin : 1, linear_res);
+    const uint64_t upto = (2 * nt < na) ? 2 * nt : na;
+    const size_t jobs = static_cast<size_t>(upto) * pl.Q * pl.Q;
     worst = jobs > worst ? jobs : worst;
+    if (nt >= na) {break;}
   }
   return worst * NDT2D_BLOCK_PARTIAL + 8;
+}
+
+size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res, uint32_t n_pts, size_t cap_bytes)
+{
+  GridDesc g{};
+  g.cell_size = cell_size;
+  // sized for the full theta range; a launch over a sub-range (other region plan)
+  // uses the table only if its own needs fit (ndt2d_launch_search_region)
+  const RegionPlan pl = make_plan(g, n_ang ? n_ang : 1, n_lin ? n_lin : 1, linear_res);
+  const size_t worst = pl.Q >= 2 ? coords_bytes(pl, n_ang ? n_ang : 1, n_pts) : 0;
+  return worst <= cap_bytes ? worst : 0;  // 0: the search computes coordinates per job
 }
 
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
-  cudaStream_t stream, Counters * ctr, uint32_t * n_jobs)
+  uint16_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
+  uint32_t * n_jobs)
 {
   RegionPlan pl = make_plan(mv.g, n_theta, sv.n_lin, linear_res);
   *n_jobs = pl.n_jobs;
-  return pl.smem_tab
-         ? launch_one<true>(pl, mv, sv, theta_begin, d_job_partials, d_scores, d_counter, stream, ctr)
-         : launch_one<false>(pl, mv, sv, theta_begin, d_job_partials, d_scores, d_counter, stream,
-           ctr);
+  // the pre-pass pays off when a slice has several regions per axis to share it
+  const bool pre = d_coords && pl.Q >= 2 && sv.n_pts > 0 &&
+    coords_bytes(pl, n_theta, sv.n_pts) <= coords_cap_bytes;
+#define NDT2D_REGION_LAUNCH(S, P) \
+  launch_one<S, P>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
+    d_coords, stream, ctr)
+  if (pl.smem_tab) {
+    return pre ? NDT2D_REGION_LAUNCH(true, true) : NDT2D_REGION_LAUNCH(true, false);
+  }
+  return pre ? NDT2D_REGION_LAUNCH(false, true) : NDT2D_REGION_LAUNCH(false, false);
+#undef NDT2D_REGION_LAUNCH
 }

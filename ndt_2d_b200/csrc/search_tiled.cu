@@ -188,7 +188,7 @@ search_tiled_kernel(
   }
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t itheta = theta_begin + blockIdx.y;
+  const uint32_t itheta = theta_begin + blockIdx.y * sv.theta_stride;
   const uint32_t tile_x = blockIdx.x / tiles_per_axis, tile_y = blockIdx.x - tile_x * tiles_per_axis;
   const uint32_t n_lin = sv.n_lin;
   const uint32_t jx0 = tile_x * P * R, jy0 = tile_y * P * R;
@@ -402,7 +402,7 @@ int launch_one(const TiledPlan & pl, const ModelView & mv, const SearchView & sv
     const uint32_t ny = min(n_theta - done, 65535u);
     dim3 grid(tiles, ny);
     kernel<<<grid, pl.threads, pl.smem_bytes, stream>>>(
-      mv, sv, theta_begin + done, pl.P, pl.tiles_per_axis,
+      mv, sv, theta_begin + done * sv.theta_stride, pl.P, pl.tiles_per_axis,
       d_block_partials + static_cast<size_t>(done) * tiles * NDT2D_BLOCK_PARTIAL, d_scores);
     NDT2D_LAUNCH_CHECK(ctr);
     done += ny;

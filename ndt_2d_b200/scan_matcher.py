@@ -242,9 +242,9 @@ class ScanMatcherNDT:
         L.check(L.lib.ndt2d_matcher_stage_scan(self.handle, L.dptr(pose3), L.dptr(pts), pts.shape[0]),
                 "ndt2d_matcher_stage_scan")
 
-    def search_staged(self, theta_begin: int, theta_end: int, d_partial: int = 0) -> None:
-        L.check(L.lib.ndt2d_matcher_search_staged(self.handle, theta_begin, theta_end,
-                                                  d_partial or None), "ndt2d_matcher_search_staged")
+    def search_staged(self, theta_begin: int, theta_end: int, d_partial: int = 0, stride: int = 1) -> None:
+        L.check(L.lib.ndt2d_matcher_search_staged_strided(self.handle, theta_begin, theta_end, stride,
+                                                          d_partial or None), "ndt2d_matcher_search_staged")
 
     def fetch_partial(self) -> np.ndarray:
         out = np.zeros(L.PARTIAL_DOUBLES)

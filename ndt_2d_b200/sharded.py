@@ -27,6 +27,18 @@ def theta_range(n_ang: int, rank: int, world: int) -> Tuple[int, int]:
     return (n_ang * rank) // world, (n_ang * (rank + 1)) // world
 
 
+def theta_slices(n_ang: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """(begin, end, stride) of the INTERLEAVED slices of `rank`: rank, rank + world, ...
+    How much of the scan overlaps the map -- the cost of a slice -- varies smoothly with
+    theta, so interleaving balances the ranks where a contiguous split does not (measured:
+    59 % / 41 % of the work at 2 GPUs on config 4)."""
+    return min(rank, n_ang), n_ang, world
+
+
+def n_slices(begin: int, end: int, stride: int) -> int:
+    return max(0, (end - begin + stride - 1) // stride)
+
+
 def lattice(size: float, resolution: float) -> np.ndarray:
     """The reference's accumulated-double loop values (host replay, no device needed)."""
     n = C.c_size_t(0)
@@ -66,13 +78,14 @@ class ShardedSearch:
         import torch
         self.m, self.rank, self.world, self.group = matcher, rank, world, group
         na, _ = matcher.search_shape()
-        self.lo, self.hi = theta_range(na, rank, world)
+        self.lo, self.hi, self.stride = theta_slices(na, rank, world)
+        self.n_theta = n_slices(self.lo, self.hi, self.stride)
         self.gathered = torch.zeros(world * PARTIAL_DOUBLES, dtype=torch.float64, device=device)
         self.mine = self.gathered[rank * PARTIAL_DOUBLES:(rank + 1) * PARTIAL_DOUBLES]
 
     def search_staged(self):
         """Launch this rank's slices of the staged scan + the exchange (asynchronous)."""
-        self.m.search_staged(self.lo, self.hi, self.mine.data_ptr())
+        self.m.search_staged(self.lo, self.hi, self.mine.data_ptr(), stride=self.stride)
         if self.world > 1:
             exchange_partials(self.mine.clone(), self.gathered, self.group)
 

@@ -264,6 +264,29 @@ def test_theta_sliced_search_matches_full(o):
         np.testing.assert_allclose(cov, full[3], rtol=1e-9, atol=1e-12)
 
 
+def test_theta_interleaved_search_matches_full(o):
+    """Strided theta slices (rank, rank + N, ...): the multi-GPU partition of bench.py."""
+    from ndt_2d_b200 import sharded
+    w = synth.config1()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    full = m.match_scan_raw(w.query_pose, w.query_points)
+    na, nl = m.search_shape()
+    m.stage_scan(w.query_pose, w.query_points)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            b, e, st = sharded.theta_slices(na, r, world)
+            m.search_staged(b, e, stride=st)
+            parts.append(m.fetch_partial())
+        parts = np.array(parts)
+        assert parts[:, 12].sum() == na * nl * nl
+        s, d, written, cov = m.combine_partials(parts)
+        assert written == full[2] and np.array_equal(d, full[1])
+        np.testing.assert_allclose(s, full[0], rtol=1e-13)
+        np.testing.assert_allclose(cov, full[3], rtol=1e-9, atol=1e-12)
+
+
 # ------------------------------------------------------------------ scoring
 def test_score_points_and_poses(o):
     w = synth.config1(laser_max_beams=100)

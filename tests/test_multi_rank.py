@@ -56,6 +56,18 @@ def test_theta_sliced_search_gloo(tmp_path, world):
         assert np.array_equal(r, res[0])                                # every rank holds the result
 
 
+def test_theta_slices_interleave_exactly():
+    for n_ang in (0, 1, 7, 80, 3142):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                b, e, st = sharded.theta_slices(n_ang, r, world)
+                idx = list(range(b, e, st))
+                assert len(idx) == sharded.n_slices(b, e, st)
+                seen += idx
+            assert sorted(seen) == list(range(n_ang))
+
+
 def test_theta_range_partitions_exactly():
     for n_ang in (0, 1, 7, 80, 200, 3142):
         for world in (1, 2, 3, 4, 8):
