@@ -181,12 +181,23 @@ __device__ __forceinline__ void eval_cell(
     float * ap = acc_f + (COL ? (u0 + lu) + (v0 + lv) * Rw : (u0 + lu) * Rw + (v0 + lv));
     const double * vp = vs + v0 + lv;
     const uint32_t ap_step = COL ? lines * Rw : lines;
-    for (uint32_t v = lv; v < nV; v += lines) {
+    uint32_t v = lv;
+    // two independent evaluations per trip: halves the loop overhead and gives the
+    // scheduler a second dependency chain (LDS -> DADD -> DFMA -> DFMA -> F2F -> MUFU)
+    for (; v + lines < nV; v += 2u * lines) {
+      const double qv0 = vp[0] - mean_v, qv1 = vp[lines] - mean_v;
+      const double e0 = fma(qv0, fma(Cv, qv0, Bqu), Cqu2);
+      const double e1 = fma(qv1, fma(Cv, qv1, Bqu), Cqu2);
+      const float f0 = ex2_ftz(static_cast<float>(e0)), f1 = ex2_ftz(static_cast<float>(e1));
+      ap[0] += f0;
+      ap[ap_step] += f1;
+      vp += 2u * lines;
+      ap += 2u * ap_step;
+    }
+    if (v < nV) {
       const double qv = *vp - mean_v;
       const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
       *ap += ex2_ftz(static_cast<float>(e));
-      vp += lines;
-      ap += ap_step;
     }
   }
 }
