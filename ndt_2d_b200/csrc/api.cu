@@ -180,7 +180,7 @@ struct ndt2d_matcher
   int sorted_buf = 0;
 
   bool staged = false;
-  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter, d_coords;
+  DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter, d_coords, d_chunk;
   double pose_x = 0, pose_y = 0;
   uint32_t n_pts = 0;
 
@@ -222,6 +222,8 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.theta_stride = 1;
   sv.coords = m->d_coords.as<uint16_t>();
   sv.coords_cap_bytes = m->d_coords.cap;
+  sv.chunk_sums = m->d_chunk.as<double>();
+  sv.chunk_cap_doubles = m->d_chunk.cap / sizeof(double);
   return sv;
 }
 
@@ -410,6 +412,10 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
         static_cast<uint32_t>(m->dlin.size()), m->prm.search_linear_resolution,
         static_cast<uint32_t>(n_use), size_t(512) << 20);
     if (cb && (rc = m->d_coords.ensure(cb))) {return rc;}
+    const size_t cd = ndt2d_region_chunk_doubles(m->prm.ndt_resolution, static_cast<uint32_t>(n_ang),
+        static_cast<uint32_t>(m->dlin.size()), m->prm.search_linear_resolution,
+        static_cast<uint32_t>(n_use));
+    if (cd && (rc = m->d_chunk.ensure(cd * sizeof(double)))) {return rc;}
   }
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
   // the pinned staging area is reused by the next call: wait for the copies
@@ -624,7 +630,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
-      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords};
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();

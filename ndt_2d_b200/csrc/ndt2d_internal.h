@@ -68,6 +68,8 @@ struct SearchView
   uint32_t n_pts, n_ang, n_lin;
   uint16_t * coords;        // scratch of the coordinate pre-pass (may be null)
   size_t coords_cap_bytes;
+  double * chunk_sums;      // scratch of the point-chunked mode of small searches (may be null)
+  size_t chunk_cap_doubles;
   uint32_t theta_stride;  // a search covers theta_begin, theta_begin + stride, ... (< theta_end)
 };
 
@@ -136,6 +138,8 @@ size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n
 // Bytes of the coordinate pre-pass table for a search of this shape (0 if above cap).
 size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res, uint32_t n_pts, size_t cap_bytes);
+size_t ndt2d_region_chunk_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res, uint32_t n_pts);
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,

@@ -53,8 +53,9 @@ constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
 // per warp: double totals, xs[32], ys[32], float block sums (16-byte rounded)
 constexpr uint32_t kWarpSmemBytes = ((kAccEntries * 8 + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
 constexpr size_t kSmemTabBudget = 32 * 1024;    // D + thresholds in shared memory up to this
-constexpr uint32_t kFlushSteps = 2;             // 32-point steps per float accumulation block
+constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
+constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
@@ -135,6 +136,8 @@ struct RegionPlan
   bool smem_tab;
   uint32_t grid;
   size_t smem_bytes;
+  uint32_t P;             // point chunks per job (1 = whole scan in one job)
+  uint32_t chunk_points;  // scan points per chunk (multiple of 32)
 };
 
 // Padded coordinate pc(v) = #{k in [0, size] : thr[k] <= v}  (0 = below the
@@ -241,6 +244,74 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
   }
 }
 
+// Per-candidate score of one job from its sums, warp argmin + the six covariance
+// sums -> the job's 9-double record.  sums[k], k = a * Rw + b.
+__device__ __forceinline__ void job_epilogue(
+  const double * __restrict__ sums, const SearchView & sv, uint32_t job, uint32_t itheta,
+  uint32_t Rw, uint32_t jx0, uint32_t jy0, uint32_t nxc, uint32_t nyc, uint32_t lane,
+  double * __restrict__ job_partials, double * __restrict__ scores)
+{
+  const uint32_t n_lin = sv.n_lin;
+  const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
+  const uint32_t RR = Rw * Rw, inv_rw = 65536u / Rw + 1u;
+  Best best{0.0, kNoIndex};
+  double sum[6] = {0, 0, 0, 0, 0, 0};
+  for (uint32_t k = lane; k < RR; k += 32) {
+    const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
+    if (a < nxc && b < nyc) {
+      const double score = -sums[k];
+      const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
+      const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
+        static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
+      if (scores) {scores[gi] = score;}
+      best_merge(best, score, static_cast<double>(gi));
+      sum[0] += score;
+      sum[1] += dx * score;
+      sum[2] += dy * score;
+      sum[3] += (dx * dx) * score;
+      sum[4] += (dx * dy) * score;
+      sum[5] += (dy * dy) * score;
+    }
+  }
+  warp_best(best);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {sum[k] = warp_sum(sum[k]);}
+  if (lane == 0) {
+    double * out = job_partials + static_cast<size_t>(job) * NDT2D_BLOCK_PARTIAL;
+    out[0] = best.score;
+    out[1] = best.index;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {out[2 + k] = sum[k];}
+    out[8] = sv.dth[itheta];
+  }
+}
+
+// Small searches split every job's scan points into P chunks (more warps in flight,
+// shorter critical path); this kernel adds the chunk sums of a job in chunk order
+// (deterministic) and finishes it.  One warp per job.
+__global__ void __launch_bounds__(256) region_chunk_reduce_kernel(
+  SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs, uint32_t P,
+  double * __restrict__ chunk_sums, double * __restrict__ job_partials,
+  double * __restrict__ scores)
+{
+  const uint32_t job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (job >= n_jobs) {return;}
+  const uint32_t QQ = Q * Q, RR = Rw * Rw;
+  const uint32_t it = job / QQ, rr = job - it * QQ;
+  const uint32_t rx = rr / Q, ry = rr - rx * Q;
+  const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
+  const uint32_t nxc = min(Rw, sv.n_lin - jx0), nyc = min(Rw, sv.n_lin - jy0);
+  double * first = chunk_sums + static_cast<size_t>(job) * P * RR;
+  for (uint32_t k = lane; k < RR; k += 32) {
+    double t = first[k];
+    for (uint32_t c = 1; c < P; ++c) {t += first[static_cast<size_t>(c) * RR + k];}
+    first[k] = t;
+  }
+  __syncwarp();
+  job_epilogue(first, sv, job, theta_begin + it * sv.theta_stride, Rw, jx0, jy0, nxc, nyc, lane,
+    job_partials, scores);
+}
+
 template<bool SMEM_TAB, bool PRE>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
@@ -248,7 +319,7 @@ search_region_kernel(
   uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
   double * __restrict__ scores, uint32_t * __restrict__ job_counter,
   unsigned long long * __restrict__ stats, const uint16_t * __restrict__ coords,
-  uint32_t n_pts_pad)
+  uint32_t n_pts_pad, uint32_t P, uint32_t chunk_points, double * __restrict__ chunk_sums)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -287,10 +358,8 @@ search_region_kernel(
   const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y;
   const double inv_cell = 1.0 / mv.g.cell_size;
   const double origin_x = mv.g.origin_x, origin_y = mv.g.origin_y;
-  const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
   const uint32_t QQ = Q * Q;
   const uint32_t RR = Rw * Rw;
-  const uint32_t inv_rw = 65536u / Rw + 1u;
 
   if (SMEM_TAB) {
     __syncthreads();       // mbarrier initialised before anyone polls it
@@ -301,7 +370,16 @@ search_region_kernel(
     uint32_t job = 0;
     if (lane == 0) {job = atomicAdd(job_counter, 1u);}
     job = __shfl_sync(0xffffffffu, job, 0);
-    if (job >= n_jobs) {break;}
+    if (job >= n_jobs * P) {break;}
+    // with P > 1 the counter enumerates (job, point chunk) pairs, chunks of a job adjacent
+    const uint32_t work = job;
+    uint32_t chunk = 0;
+    if (P > 1) {
+      chunk = work % P;
+      job = work / P;
+    }
+    const uint32_t p_begin = chunk * chunk_points;
+    const uint32_t p_end = (P > 1) ? min(sv.n_pts, p_begin + chunk_points) : sv.n_pts;
     const uint32_t it = job / QQ, rr = job - it * QQ;
     const uint32_t rx = rr / Q, ry = rr - rx * Q;
     const uint32_t itheta = theta_begin + it * sv.theta_stride;
@@ -326,14 +404,15 @@ search_region_kernel(
     __syncwarp();
 
     uint32_t dirty_steps = 0;  // steps with hits since the last flush
-    for (uint32_t p0 = 0; p0 < sv.n_pts; p0 += 32) {
+    uint32_t job_useful = 0;
+    for (uint32_t p0 = p_begin; p0 < p_end; p0 += 32) {
       const uint32_t i = p0 + lane;
       double ox = 0.0, oy = 0.0;
       uint32_t pcx = 0, pcy = 0;
       bool hit = false;
       if (PRE) {
         // coordinates of the region's first column / row from the pre-pass table
-        if (i < sv.n_pts) {
+        if (i < p_end) {
           pcx = cx_tab[i];
           pcy = cy_tab[i];
           const uint32_t idx = pcy * pitch + pcx;
@@ -344,7 +423,7 @@ search_region_kernel(
           ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
           oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
         }
-      } else if (i < sv.n_pts) {
+      } else if (i < p_end) {
         const double2 p = sv.pts[i];
         // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
         ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
@@ -398,7 +477,7 @@ search_region_kernel(
           const uint32_t vx = v & 1u, vy = v >> 1;
           const uint32_t cx0 = vx ? nx : 0u, w = vx ? nxc - nx : nx;
           const uint32_t cy0 = vy ? ny : 0u, h = vy ? nyc - ny : ny;
-          n_useful += w * h;
+          job_useful += w * h;
           const double2 * f2 = reinterpret_cast<const double2 *>(
             mv.rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
           const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
@@ -433,7 +512,7 @@ search_region_kernel(
         __syncwarp();
       }
       // float block sums go to the double totals every kFlushSteps steps with hits:
-      // a block sum stays below 32 * kFlushSteps, so its rounding stays ~1e-8 of a score
+      // a block sum stays below 32 * kFlushSteps = 128, so its rounding stays ~1e-8 of a score
       if (dirty_steps == kFlushSteps) {
         flush_block(acc_d, acc_f, RR, lane);
         dirty_steps = 0;
@@ -445,36 +524,15 @@ search_region_kernel(
       __syncwarp();
     }
 
-    // ---- epilogue: per-candidate score, job partial
-    Best best{0.0, kNoIndex};
-    double sum[6] = {0, 0, 0, 0, 0, 0};
-    for (uint32_t k = lane; k < RR; k += 32) {
-      const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
-      if (a < nxc && b < nyc) {
-        const double score = -acc_d[k];
-        const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
-        const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
-          static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
-        if (scores) {scores[gi] = score;}
-        best_merge(best, score, static_cast<double>(gi));
-        sum[0] += score;
-        sum[1] += dx * score;
-        sum[2] += dy * score;
-        sum[3] += (dx * dx) * score;
-        sum[4] += (dx * dy) * score;
-        sum[5] += (dy * dy) * score;
-      }
-    }
-    warp_best(best);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {sum[k] = warp_sum(sum[k]);}
-    if (lane == 0) {
-      double * out = job_partials + static_cast<size_t>(job) * NDT2D_BLOCK_PARTIAL;
-      out[0] = best.score;
-      out[1] = best.index;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {out[2 + k] = sum[k];}
-      out[8] = sv.dth[itheta];
+    n_useful += job_useful;
+
+    // ---- epilogue
+    if (P > 1) {
+      // this chunk's sums; region_chunk_reduce_kernel adds the chunks and finishes the job
+      double * out = chunk_sums + static_cast<size_t>(work) * RR;
+      for (uint32_t k = lane; k < RR; k += 32) {out[k] = acc_d[k];}
+    } else {
+      job_epilogue(acc_d, sv, job, itheta, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
     }
     __syncwarp();
   }
@@ -510,13 +568,34 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
   pl.smem_tab = d_bytes + t_bytes <= kSmemTabBudget;
   pl.tab_bytes = pl.smem_tab ? static_cast<uint32_t>(d_bytes + t_bytes) : 0u;
   pl.smem_bytes = 16 + pl.tab_bytes + static_cast<size_t>(kWarpSmemBytes) * kWarps;
+  pl.P = 1;
+  pl.chunk_points = 0;
   return pl;
+}
+
+// Small searches: split the scan points of every job into chunks until there are
+// about kChunkTargetWork (job, chunk) pairs, bounded by the chunk-sum scratch.
+void plan_chunks(RegionPlan & pl, uint32_t n_pts, size_t chunk_cap_doubles)
+{
+  pl.P = 1;
+  pl.chunk_points = (n_pts + 31u) & ~31u;
+  const uint32_t steps = (n_pts + 31u) / 32u;
+  if (pl.n_jobs == 0 || steps < 2 || pl.n_jobs >= kChunkTargetWork) {return;}
+  uint32_t P = (kChunkTargetWork + pl.n_jobs - 1) / pl.n_jobs;
+  if (P > steps) {P = steps;}
+  const size_t per_chunk = static_cast<size_t>(pl.n_jobs) * pl.Rw * pl.Rw;
+  if (per_chunk * P > chunk_cap_doubles) {P = static_cast<uint32_t>(chunk_cap_doubles / per_chunk);}
+  if (P < 2) {return;}
+  const uint32_t spc = (steps + P - 1) / P;
+  pl.P = (steps + spc - 1) / spc;
+  pl.chunk_points = spc * 32u;
 }
 
 template<bool S, bool PRE>
 int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   uint32_t theta_begin, uint32_t n_theta, double * d_job_partials, double * d_scores,
-  uint32_t * d_counter, uint16_t * d_coords, cudaStream_t stream, Counters * ctr)
+  uint32_t * d_counter, uint16_t * d_coords, double * d_chunk_sums, cudaStream_t stream,
+  Counters * ctr)
 {
   auto kernel = search_region_kernel<S, PRE>;
   NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -526,7 +605,7 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // one persistent CTA per SM; small searches still spread over all SMs (the
   // warps of every CTA draw jobs from the same counter)
-  pl.grid = min(pl.n_jobs, static_cast<uint32_t>(sms));
+  pl.grid = min(pl.n_jobs * pl.P, static_cast<uint32_t>(sms));
   // d_counter: [0] job counter (u32, + pad), [1..2] u64 statistics of this launch
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 32, stream));
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
@@ -540,8 +619,14 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
   kernel<<<pl.grid, kWarps * 32, pl.smem_bytes, stream>>>(
     mv, sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, d_bytes, t_bytes, d_job_partials, d_scores,
-    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1, d_coords, n_pts_pad);
+    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1, d_coords, n_pts_pad, pl.P,
+    pl.chunk_points, d_chunk_sums);
   NDT2D_LAUNCH_CHECK(ctr);
+  if (pl.P > 1) {
+    region_chunk_reduce_kernel<<<(pl.n_jobs + 7u) / 8u, 256, 0, stream>>>(
+      sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, pl.P, d_chunk_sums, d_job_partials, d_scores);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
   return NDT2D_OK;
 }
 
@@ -586,6 +671,19 @@ size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_li
   return worst <= cap_bytes ? worst : 0;  // 0: the search computes coordinates per job
 }
 
+size_t ndt2d_region_chunk_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
+  double linear_res, uint32_t n_pts)
+{
+  // any theta sub-range: at most ~2 * kChunkTargetWork (job, chunk) pairs of Rw^2 sums
+  // (regions of small searches are shrunk to <= 13 x 13 before chunking matters)
+  (void)cell_size;
+  (void)n_ang;
+  (void)n_lin;
+  (void)linear_res;
+  if (n_pts < 64) {return 0;}
+  return static_cast<size_t>(2) * kChunkTargetWork * 13 * 13;
+}
+
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
@@ -594,12 +692,13 @@ int ndt2d_launch_search_region(
 {
   RegionPlan pl = make_plan(mv.g, n_theta, sv.n_lin, linear_res);
   *n_jobs = pl.n_jobs;
+  plan_chunks(pl, sv.n_pts, sv.chunk_sums ? sv.chunk_cap_doubles : 0);
   // the pre-pass pays off when a slice has several regions per axis to share it
   const bool pre = d_coords && pl.Q >= 2 && sv.n_pts > 0 &&
     coords_bytes(pl, n_theta, sv.n_pts) <= coords_cap_bytes;
 #define NDT2D_REGION_LAUNCH(S, P) \
   launch_one<S, P>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
-    d_coords, stream, ctr)
+    d_coords, sv.chunk_sums, stream, ctr)
   if (pl.smem_tab) {
     return pre ? NDT2D_REGION_LAUNCH(true, true) : NDT2D_REGION_LAUNCH(true, false);
   }
