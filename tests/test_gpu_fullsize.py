@@ -1,0 +1,160 @@
+"""BASELINE.json's FULL sizes on the GPU.  Where the oracle finishes in seconds it is compared
+directly; where it cannot (config 4: 5.4e11 evaluations, hours on a CPU) the result is pinned
+through size-independent properties: partition invariance (theta slices, interleaved or
+contiguous, combine to the same answer), agreement of two independently written kernels on a
+sub-volume, candidate-count bookkeeping, and an oracle search of the window around the winner."""
+import numpy as np
+import pytest
+
+from ndt_2d_b200 import ParticleFilter, Pose2d, Scan, ScanMatcherNDT, sharded, synth
+from oracle import binding as B
+from test_gpu_parity import RTOL, ATOL_SCORE, check_cells, ref_keys, world_points
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def o(oracle, gpu):
+    return oracle
+
+
+# ------------------------------------------------------------------ config 5: 20,000 scans, 0.1 m grid
+def test_config5_full_build(o):
+    w = synth.config5()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.poses, w.offsets, w.points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.poses, w.offsets, w.points)                          # ~1 s on the host
+    assert m.grid_info() == mo.grid()
+    n_pts = w.points.shape[0]
+    keys = m.dump_keys(n_pts)
+    expect = ref_keys(mo.grid(), world_points(w.poses, w.offsets, w.points))
+    assert np.array_equal(keys, expect)                                 # 5.6 M cell indices, bit-exact
+    gc, oc = m.dump_cells(), mo.dump_cells()
+    check_cells(gc, oc)                                                 # every cell of the 1200 x 1200 grid
+    assert gc[:, 1].sum() == (expect >= 0).sum()                        # every in-grid point counted once
+    assert m.counters()["valid_cells"] == int((oc[:, 1] >= 5).sum())
+
+
+# ------------------------------------------------------------------ config 2: 5,000 particles
+def test_config2_full_filter(o):
+    w = synth.config2()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)           # 2,500 scans, 473 x 473 cells
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    assert m.grid_info() == mo.grid()
+    P = w.particles.shape[0]
+    assert P == 5000
+    f = ParticleFilter(w.min_particles, w.max_particles)
+    f.set_particles(w.particles, np.full(P, 1.0 / P))
+    f.set_covariance(np.zeros((3, 3)))
+    f.measure(m, Scan(0, Pose2d(), w.scan_points))
+    raw = B.pf_measure(o, mo, w.particles, w.scan_points)
+    wn, mean_o, cov_o = B.pf_update_statistics(o, w.particles, raw, np.zeros((3, 3)))
+    _, wg = f.get_particles()
+    np.testing.assert_allclose(wg, wn, rtol=RTOL, atol=1e-30)
+    np.testing.assert_allclose(f.getMean(), mean_o, rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(f.getCovariance(), cov_o, rtol=RTOL, atol=RTOL * np.abs(cov_o).max())
+    # scorePoses == 5,000 calls of the reference's scorePoints
+    np.testing.assert_allclose(m.scorePoses(w.scan_points, w.particles), raw, rtol=RTOL, atol=ATOL_SCORE)
+    # resample with a replayed uniform stream: same draws, same KLD stop index
+    u = synth.uniform(99, w.max_particles)
+    po, wo, idx = B.pf_resample(o, w.particles, wn, w.min_particles, w.max_particles, w.kld_err, w.kld_z, u)
+    f.set_particles(w.particles, wn)
+    f.resample(w.kld_err, w.kld_z, uniforms=u)
+    assert f.size() == po.shape[0] and np.array_equal(f.last_draws(), idx)
+    assert np.array_equal(f.get_particles()[0], po)
+
+
+# ------------------------------------------------------------------ config 3: 50 loop-closure jobs
+def test_config3_full_batch(o):
+    w = synth.config3()
+    n_jobs = w.query_poses.shape[0]
+    assert n_jobs == 50
+    m = ScanMatcherNDT.from_params(w.params)
+    score, delta, written, cov = m.match_scan_batch(w.job_scan_offsets, w.map_poses, w.map_offsets,
+                                                    w.map_points, w.query_poses, w.query_offsets,
+                                                    w.query_points)
+    mo = o.new_matcher(w.params)
+    for j in range(n_jobs):
+        s0, s1 = int(w.job_scan_offsets[j]), int(w.job_scan_offsets[j + 1])
+        mo.reset()
+        offs = w.map_offsets[s0:s1 + 1]
+        mo.add_scans(w.map_poses[s0:s1], offs - offs[0], w.map_points[int(offs[0]):int(offs[-1])])
+        q0, q1 = int(w.query_offsets[j]), int(w.query_offsets[j + 1])
+        so, do, wo, co, sc = mo.match_scan(w.query_poses[j], w.query_points[q0:q1], want_scores=True)
+        assert written[j] == wo
+        np.testing.assert_allclose(score[j], so, rtol=RTOL, atol=ATOL_SCORE)
+        if wo and not np.array_equal(delta[j], do):
+            flat = sc.ravel()
+            assert (np.abs(flat - flat.min()) <= RTOL * abs(flat.min())).sum() > 1, (j, delta[j], do)
+        if np.all(np.isfinite(co)):
+            np.testing.assert_allclose(cov[j], co, rtol=RTOL, atol=RTOL * np.abs(co).max())
+
+
+# ------------------------------------------------------------------ config 4: 502,720,000 candidates
+@pytest.fixture(scope="module")
+def big(o):
+    w = synth.config4()
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    full = m.match_scan_raw(w.query_pose, w.query_points)
+    return w, m, full
+
+
+def test_config4_full_search_winner_matches_oracle_window(o, big):
+    w, m, (score, delta, written, cov, _) = big
+    na, nl = m.search_shape()
+    assert (na, nl) == (3142, 400)                                      # accumulated-double loop counts
+    assert written
+    dth, dlin = m.search_values()
+    it = int(np.argmin(np.abs(dth - delta[2])))
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    # the reference's sequential search restricted to the 3 theta slices around the winner
+    # (480,000 candidates): same candidate, same score
+    so, ncand, do, wo, _ = mo.match_scan_window(w.query_pose, w.query_points, max(0, it - 1), min(na, it + 2))
+    assert wo and np.array_equal(do, delta)
+    np.testing.assert_allclose(score, so, rtol=RTOL)
+    # and the winner is at the true pose up to the lattice step
+    est = w.query_pose + delta
+    assert abs(est[0] - w.true_pose[0]) <= 0.011 and abs(est[1] - w.true_pose[1]) <= 0.011
+    assert abs(est[2] - w.true_pose[2]) <= 0.0021
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_config4_full_search_partition_invariance(big, world):
+    """theta slices interleaved over `world` ranks + one combine == the single search."""
+    w, m, (score, delta, written, cov, _) = big
+    na, nl = m.search_shape()
+    m.stage_scan(w.query_pose, w.query_points)
+    parts = []
+    for r in range(world):
+        b, e, st = sharded.theta_slices(na, r, world)
+        m.search_staged(b, e, stride=st)
+        parts.append(m.fetch_partial())
+    parts = np.array(parts)
+    assert parts[:, 12].sum() == na * nl * nl == 502_720_000            # every candidate exactly once
+    s, d, wr, c = m.combine_partials(parts)
+    assert wr == written and np.array_equal(d, delta) and s == score
+    np.testing.assert_allclose(c, cov, rtol=1e-9, atol=1e-12 * np.abs(cov).max())
+
+
+def test_config4_slab_two_kernels_agree(big):
+    """The production kernel and the plain per-candidate kernel (reference arithmetic per
+    evaluation, written independently) on the same 6 theta slices of the full lattice:
+    960,000 candidates, same argmin, same partial sums."""
+    w, m, _ = big
+    m1 = ScanMatcherNDT.from_params(w.params, kernel_variant=1)
+    m1.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    for lo in (0, 1768):
+        m.stage_scan(w.query_pose, w.query_points)
+        m1.stage_scan(w.query_pose, w.query_points)
+        m.search_staged(lo, lo + 6)
+        m1.search_staged(lo, lo + 6)
+        a, b = m.fetch_partial(), m1.fetch_partial()
+        assert a[12] == b[12] == 6 * 400 * 400
+        assert a[1] == b[1]                                             # same best candidate index
+        np.testing.assert_allclose(a[0], b[0], rtol=RTOL)
+        np.testing.assert_allclose(a[2:12], b[2:12], rtol=RTOL, atol=1e-12)
