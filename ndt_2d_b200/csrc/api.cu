@@ -185,6 +185,12 @@ struct ndt2d_matcher
   uint32_t n_pts = 0;
 
   PinnedBuffer h_stage, h_result;
+  // Pipelined mode (match_scan_batch): host staging comes from a pinned arena that is
+  // only recycled after a stream synchronisation, and no call waits for the device.
+  bool pipelined = false;
+  PinnedBuffer h_arena;
+  size_t arena_off = 0;
+  DeviceBuffer d_batch_results;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the last search kernel
   bool ev_valid = false;
 };
@@ -225,6 +231,31 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.chunk_sums = m->d_chunk.as<double>();
   sv.chunk_cap_doubles = m->d_chunk.cap / sizeof(double);
   return sv;
+}
+
+// Host staging for `bytes` of H2D source data.  Normal mode: the handle's pinned buffer
+// (the caller synchronises before returning, so it can be reused by the next call).
+// Pipelined mode: a slice of the arena; when the arena is exhausted the stream is
+// drained once and the arena starts over.
+int stage_alloc(ndt2d_matcher * m, size_t bytes, char ** out)
+{
+  bytes = (bytes + 63) & ~size_t(63);
+  if (!m->pipelined) {
+    const int rc = m->h_stage.ensure(bytes);
+    *out = m->h_stage.as<char>();
+    return rc;
+  }
+  if (m->arena_off + bytes > m->h_arena.cap) {
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->arena_off = 0;
+    if (bytes > m->h_arena.cap) {
+      const int rc = m->h_arena.ensure(bytes * 2);
+      if (rc) {return rc;}
+    }
+  }
+  *out = m->h_arena.as<char>() + m->arena_off;
+  m->arena_off += bytes;
+  return NDT2D_OK;
 }
 
 // scan_matcher_ndt.cpp:95-96,110 : n = min(laser_max_beams, N); j = size_t(i * (N / n))
@@ -292,9 +323,9 @@ int add_scans_locked(
   const size_t tf_bytes = n_scans * sizeof(double4);
   const size_t off_bytes = (n_scans + 1) * sizeof(uint64_t);
   const size_t thr_bytes = (thr_x.size() + thr_y.size()) * sizeof(double);
-  int rc = m->h_stage.ensure(tf_bytes + off_bytes + thr_bytes);
+  char * hs = nullptr;
+  int rc = stage_alloc(m, tf_bytes + off_bytes + thr_bytes, &hs);
   if (rc) {return rc;}
-  char * hs = m->h_stage.as<char>();
   double4 * h_tf = reinterpret_cast<double4 *>(hs);
   uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + tf_bytes);
   double * h_thr = reinterpret_cast<double *>(hs + tf_bytes + off_bytes);
@@ -352,7 +383,15 @@ int add_scans_locked(
   NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_offsets.p, h_off, off_bytes, cudaMemcpyHostToDevice, st));
   NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_thr.p, h_thr, thr_bytes, cudaMemcpyHostToDevice, st));
   if (n_points) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_mappts.p, pts_xy + 2 * off0, n_points * sizeof(double2),
+    const double * src = pts_xy + 2 * off0;
+    if (m->pipelined) {
+      // pageable sources make cudaMemcpyAsync wait for the stream: go through the arena
+      char * hp = nullptr;
+      if ((rc = stage_alloc(m, n_points * sizeof(double2), &hp))) {return rc;}
+      memcpy(hp, src, n_points * sizeof(double2));
+      src = reinterpret_cast<const double *>(hp);
+    }
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_mappts.p, src, n_points * sizeof(double2),
       cudaMemcpyHostToDevice, st));
   }
   m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
@@ -362,7 +401,9 @@ int add_scans_locked(
       m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st,
       &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
-  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
+  if (!m->pipelined) {
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
+  }
   m->g = g;
   m->n_map_points = n_points;
   m->has_model = true;
@@ -376,11 +417,12 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   const size_t n_ang = m->dth.size();
   const size_t pts_bytes = n_use * sizeof(double2);
   const size_t trig_bytes = n_ang * sizeof(double2);
-  int rc = m->h_stage.ensure(pts_bytes + trig_bytes + 64);
+  char * hs = nullptr;
+  int rc = stage_alloc(m, pts_bytes + trig_bytes + 64, &hs);
   if (rc) {return rc;}
   if ((rc = m->d_pts.ensure(pts_bytes ? pts_bytes : 16))) {return rc;}
   if ((rc = m->d_trig.ensure(trig_bytes ? trig_bytes : 16))) {return rc;}
-  double * h_pts = m->h_stage.as<double>();
+  double * h_pts = reinterpret_cast<double *>(hs);
   double * h_trig = h_pts + 2 * n_use;
   if (n_use) {subsample_points(pts_xy, npts, n_use, h_pts);}
   for (size_t k = 0; k < n_ang; ++k) {
@@ -419,7 +461,9 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   }
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
   // the pinned staging area is reused by the next call: wait for the copies
-  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  if (!m->pipelined) {
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   m->staged = true;
   return NDT2D_OK;
 }
@@ -630,10 +674,11 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
       &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
-      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk};
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();
+    m->h_arena.release();
     if (m->ev_begin) {cudaEventDestroy(m->ev_begin);}
     if (m->ev_end) {cudaEventDestroy(m->ev_end);}
     if (m->own_stream && m->stream) {cudaStreamDestroy(m->stream);}
@@ -734,20 +779,56 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
   }
   std::lock_guard<std::mutex> lock(m->mu);
   DeviceGuard guard(m->device);
-  for (size_t j = 0; j < n_jobs; ++j) {
-    const uint64_t s0 = job_scan_offsets[j], s1 = job_scan_offsets[j + 1];
-    int rc = add_scans_locked(m, static_cast<size_t>(s1 - s0), map_poses + 3 * s0,
-        map_pt_offsets + s0, map_pts_xy);
-    if (rc) {return rc;}
-    const uint64_t q0 = query_pt_offsets[j], q1 = query_pt_offsets[j + 1];
-    if (delta_written) {delta_written[j] = 0;}
-    rc = match_scan_locked(m, query_poses + 3 * j, query_pts_xy + 2 * q0,
-        static_cast<size_t>(q1 - q0), out_delta3 ? out_delta3 + 3 * j : nullptr,
-        delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
-        out_score ? out_score + j : nullptr);
-    if (rc) {return rc;}
+  if (n_jobs == 0) {
+    m->has_model = false;
+    return NDT2D_OK;
   }
+  // Pipelined: every job's build + search is enqueued on the handle's stream without
+  // waiting for the device (host staging from the pinned arena); the 32-double result
+  // records are collected on the device and fetched with one copy at the end.
+  int rc = m->h_arena.ensure(size_t(8) << 20);
+  if (!rc) {rc = m->d_batch_results.ensure(n_jobs * 32 * sizeof(double));}
+  if (!rc) {rc = m->h_result.ensure(std::max<size_t>(n_jobs * 32, 64) * sizeof(double));}
+  if (rc) {return rc;}
+  m->pipelined = true;
+  m->arena_off = 0;
+  for (size_t j = 0; j < n_jobs && !rc; ++j) {
+    const uint64_t s0 = job_scan_offsets[j], s1 = job_scan_offsets[j + 1];
+    rc = add_scans_locked(m, static_cast<size_t>(s1 - s0), map_poses + 3 * s0,
+        map_pt_offsets + s0, map_pts_xy);
+    if (rc) {break;}
+    const uint64_t q0 = query_pt_offsets[j], q1 = query_pt_offsets[j + 1];
+    rc = stage_scan_locked(m, query_poses + 3 * j, query_pts_xy + 2 * q0,
+        static_cast<size_t>(q1 - q0));
+    if (rc) {break;}
+    rc = ndt2d_launch_search(model_view(m), search_view(m), 0,
+        static_cast<uint32_t>(m->dth.size()), m->prm.kernel_variant, m->d_blockpart.as<double>(),
+        m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
+    if (rc) {break;}
+    if (cudaMemcpyAsync(m->d_batch_results.as<double>() + 32 * j, m->d_partial.p,
+      32 * sizeof(double), cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess)
+    {
+      rc = NDT2D_ERR_CUDA;
+    }
+  }
+  m->pipelined = false;
   m->has_model = false;
+  m->staged = false;
+  m->ev_valid = false;
+  if (rc) {
+    cudaStreamSynchronize(m->stream);
+    return rc;
+  }
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->h_result.p, m->d_batch_results.p, n_jobs * 32 * sizeof(double),
+    cudaMemcpyDeviceToHost, m->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->ctr.d2h_bytes += n_jobs * 32 * sizeof(double);
+  for (size_t j = 0; j < n_jobs; ++j) {
+    if (delta_written) {delta_written[j] = 0;}
+    unpack_result(m->h_result.as<double>() + 32 * j, out_delta3 ? out_delta3 + 3 * j : nullptr,
+      delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
+      out_score ? out_score + j : nullptr);
+  }
   return NDT2D_OK;
 }
 
