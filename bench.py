@@ -250,10 +250,14 @@ def other_workloads(torch, dev_index: int):
     npts = int(w.points.shape[0])
     nocc = m.counters()["valid_cells"]
     algo = 16 * npts + 24 * w.poses.shape[0] + 48 * nocc
+    k_ms = m.build_stats()["kernels_ms"]
     out["config5_model_build"] = {
         "scans": int(w.poses.shape[0]), "points": npts, "grid": [sx, sy], "valid_cells": nocc,
         "add_scans_ms_e2e_pinned_host": t_b * 1e3, "points_per_s": npts / t_b,
-        "algorithmic_GBps_e2e": algo / t_b / 1e9}
+        "algorithmic_GBps_e2e": algo / t_b / 1e9,
+        "kernels_ms": k_ms, "points_per_s_device": npts / (k_ms * 1e-3) if k_ms else None,
+        "algorithmic_GBps_device": algo / (k_ms * 1e-3) / 1e9 if k_ms else None,
+        "hbm_roofline_frac_device": (algo / (k_ms * 1e-3) / 1e9) / measured_peaks()[0] if k_ms else None}
     m.close()
     return out
 

@@ -232,6 +232,9 @@ NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4);
  *     exit, [3] duration of the search kernel alone in nanoseconds (CUDA events
  *     recorded around it on the handle's stream). */
 NDT2D_API int ndt2d_matcher_search_stats(ndt2d_matcher * m, uint64_t * out4);
+/* The last model build: [0] duration of its kernels (K1..K3, H2D copies excluded) in
+ * nanoseconds, [1] map points, [2] occupied (n >= 5) cells, [3] cells of the grid. */
+NDT2D_API int ndt2d_matcher_build_stats(ndt2d_matcher * m, uint64_t * out4);
 /* cudaStream_t the handle runs on. */
 NDT2D_API void * ndt2d_matcher_stream(ndt2d_matcher * m);
 

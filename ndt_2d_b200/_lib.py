@@ -83,6 +83,7 @@ SIGNATURES = {
     "ndt2d_matcher_dump_scores": (C.c_int, [_vp, _dp, _dp, C.c_size_t, _dp, C.c_size_t]),
     "ndt2d_matcher_counters": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_search_stats": (C.c_int, [_vp, _u64p]),
+    "ndt2d_matcher_build_stats": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_stream": (_vp, [_vp]),
     "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),

@@ -174,7 +174,7 @@ struct ndt2d_matcher
   uint32_t n_valid = 0;
 
   BuildScratch bs{};
-  DeviceBuffer d_wx, d_wy, d_key0, d_key1, d_val0, d_val1, d_seglen, d_hist, d_scantmp;
+  DeviceBuffer d_sx, d_sy, d_heads, d_nheads, d_wx, d_wy, d_key0, d_key1, d_val0, d_val1, d_seglen, d_hist, d_scantmp;
   DeviceBuffer d_scan_tf, d_offsets, d_mappts;
   size_t n_map_points = 0;
   int sorted_buf = 0;
@@ -193,6 +193,8 @@ struct ndt2d_matcher
   DeviceBuffer d_batch_results;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the last search kernel
   bool ev_valid = false;
+  cudaEvent_t evb_begin = nullptr, evb_end = nullptr;  // bracket the kernels of the last build
+  bool evb_valid = false;
 };
 
 namespace
@@ -347,6 +349,9 @@ int add_scans_locked(
   if ((rc = m->d_mappts.ensure(np1 * sizeof(double2)))) {return rc;}
   if ((rc = m->d_wx.ensure(np1 * sizeof(double)))) {return rc;}
   if ((rc = m->d_wy.ensure(np1 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_sx.ensure(np1 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_sy.ensure(np1 * sizeof(double)))) {return rc;}
+  if ((rc = m->d_nheads.ensure(sizeof(uint32_t)))) {return rc;}
   if ((rc = m->d_key0.ensure(np1 * sizeof(uint32_t)))) {return rc;}
   if ((rc = m->d_key1.ensure(np1 * sizeof(uint32_t)))) {return rc;}
   if ((rc = m->d_val0.ensure(np1 * sizeof(uint32_t)))) {return rc;}
@@ -364,9 +369,14 @@ int add_scans_locked(
   m->rec_cap = static_cast<uint32_t>(cap64);
   if ((rc = m->d_rec.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
   if ((rc = m->d_rec_fast.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
+  if ((rc = m->d_heads.ensure(cap64 * sizeof(uint2)))) {return rc;}
 
   m->bs.wx = m->d_wx.as<double>();
   m->bs.wy = m->d_wy.as<double>();
+  m->bs.sx = m->d_sx.as<double>();
+  m->bs.sy = m->d_sy.as<double>();
+  m->bs.heads = m->d_heads.as<uint2>();
+  m->bs.n_heads = m->d_nheads.as<uint32_t>();
   m->bs.key[0] = m->d_key0.as<uint32_t>();
   m->bs.key[1] = m->d_key1.as<uint32_t>();
   m->bs.val[0] = m->d_val0.as<uint32_t>();
@@ -396,11 +406,16 @@ int add_scans_locked(
   }
   m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
 
+  if (m->evb_begin) {cudaEventRecord(m->evb_begin, st);}
   rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
       m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
       m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st,
       &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
+  if (m->evb_end) {
+    cudaEventRecord(m->evb_end, st);
+    m->evb_valid = true;
+  }
   if (!m->pipelined) {
     NDT2D_CUDA_TRY(cudaStreamSynchronize(st));  // host staging is reused by the next call
   }
@@ -641,8 +656,10 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
     }
     m->own_stream = true;
   }
-  if (cudaEventCreate(&m->ev_begin) != cudaSuccess || cudaEventCreate(&m->ev_end) != cudaSuccess) {
-    m->ev_begin = m->ev_end = nullptr;  // timing is optional
+  if (cudaEventCreate(&m->ev_begin) != cudaSuccess || cudaEventCreate(&m->ev_end) != cudaSuccess ||
+    cudaEventCreate(&m->evb_begin) != cudaSuccess || cudaEventCreate(&m->evb_end) != cudaSuccess)
+  {
+    m->ev_begin = m->ev_end = m->evb_begin = m->evb_end = nullptr;  // timing is optional
     cudaGetLastError();
   }
   const size_t na = m->dth.size(), nl = m->dlin.size();
@@ -672,7 +689,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
-      &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
+      &m->d_sx, &m->d_sy, &m->d_heads, &m->d_nheads, &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results};
     for (DeviceBuffer * b : bufs) {b->release();}
@@ -681,6 +698,8 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     m->h_arena.release();
     if (m->ev_begin) {cudaEventDestroy(m->ev_begin);}
     if (m->ev_end) {cudaEventDestroy(m->ev_end);}
+    if (m->evb_begin) {cudaEventDestroy(m->evb_begin);}
+    if (m->evb_end) {cudaEventDestroy(m->evb_end);}
     if (m->own_stream && m->stream) {cudaStreamDestroy(m->stream);}
   }
   delete m;
@@ -1122,6 +1141,30 @@ NDT2D_API int ndt2d_matcher_search_stats(ndt2d_matcher * m, uint64_t * out4)
       cudaGetLastError();
     }
   }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_build_stats(ndt2d_matcher * m, uint64_t * out4)
+{
+  if (!m || !out4) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  DeviceGuard guard(m->device);
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (m->evb_valid && m->evb_begin && m->evb_end) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->evb_begin, m->evb_end) == cudaSuccess) {
+      out4[0] = static_cast<uint64_t>(static_cast<double>(ms) * 1.0e6);
+    } else {
+      cudaGetLastError();
+    }
+  }
+  out4[1] = m->n_map_points;
+  uint32_t nv = 0;
+  NDT2D_CUDA_TRY(cudaMemcpy(&nv, m->d_nvalid.p, sizeof(nv), cudaMemcpyDeviceToHost));
+  out4[2] = nv;
+  out4[3] = static_cast<uint64_t>(m->g.size_x) * m->g.size_y;
   return NDT2D_OK;
 }
 

@@ -296,24 +296,54 @@ __device__ __forceinline__ uint32_t padded_index(const GridDesc & g, uint32_t ke
   return (gy + 1) * g.pitch + gx + 1;
 }
 
-// K3a: heads count their segment; cells with n >= 5 get their occupancy bit.
+// K3a: heads measure their segment (galloping + binary search for the end of the run of
+// equal keys: no serial walk); cells with n >= 5 get their occupancy bit and are appended
+// to the list of cells that need a record.
 __global__ void __launch_bounds__(256) segment_count_kernel(
   GridDesc g, const uint32_t * __restrict__ key, size_t n, uint32_t * __restrict__ seglen,
-  uint2 * __restrict__ occ)
+  uint2 * __restrict__ occ, uint2 * __restrict__ heads, uint32_t * __restrict__ n_heads)
 {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) {return;}
   const uint32_t k = key[i];
   if (k >= g.n_cells) {return;}
   if (i > 0 && key[i - 1] == k) {return;}
-  size_t j = i + 1;
-  while (j < n && key[j] == k) {++j;}
-  const uint32_t len = static_cast<uint32_t>(j - i);
+  // first position j > i with key[j] != k
+  size_t lo = i, step = 1;            // key[lo] == k
+  size_t hi = n;                      // key[hi] != k (or hi == n)
+  while (lo + step < n) {
+    if (key[lo + step] == k) {
+      lo += step;
+      step <<= 1;
+    } else {
+      hi = lo + step;
+      break;
+    }
+  }
+  while (hi - lo > 1) {
+    const size_t mid = lo + ((hi - lo) >> 1);
+    if (key[mid] == k) {lo = mid;} else {hi = mid;}
+  }
+  const uint32_t len = static_cast<uint32_t>(hi - i);
   seglen[i] = len;
   if (len >= 5) {
     const uint32_t p = padded_index(g, k);
     atomicOr(&occ[p >> 5].x, 1u << (p & 31u));
+    heads[atomicAdd(n_heads, 1u)] = make_uint2(static_cast<uint32_t>(i), len);
   }
+}
+
+// Sorted-order copies of the world coordinates: the moment kernels then read a cell's
+// points contiguously.
+__global__ void __launch_bounds__(256) gather_sorted_kernel(
+  const uint32_t * __restrict__ val, size_t n, const double * __restrict__ wx,
+  const double * __restrict__ wy, double * __restrict__ sx, double * __restrict__ sy)
+{
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) {return;}
+  const uint32_t p = val[i];
+  sx[i] = wx[p];
+  sy[i] = wy[p];
 }
 
 struct CellStats
@@ -368,70 +398,93 @@ __device__ __forceinline__ void stats_finalize(CellStats & c)
 }
 
 __device__ __forceinline__ void stats_walk(
-  CellStats & c, const uint32_t * __restrict__ val, const double * __restrict__ wx,
-  const double * __restrict__ wy, size_t i, uint32_t len)
+  CellStats & c, const double * __restrict__ sx, const double * __restrict__ sy, size_t i,
+  uint32_t len)
 {
   c.n = 0.0;
   c.mean[0] = c.mean[1] = 0.0;
   c.corr[0] = c.corr[1] = c.corr[2] = 0.0;
   for (uint32_t j = 0; j < len; ++j) {
-    const uint32_t p = val[i + j];
-    stats_add(c, wx[p], wy[p]);
+    stats_add(c, sx[i + j], sy[i + j]);
   }
 }
 
-// K3b: heads of cells with n >= 5 replay the recurrence and emit the record.
-__global__ void __launch_bounds__(128) segment_moments_kernel(
-  GridDesc g, const uint32_t * __restrict__ key, const uint32_t * __restrict__ val, size_t n,
-  const uint32_t * __restrict__ seglen, const double * __restrict__ wx,
-  const double * __restrict__ wy, const uint2 * __restrict__ occ, double * __restrict__ rec,
+// K3b: the cells of the head list replay Cell::addPoint's recurrence and emit their
+// records.  The five running quantities (mean x, mean y, second moments xx, xy, yy) are
+// independent recurrences of the same form v <- (v * n + term) / (n + 1), so a cell is
+// given to a group of 8 lanes, lanes 0..4 each carrying one of them through the cell's
+// points in order (bit-identical to the sequential CPU build, one divide per point on
+// the critical path instead of five); 4 cells per warp.
+__global__ void __launch_bounds__(256) segment_moments_kernel(
+  GridDesc g, const uint32_t * __restrict__ key, const uint2 * __restrict__ heads,
+  const uint32_t * __restrict__ n_heads, const double * __restrict__ sx,
+  const double * __restrict__ sy, const uint2 * __restrict__ occ, double * __restrict__ rec,
   double * __restrict__ rec_fast, uint32_t rec_cap, uint32_t * __restrict__ n_valid)
 {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
     // total number of occupied cells = prefix + popc of the last word
     const uint2 last = occ[g.n_words - 1];
     *n_valid = last.y + __popc(last.x);
   }
-  if (i >= n) {return;}
-  const uint32_t k = key[i];
-  if (k >= g.n_cells) {return;}
-  if (i > 0 && key[i - 1] == k) {return;}
-  const uint32_t len = seglen[i];
-  if (len < 5) {return;}
+  const uint32_t cell = t >> 3, r = t & 7u;
+  const uint32_t total = *n_heads;
+  const bool have = cell < total;
+  const uint2 h = have ? heads[cell] : make_uint2(0u, 0u);
+  const size_t i = h.x;
+  const uint32_t len = h.y;
+  double v = 0.0, n = 0.0;
+  if (have && r < 5u) {
+    for (uint32_t j = 0; j < len; ++j) {
+      const double x = sx[i + j], y = sy[i + j];
+      const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
+        r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
+      const double n1 = __dadd_rn(n, 1.0);
+      v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+      n = n1;
+    }
+  }
+  // collect the five quantities in lane 0 of the group (all 32 lanes shuffle)
   CellStats c;
-  stats_walk(c, val, wx, wy, i, len);
+  c.n = static_cast<double>(len);
+  c.mean[0] = __shfl_sync(0xffffffffu, v, 0, 8);
+  c.mean[1] = __shfl_sync(0xffffffffu, v, 1, 8);
+  c.corr[0] = __shfl_sync(0xffffffffu, v, 2, 8);
+  c.corr[1] = __shfl_sync(0xffffffffu, v, 3, 8);
+  c.corr[2] = __shfl_sync(0xffffffffu, v, 4, 8);
+  if (!have || r != 0u) {return;}
   stats_finalize(c);
+  const uint32_t k = key[i];
   const uint32_t p = padded_index(g, k);
   const uint2 w = occ[p >> 5];
   const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
   if (rank >= rec_cap) {return;}
-  double * r = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
+  double * rr = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
   // -0.5 * information: scaling by a power of two is exact, so the device
   // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
-  r[0] = c.mean[0];
-  r[1] = c.mean[1];
-  r[2] = -0.5 * c.info[0];  // (0,0)
-  r[3] = -0.5 * c.info[2];  // (1,0)
-  r[4] = -0.5 * c.info[1];  // (0,1)
-  r[5] = -0.5 * c.info[3];  // (1,1)
+  rr[0] = c.mean[0];
+  rr[1] = c.mean[1];
+  rr[2] = -0.5 * c.info[0];  // (0,0)
+  rr[3] = -0.5 * c.info[2];  // (1,0)
+  rr[4] = -0.5 * c.info[1];  // (0,1)
+  rr[5] = -0.5 * c.info[3];  // (1,1)
   // short-form record of the search kernel (ndt2d_internal.h, ModelView::rec_fast)
   constexpr double kLog2e = 1.44269504088896340736;
   double * f = rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
   const double mag = fmax(fmax(fabs(c.info[0]), fabs(c.info[3])), fmax(fabs(c.info[1]), fabs(c.info[2])));
   f[0] = c.mean[0];
   f[1] = c.mean[1];
-  f[2] = r[2] * kLog2e;
-  f[3] = (r[3] + r[4]) * kLog2e;
-  f[4] = r[5] * kLog2e;
+  f[2] = rr[2] * kLog2e;
+  f[3] = (rr[3] + rr[4]) * kLog2e;
+  f[4] = rr[5] * kLog2e;
   f[5] = (mag * (g.cell_size * g.cell_size) <= 1.0e7) ? 0.0 : 1.0;  // NaN -> stiff
 }
 
 // Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.
 __global__ void __launch_bounds__(128) segment_dump_kernel(
-  GridDesc g, const uint32_t * __restrict__ key, const uint32_t * __restrict__ val, size_t n,
-  const uint32_t * __restrict__ seglen, const double * __restrict__ wx,
-  const double * __restrict__ wy, double * __restrict__ out)
+  GridDesc g, const uint32_t * __restrict__ key, size_t n,
+  const uint32_t * __restrict__ seglen, const double * __restrict__ sx,
+  const double * __restrict__ sy, double * __restrict__ out)
 {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) {return;}
@@ -440,7 +493,7 @@ __global__ void __launch_bounds__(128) segment_dump_kernel(
   if (i > 0 && key[i - 1] == k) {return;}
   const uint32_t len = seglen[i];
   CellStats c;
-  stats_walk(c, val, wx, wy, i, len);
+  stats_walk(c, sx, sy, i, len);
   double * o = out + static_cast<size_t>(k) * 16;
   o[1] = c.n;
   o[2] = c.mean[0];
@@ -512,6 +565,7 @@ int ndt2d_launch_build(
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint2), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ_dilated, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, sizeof(uint32_t), stream));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(s.n_heads, 0, sizeof(uint32_t), stream));
   int cur = 0;
   if (n_points > 0) {
     const uint32_t grid = static_cast<uint32_t>(n_scans < 65535u * 8u ? n_scans : 65535u * 8u);
@@ -534,7 +588,10 @@ int ndt2d_launch_build(
       cur ^= 1;
     }
     const uint32_t nb = static_cast<uint32_t>((n_points + 255) / 256);
-    segment_count_kernel<<<nb, 256, 0, stream>>>(g, s.key[cur], n_points, s.seglen, d_occ);
+    segment_count_kernel<<<nb, 256, 0, stream>>>(g, s.key[cur], n_points, s.seglen, d_occ,
+      s.heads, s.n_heads);
+    NDT2D_LAUNCH_CHECK(ctr);
+    gather_sorted_kernel<<<nb, 256, 0, stream>>>(s.val[cur], n_points, s.wx, s.wy, s.sx, s.sy);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   {
@@ -544,10 +601,10 @@ int ndt2d_launch_build(
     NDT2D_LAUNCH_CHECK(ctr);
   }
   if (n_points > 0) {
-    const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);
-    segment_moments_kernel<<<nb, 128, 0, stream>>>(
-      g, s.key[cur], s.val[cur], n_points, s.seglen, s.wx, s.wy, d_occ, d_rec, d_rec_fast, rec_cap,
-      d_n_valid);
+    // one 8-lane group per listed cell; the list cannot be longer than rec_cap
+    const uint32_t nb = (rec_cap * 8u + 255u) / 256u;
+    segment_moments_kernel<<<nb, 256, 0, stream>>>(
+      g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, d_occ, d_rec, d_rec_fast, rec_cap, d_n_valid);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   *sorted_buf = cur;
@@ -563,7 +620,7 @@ int ndt2d_launch_dump_cells(
   if (n_points > 0) {
     const uint32_t nb = static_cast<uint32_t>((n_points + 127) / 128);
     segment_dump_kernel<<<nb, 128, 0, stream>>>(
-      g, s.key[sorted_buf], s.val[sorted_buf], n_points, s.seglen, s.wx, s.wy, d_out);
+      g, s.key[sorted_buf], n_points, s.seglen, s.sx, s.sy, d_out);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   return NDT2D_OK;

@@ -89,6 +89,9 @@ struct BuildScratch
 {
   // all device pointers, capacities in elements
   double * wx, * wy;        // world coordinates per map point
+  double * sx, * sy;        // the same in sorted (cell) order
+  uint2 * heads;            // (sorted position, length) of every cell with n >= 5
+  uint32_t * n_heads;
   uint32_t * key[2];        // ping-pong sort keys (cell index, n_cells = outside)
   uint32_t * val[2];        // ping-pong values (point index)
   uint32_t * seglen;        // per sorted position: segment length (heads only)

@@ -308,5 +308,12 @@ class ScanMatcherNDT:
         return dict(useful_evaluations=int(out[0]), items=int(out[1]), jobs_drawn=int(out[2]),
                     kernel_ms=float(out[3]) * 1e-6)
 
+    def build_stats(self) -> dict:
+        """The last model build (ndt2d_matcher_build_stats)."""
+        out = np.zeros(4, dtype=np.uint64)
+        L.check(L.lib.ndt2d_matcher_build_stats(self.handle, L.u64ptr(out)), "build_stats")
+        return dict(kernels_ms=float(out[0]) * 1e-6, points=int(out[1]), valid_cells=int(out[2]),
+                    grid_cells=int(out[3]))
+
     def stream(self) -> int:
         return int(L.lib.ndt2d_matcher_stream(self.handle) or 0)
