@@ -435,7 +435,26 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
   const uint32_t len = h.y;
   double v = 0.0, n = 0.0;
   if (have && r < 5u) {
-    for (uint32_t j = 0; j < len; ++j) {
+    // the loads of four points are issued before the (dependent) recurrence steps
+    // that consume them: the chain is then bound by the divide, not by memory latency
+    uint32_t j = 0;
+    for (; j + 4 <= len; j += 4) {
+      double x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        x[u] = sx[i + j + u];
+        y[u] = sy[i + j + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double term = r == 0u ? x[u] : r == 1u ? y[u] : r == 2u ? __dmul_rn(x[u], x[u]) :
+          r == 3u ? __dmul_rn(x[u], y[u]) : __dmul_rn(y[u], y[u]);
+        const double n1 = __dadd_rn(n, 1.0);
+        v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+        n = n1;
+      }
+    }
+    for (; j < len; ++j) {
       const double x = sx[i + j], y = sy[i + j];
       const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
         r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);

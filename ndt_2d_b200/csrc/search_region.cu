@@ -598,11 +598,20 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   Counters * ctr)
 {
   auto kernel = search_region_kernel<S, PRE>;
-  NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-    static_cast<int>(pl.smem_bytes)));
-  int dev = 0, sms = 148;
+  // per (instantiation, device): opt in to the large dynamic shared memory once, and
+  // remember the SM count (both calls cost microseconds that a 100 us search notices)
+  static int configured_sms[64] = {0};
+  int dev = 0;
   NDT2D_CUDA_TRY(cudaGetDevice(&dev));
-  NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int slot = dev & 63;
+  if (configured_sms[slot] == 0) {
+    int n = 148;
+    NDT2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      static_cast<int>(16 + kSmemTabBudget + static_cast<size_t>(kWarpSmemBytes) * kWarps)));
+    NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    configured_sms[slot] = n;
+  }
+  const int sms = configured_sms[slot];
   // one persistent CTA per SM; small searches still spread over all SMs (the
   // warps of every CTA draw jobs from the same counter)
   pl.grid = min(pl.n_jobs * pl.P, static_cast<uint32_t>(sms));
