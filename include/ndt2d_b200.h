@@ -145,6 +145,30 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
   const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
   double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
 
+/* replaces the inner loop of Mapper::loopClosureThread (ndt_mapper.cpp:619-671) for ONE
+ * new scan, with its sequential semantics: candidates (indices into the graph's scans, in
+ * Graph::findNearest order) are taken in order; a candidate whose scan has no points is
+ * skipped without counting (:625); candidate i is matched against a fresh model of the
+ * scans [i-1 (i if i == 0), i+1 if i < rolling else i) (:628-635); a finite score below
+ * typical_response (:645) is accepted and moves the query scan's pose by the correction
+ * (:652-655) BEFORE the next candidate is matched; at most search_limit candidates are
+ * processed (:671).  Internally all remaining candidates are matched speculatively in one
+ * batch and the remainder is re-issued after every acceptance, so the outputs equal the
+ * sequential loop's.
+ *   scan_poses / scan_pt_offsets / scan_pts_xy : the graph's scans (n_scans)
+ *   query_pose3   in: pose of the new scan; out: its pose after all accepted corrections
+ *   out_*         one entry per processed candidate (room for min(search_limit,
+ *                 n_candidates)): candidate index, score, accepted flag, scan pose after
+ *                 this candidate, covariance of the match
+ *   *n_batches    number of batch submissions it took (1 + number of acceptances that
+ *                 were not the last processed candidate) */
+NDT2D_API int ndt2d_matcher_close_loop(
+  ndt2d_matcher * m, size_t n_scans, const double * scan_poses, const uint64_t * scan_pt_offsets,
+  const double * scan_pts_xy, const uint64_t * candidates, size_t n_candidates, size_t rolling,
+  size_t search_limit, double typical_response, double * query_pose3, const double * query_pts_xy,
+  size_t query_npts, uint64_t * out_candidate, double * out_score, int * out_accepted,
+  double * out_pose3, double * out_cov9, size_t * n_processed, size_t * n_batches);
+
 /* ---- staged / partial search: device-resident inputs, theta-sliced ----- */
 
 /* Candidate lattice of this handle: the reference's accumulated-double loops

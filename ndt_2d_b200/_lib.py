@@ -66,6 +66,10 @@ SIGNATURES = {
     "ndt2d_matcher_likelihood_scan": (C.c_int, [_vp, _dp, _dp, C.c_size_t, _dp]),
     "ndt2d_matcher_match_scan_batch": (
         C.c_int, [_vp, C.c_size_t, _u64p, _dp, _u64p, _dp, _dp, _u64p, _dp, _dp, _ip, _dp, _dp]),
+    "ndt2d_matcher_close_loop": (
+        C.c_int, [_vp, C.c_size_t, _dp, _u64p, _dp, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double,
+                  _dp, _dp, C.c_size_t, _u64p, _dp, _ip, _dp, _dp, C.POINTER(C.c_size_t),
+                  C.POINTER(C.c_size_t)]),
     "ndt2d_matcher_search_shape": (C.c_int, [_vp, _u64p, _u64p]),
     "ndt2d_matcher_search_values": (C.c_int, [_vp, _dp, _dp]),
     "ndt2d_matcher_stage_scan": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),

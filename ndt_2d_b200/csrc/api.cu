@@ -577,6 +577,13 @@ int score_poses_locked(
 
 }  // namespace
 
+static int match_scan_batch_locked(
+  ndt2d_matcher * m, size_t n_jobs,
+  const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
+  const double * map_pts_xy,
+  const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+
 extern "C" {
 
 NDT2D_API const char * ndt2d_version(void) {return "ndt2d_b200 0.1 (sm_100a)";}
@@ -798,6 +805,20 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
   }
   std::lock_guard<std::mutex> lock(m->mu);
   DeviceGuard guard(m->device);
+  return match_scan_batch_locked(m, n_jobs, job_scan_offsets, map_poses, map_pt_offsets, map_pts_xy,
+           query_poses, query_pt_offsets, query_pts_xy, out_delta3, delta_written, out_cov9,
+           out_score);
+}
+
+}  // extern "C"
+
+static int match_scan_batch_locked(
+  ndt2d_matcher * m, size_t n_jobs,
+  const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
+  const double * map_pts_xy,
+  const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
   if (n_jobs == 0) {
     m->has_model = false;
     return NDT2D_OK;
@@ -847,6 +868,109 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
     unpack_result(m->h_result.as<double>() + 32 * j, out_delta3 ? out_delta3 + 3 * j : nullptr,
       delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
       out_score ? out_score + j : nullptr);
+  }
+  return NDT2D_OK;
+}
+
+extern "C" {
+
+// Mapper::loopClosureThread's inner loop (ndt_mapper.cpp:619-671) with its exact sequential
+// semantics, evaluated speculatively: all remaining candidates are matched in one batch with
+// the query scan's CURRENT pose; results are consumed in order up to and including the first
+// acceptance (finite score < typical_response, :645), which moves the scan pose (:652-655) and
+// thereby invalidates the later results of that batch -- the remainder is re-issued.
+NDT2D_API int ndt2d_matcher_close_loop(
+  ndt2d_matcher * m, size_t n_scans, const double * scan_poses, const uint64_t * scan_pt_offsets,
+  const double * scan_pts_xy, const uint64_t * candidates, size_t n_candidates, size_t rolling,
+  size_t search_limit, double typical_response, double * query_pose3, const double * query_pts_xy,
+  size_t query_npts, uint64_t * out_candidate, double * out_score, int * out_accepted,
+  double * out_pose3, double * out_cov9, size_t * n_processed, size_t * n_batches)
+{
+  if (!m || !query_pose3 || !n_processed || (n_scans && (!scan_poses || !scan_pt_offsets)) ||
+    (n_candidates && !candidates) || (query_npts && !query_pts_xy))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  *n_processed = 0;
+  if (n_batches) {*n_batches = 0;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  // candidates the reference would look at, in order: empty scans are skipped without
+  // counting (:625), at most search_limit are processed (:671)
+  std::vector<uint64_t> todo;
+  for (size_t k = 0; k < n_candidates && todo.size() < search_limit; ++k) {
+    const uint64_t i = candidates[k];
+    if (i >= n_scans) {return NDT2D_ERR_INVALID;}
+    if (scan_pt_offsets[i + 1] == scan_pt_offsets[i]) {continue;}
+    todo.push_back(i);
+  }
+  size_t next = 0;
+  std::vector<uint64_t> job_offsets, q_offsets;
+  std::vector<double> q_poses, delta, cov, score;
+  std::vector<int> written;
+  while (next < todo.size()) {
+    const size_t n_jobs = todo.size() - next;
+    // job j: window [i-1 (or i), i+1 if i < rolling else i) of the graph's scans (:628-631);
+    // the windows are contiguous scan ranges, so they index the caller's arrays directly
+    job_offsets.assign(1, 0);
+    std::vector<double> w_poses;
+    std::vector<uint64_t> w_offsets(1, 0);
+    std::vector<double> w_points;
+    for (size_t j = 0; j < n_jobs; ++j) {
+      const uint64_t i = todo[next + j];
+      const uint64_t begin = i > 0 ? i - 1 : i, end = i < rolling ? i + 1 : i;
+      for (uint64_t s = begin; s < end; ++s) {
+        w_poses.insert(w_poses.end(), scan_poses + 3 * s, scan_poses + 3 * s + 3);
+        w_points.insert(w_points.end(), scan_pts_xy + 2 * scan_pt_offsets[s],
+          scan_pts_xy + 2 * scan_pt_offsets[s + 1]);
+        w_offsets.push_back(w_points.size() / 2);
+      }
+      job_offsets.push_back(w_poses.size() / 3);
+    }
+    q_poses.resize(3 * n_jobs);
+    q_offsets.resize(n_jobs + 1);
+    std::vector<double> q_points(2 * query_npts * n_jobs);
+    for (size_t j = 0; j < n_jobs; ++j) {
+      memcpy(&q_poses[3 * j], query_pose3, 3 * sizeof(double));
+      q_offsets[j] = j * query_npts;
+      if (query_npts) {
+        memcpy(&q_points[2 * query_npts * j], query_pts_xy, 2 * query_npts * sizeof(double));
+      }
+    }
+    q_offsets[n_jobs] = n_jobs * query_npts;
+    delta.assign(3 * n_jobs, 0.0);
+    cov.assign(9 * n_jobs, 0.0);
+    score.assign(n_jobs, 0.0);
+    written.assign(n_jobs, 0);
+    const int rc = match_scan_batch_locked(m, n_jobs, job_offsets.data(), w_poses.data(),
+        w_offsets.data(), w_points.data(), q_poses.data(), q_offsets.data(), q_points.data(),
+        delta.data(), written.data(), cov.data(), score.data());
+    if (rc) {return rc;}
+    if (n_batches) {*n_batches += 1;}
+    // consume in order up to the first acceptance
+    size_t j = 0;
+    for (; j < n_jobs; ++j) {
+      const size_t o = *n_processed;
+      const bool accept = std::isfinite(score[j]) && score[j] < typical_response;  // :645
+      if (accept) {
+        // correction += scan pose; scan->setPose(correction)  (:652-655); an unwritten
+        // correction is the default Pose2d (0, 0, 0)
+        query_pose3[0] = (written[j] ? delta[3 * j] : 0.0) + query_pose3[0];
+        query_pose3[1] = (written[j] ? delta[3 * j + 1] : 0.0) + query_pose3[1];
+        query_pose3[2] = (written[j] ? delta[3 * j + 2] : 0.0) + query_pose3[2];
+      }
+      if (out_candidate) {out_candidate[o] = todo[next + j];}
+      if (out_score) {out_score[o] = score[j];}
+      if (out_accepted) {out_accepted[o] = accept ? 1 : 0;}
+      if (out_pose3) {memcpy(out_pose3 + 3 * o, query_pose3, 3 * sizeof(double));}
+      if (out_cov9) {memcpy(out_cov9 + 9 * o, &cov[9 * j], 9 * sizeof(double));}
+      *n_processed = o + 1;
+      if (accept) {
+        ++j;
+        break;
+      }
+    }
+    next += j;
   }
   return NDT2D_OK;
 }

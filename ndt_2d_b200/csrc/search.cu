@@ -130,7 +130,7 @@ __device__ void finish_record(double * rec, const double * dth, const double * d
   }
   // :148 (n == 0 -> NaN, as in the reference); `best` stays the +0.0 it was
   // initialised with when no candidate scored below zero (:83,128)
-  rec[29] = (written ? best : 0.0) / n;
+  rec[29] = written ? best / n : 0.0 / n;
   rec[30] = rec[31] = 0.0;
 }
 

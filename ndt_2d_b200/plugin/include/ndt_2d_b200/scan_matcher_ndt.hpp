@@ -80,6 +80,25 @@ public:
     const std::vector<std::vector<ndt_2d::ScanPtr>> & maps,
     const std::vector<ndt_2d::ScanPtr> & scans);
 
+  // The inner loop of Mapper::loopClosureThread (ndt_mapper.cpp:619-671) for one new scan,
+  // sequential semantics kept (an accepted match moves `scan`'s pose before the next
+  // candidate is matched), evaluated as speculative batches.  `graph_scans` is
+  // graph_->scans, `candidates` the result of Graph::findNearest, in its order.  The
+  // caller still owns the graph: it adds a constraint per accepted entry
+  // (makeConstraint(graph_scans[candidate], scan, covariance), :658-661).
+  struct LoopClosure
+  {
+    size_t candidate;
+    double score;
+    bool accepted;
+    ndt_2d::Pose2d scan_pose;       // pose of `scan` after this candidate
+    Eigen::Matrix3d covariance;
+  };
+  std::vector<LoopClosure> closeLoop(
+    const std::vector<ndt_2d::ScanPtr> & graph_scans, const ndt_2d::ScanPtr & scan,
+    const std::vector<size_t> & candidates, size_t rolling, size_t search_limit,
+    double typical_response, size_t * n_batches = nullptr);
+
   // CUDA device / stream selection, before initialize() (defaults: current device,
   // a stream owned by the handle).
   void setDevice(int device, void * cuda_stream = nullptr);

@@ -1,6 +1,7 @@
 // ndt_2d_b200::ScanMatcherNDT -- see include/ndt_2d_b200/scan_matcher_ndt.hpp.
 #include <ndt_2d_b200/scan_matcher_ndt.hpp>
 
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -208,6 +209,48 @@ std::vector<ScanMatcherNDT::BatchResult> ScanMatcherNDT::matchScanBatch(
     for (int r = 0; r < 3; ++r) {
       for (int c = 0; c < 3; ++c) {out[j].covariance(r, c) = cov[9 * j + 3 * r + c];}
     }
+  }
+  return out;
+}
+
+std::vector<ScanMatcherNDT::LoopClosure> ScanMatcherNDT::closeLoop(
+  const std::vector<ndt_2d::ScanPtr> & graph_scans, const ndt_2d::ScanPtr & scan,
+  const std::vector<size_t> & candidates, size_t rolling, size_t search_limit,
+  double typical_response, size_t * n_batches)
+{
+  require_handle("closeLoop");
+  FlatScans graph;
+  for (const auto & s : graph_scans) {graph.append(s);}
+  std::vector<uint64_t> cand(candidates.begin(), candidates.end());
+  const ndt_2d::Pose2d pose0 = scan->getPose();
+  double query_pose[3] = {pose0.x, pose0.y, pose0.theta};
+  const std::vector<ndt_2d::Point> points = scan->getPoints();
+  const size_t cap = std::max<size_t>(1, std::min(search_limit, cand.size()));
+  std::vector<uint64_t> out_cand(cap);
+  std::vector<double> out_score(cap), out_pose(3 * cap), out_cov(9 * cap);
+  std::vector<int> out_acc(cap);
+  size_t n = 0, nb = 0;
+  const int rc = ndt2d_matcher_close_loop(
+    handle_, graph.n_scans(), graph.poses.data(), graph.offsets_ptr(), graph.points.data(),
+    cand.data(), cand.size(), rolling, search_limit, typical_response, query_pose, xy(points),
+    points.size(), out_cand.data(), out_score.data(), out_acc.data(), out_pose.data(),
+    out_cov.data(), &n, &nb);
+  if (rc != NDT2D_OK) {fail("closeLoop", rc);}
+  if (n_batches) {*n_batches = nb;}
+  std::vector<LoopClosure> out(n);
+  bool any = false;
+  for (size_t k = 0; k < n; ++k) {
+    out[k].candidate = static_cast<size_t>(out_cand[k]);
+    out[k].score = out_score[k];
+    out[k].accepted = out_acc[k] != 0;
+    out[k].scan_pose = ndt_2d::Pose2d(out_pose[3 * k], out_pose[3 * k + 1], out_pose[3 * k + 2]);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {out[k].covariance(r, c) = out_cov[9 * k + 3 * r + c];}
+    }
+    any = any || out[k].accepted;
+  }
+  if (any) {
+    scan->setPose(ndt_2d::Pose2d(query_pose[0], query_pose[1], query_pose[2]));  // :655
   }
   return out;
 }

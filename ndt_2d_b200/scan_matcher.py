@@ -224,6 +224,30 @@ class ScanMatcherNDT:
             L.dptr(cov), L.dptr(score)), "ndt2d_matcher_match_scan_batch")
         return score, delta, written.astype(bool), cov
 
+    def close_loop(self, scan_poses, scan_offsets, scan_points, candidates, rolling: int,
+                   search_limit: int, typical_response: float, query_pose, query_points):
+        """Mapper::loopClosureThread's inner loop for one new scan (ndt_mapper.cpp:619-671).
+        -> (final query pose[3], list of dicts per processed candidate, n_batches)"""
+        sp = L.f64(scan_poses).reshape(-1, 3)
+        so = np.ascontiguousarray(scan_offsets, dtype=np.uint64)
+        spts = L.f64(scan_points).reshape(-1, 2)
+        cand = np.ascontiguousarray(candidates, dtype=np.uint64)
+        qp = _pose3(query_pose).copy()
+        qpts = L.f64(query_points).reshape(-1, 2)
+        cap = max(1, min(int(search_limit), cand.shape[0]))
+        oc = np.zeros(cap, dtype=np.uint64)
+        osc, oacc = np.zeros(cap), np.zeros(cap, dtype=np.int32)
+        opose, ocov = np.zeros((cap, 3)), np.zeros((cap, 3, 3))
+        n, nb = C.c_size_t(0), C.c_size_t(0)
+        L.check(L.lib.ndt2d_matcher_close_loop(
+            self.handle, sp.shape[0], L.dptr(sp), L.u64ptr(so), L.dptr(spts), L.u64ptr(cand), cand.shape[0],
+            rolling, search_limit, typical_response, L.dptr(qp), L.dptr(qpts), qpts.shape[0], L.u64ptr(oc),
+            L.dptr(osc), oacc.ctypes.data_as(C.POINTER(C.c_int)), L.dptr(opose), L.dptr(ocov),
+            C.byref(n), C.byref(nb)), "ndt2d_matcher_close_loop")
+        out = [dict(candidate=int(oc[k]), score=float(osc[k]), accepted=bool(oacc[k]), pose=opose[k].copy(),
+                    covariance=ocov[k].copy()) for k in range(n.value)]
+        return qp, out, int(nb.value)
+
     # ---- staged / partial search
     def search_shape(self):
         na, nl = C.c_uint64(0), C.c_uint64(0)

@@ -201,6 +201,61 @@ int main(int argc, char ** argv)
     compare_match(r2, d2, q2, "plugin defaults");
   }
 
+  // ---- loop closure: the reference's sequential loop (ndt_mapper.cpp:619-671, written out
+  // here against the reference plugin) next to ScanMatcherNDT::closeLoop
+  {
+    const std::vector<size_t> candidates = {3, 8, 0, 9, 6, 1};
+    const size_t rolling = 8, limit = 5;
+    const double typical = -0.05;
+    ndt_2d::ScanPtr sr(new ndt_2d::Scan(200)), sd(new ndt_2d::Scan(201));
+    for (auto & s : {sr, sd}) {
+      s->setPose(query->getPose());
+      s->setPoints(query->getPoints());
+    }
+    struct Seq {size_t i; double score; bool accepted; ndt_2d::Pose2d pose;};
+    std::vector<Seq> seq;
+    size_t left = limit;
+    for (auto i : candidates) {
+      if (scans[i]->getPoints().empty()) {continue;}
+      const size_t begin_idx = (i > 0) ? i - 1 : i, end_idx = (i < rolling) ? i + 1 : i;
+      ref->reset();
+      ref->addScans(scans.begin() + begin_idx, scans.begin() + end_idx);
+      ndt_2d::Pose2d correction;
+      Eigen::Matrix3d covariance;
+      const double score = ref->matchScan(sr, correction, covariance);
+      const bool accept = std::isfinite(score) && (score < typical);
+      if (accept) {
+        correction.x += sr->getPose().x;
+        correction.y += sr->getPose().y;
+        correction.theta += sr->getPose().theta;
+        sr->setPose(correction);
+      }
+      seq.push_back({i, score, accept, sr->getPose()});
+      if (--left == 0) {break;}
+    }
+    size_t n_batches = 0;
+    auto * ours = dynamic_cast<ndt_2d_b200::ScanMatcherNDT *>(dev.get());
+    const auto got = ours->closeLoop(scans, sd, candidates, rolling, limit, typical, &n_batches);
+    expect(got.size() == seq.size(), "closeLoop processes the same candidates");
+    size_t accepted = 0;
+    for (size_t k = 0; k < got.size() && k < seq.size(); ++k) {
+      expect(got[k].candidate == seq[k].i && got[k].accepted == seq[k].accepted, "closeLoop decisions");
+      expect(close_rel(got[k].score, seq[k].score, 1e-5, 1e-30), "closeLoop scores within 1e-5");
+      expect(got[k].scan_pose.x == seq[k].pose.x && got[k].scan_pose.y == seq[k].pose.y &&
+        got[k].scan_pose.theta == seq[k].pose.theta, "closeLoop poses identical");
+      accepted += seq[k].accepted ? 1 : 0;
+    }
+    expect(sd->getPose().x == sr->getPose().x && sd->getPose().theta == sr->getPose().theta,
+      "closeLoop leaves the scan at the reference's pose");
+    std::printf("closeLoop: %zu candidates, %zu accepted, %zu batch submissions\n", got.size(),
+      accepted, n_batches);
+    // restore the rolling-window model for the checks below
+    for (auto & m : {ref, dev}) {
+      m->reset();
+      m->addScans(scans.begin(), scans.end());
+    }
+  }
+
   // ---- scorePoints at assorted poses ------------------------------------------------
   const std::vector<ndt_2d::Point> qpts = query->getPoints();
   for (int k = 0; k < 8; ++k) {

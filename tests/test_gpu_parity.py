@@ -333,6 +333,66 @@ def test_match_scan_batch(o):
     assert m.match_scan_raw(w.query_poses[0], w.query_points[:10])[4] == L.ERR_NO_MAP
 
 
+def _sequential_loop_closure(mo, poses, offs, pts, candidates, rolling, limit, typical, qpose, qpts):
+    """The reference's inner loop (ndt_mapper.cpp:619-671) with the oracle matcher, one
+    candidate at a time."""
+    qpose = np.array(qpose, dtype=np.float64)
+    out, left = [], limit
+    for i in candidates:
+        i = int(i)
+        if offs[i + 1] == offs[i]:
+            continue                                                              # :625
+        b, e = (i - 1 if i > 0 else i), (i + 1 if i < rolling else i)             # :628-631
+        mo.reset()
+        o = offs[b:e + 1]
+        mo.add_scans(poses[b:e], o - o[0], pts[int(o[0]):int(o[-1])])
+        s, d, written, cov, _ = mo.match_scan(qpose, qpts)
+        accept = bool(np.isfinite(s) and s < typical)                             # :645
+        if accept:
+            qpose = (d if written else np.zeros(3)) + qpose                       # :652-655
+        out.append(dict(candidate=i, score=s, accepted=accept, pose=qpose.copy(), covariance=cov))
+        left -= 1
+        if left == 0:
+            break
+    return qpose, out
+
+
+@pytest.mark.parametrize("typical,limit", [(-0.05, 5), (-0.3, 6), (-10.0, 3), (0.5, 4)])
+def test_close_loop_matches_sequential_reference_loop(o, typical, limit):
+    """Speculative batches + exact re-issue after an acceptance == the sequential loop."""
+    w = synth.config1()
+    poses, offs, pts = w.map_poses.copy(), w.map_offsets.astype(np.int64), w.map_points
+    # graph scan 5 has no points: skipped without counting
+    keep = np.ones(pts.shape[0], dtype=bool)
+    keep[offs[5]:offs[6]] = False
+    sizes = np.diff(offs)
+    sizes[5] = 0
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    pts = np.ascontiguousarray(pts[keep])
+    candidates = np.array([3, 5, 8, 0, 9, 6, 1, 2], dtype=np.uint64)
+    rolling = 8
+    m = ScanMatcherNDT.from_params(w.params)
+    mo = o.new_matcher(w.params)
+    qp_o, seq = _sequential_loop_closure(mo, poses, offs, pts, candidates, rolling, limit, typical,
+                                         w.query_pose, w.query_points)
+    qp_g, got, n_batches = m.close_loop(poses, offs.astype(np.uint64), pts, candidates, rolling, limit,
+                                        typical, w.query_pose, w.query_points)
+    assert [g["candidate"] for g in got] == [s["candidate"] for s in seq]
+    assert [g["accepted"] for g in got] == [s["accepted"] for s in seq]
+    for g, s in zip(got, seq):
+        np.testing.assert_allclose(g["score"], s["score"], rtol=RTOL, atol=ATOL_SCORE)
+        assert np.array_equal(g["pose"], s["pose"])                               # identical corrections
+        if np.all(np.isfinite(s["covariance"])):
+            np.testing.assert_allclose(g["covariance"], s["covariance"], rtol=RTOL,
+                                       atol=RTOL * np.abs(s["covariance"]).max())
+    assert np.array_equal(qp_g, qp_o)
+    acc = [s["accepted"] for s in seq]
+    assert n_batches == 1 + sum(acc[:-1])
+    assert 5 not in [g["candidate"] for g in got]
+    # the model is left empty, like after the reference's last reset/addScans/matchScan it is not reused
+    assert m.match_scan_raw(w.query_pose, w.query_points)[4] == L.ERR_NO_MAP
+
+
 # ------------------------------------------------------------------ particle filter
 def test_filter_measure_and_statistics(o):
     w = synth.config2(n_side=12, n_particles=700)
