@@ -127,13 +127,14 @@ inline int64_t ref_coord(double v, double origin, double cell, uint32_t size)
   return static_cast<int64_t>(static_cast<unsigned int>(q));
 }
 
-// thr[k], k = 0..size: the smallest double v with ref_coord(v) >= k.
+// thr[k], k = 0..size: the smallest double v with ref_coord(v) >= k; thr[size + 1] = +inf.
 // ref_coord is monotone non-decreasing in v (subtraction, division by a
 // positive constant and truncation all are), so the thresholds partition the
 // axis exactly like the reference's own arithmetic does.
 void axis_thresholds(double origin, double cell, uint32_t size, std::vector<double> & thr)
 {
-  thr.resize(static_cast<size_t>(size) + 1);
+  thr.resize(static_cast<size_t>(size) + 2);
+  thr[size + 1] = std::numeric_limits<double>::infinity();
   thr[0] = origin;
   for (uint32_t k = 1; k <= size; ++k) {
     double v = origin + static_cast<double>(k) * cell;
@@ -209,7 +210,7 @@ ModelView model_view(const ndt2d_matcher * m)
   mv.rec = m->d_rec.as<double>();
   mv.rec_fast = m->d_rec_fast.as<double>();
   mv.thr_x = m->d_thr.as<double>();
-  mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 1);
+  mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 2);
   mv.n_valid_cap = m->rec_cap;
   return mv;
 }

@@ -49,8 +49,8 @@ struct ModelView
   const uint32_t * occ_dilated;  // D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1]
   const double * rec;
   const double * rec_fast;  // 6 doubles per occupied cell, see below
-  const double * thr_x;  // size_x + 1 entries
-  const double * thr_y;  // size_y + 1 entries
+  const double * thr_x;  // size_x + 2 entries (the last is +inf)
+  const double * thr_y;  // size_y + 2 entries
   uint32_t n_valid_cap;
 };
 

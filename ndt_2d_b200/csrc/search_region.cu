@@ -106,6 +106,7 @@ struct Tables
 {
   uint8_t rounds[kMaxRw + 1][kMaxRw + 1];  // [n][m] = ceil(m / (32 / n)): rounds to cover m lines
                                            // when the lane-fixed axis has n entries
+  uint8_t colmode[kMaxRw + 1][kMaxRw + 1];  // [h][w] = 1: lay the rows (y) over the lanes
   uint8_t div32[33];                       // 32 / n
   uint32_t inv[33];                        // 65536 / n + 1: (k * inv[n]) >> 16 == k / n, k < 1100
 };
@@ -120,6 +121,11 @@ constexpr Tables make_tables()
     for (uint32_t m = 0; m <= kMaxRw; ++m) {
       const uint32_t lines = 32u / n;
       t.rounds[n][m] = static_cast<uint8_t>((m + lines - 1) / lines);
+    }
+  }
+  for (uint32_t h = 1; h <= kMaxRw; ++h) {
+    for (uint32_t w = 1; w <= kMaxRw; ++w) {
+      t.colmode[h][w] = t.rounds[h][w] <= t.rounds[w][h] ? 1 : 0;
     }
   }
   return t;
@@ -184,20 +190,19 @@ __device__ __forceinline__ void eval_cell(
     float * ap = acc_f + (COL ? (u0 + lu) + (v0 + lv) * Rw : (u0 + lu) * Rw + (v0 + lv));
     const double * vp = vs + v0 + lv;
     const uint32_t ap_step = COL ? lines * Rw : lines;
-    uint32_t v = lv;
+    const double * const vend = vs + v0 + nV;   // one past the last entry of the iterated axis
     // two independent evaluations per trip: halves the loop overhead and gives the
     // scheduler a second dependency chain (LDS -> DADD -> DFMA -> DFMA -> F2F -> MUFU)
-    for (; v + lines < nV; v += 2u * lines) {
+    for (; vp + lines < vend; vp += 2u * lines) {
       const double qv0 = vp[0] - mean_v, qv1 = vp[lines] - mean_v;
       const double e0 = fma(qv0, fma(Cv, qv0, Bqu), Cqu2);
       const double e1 = fma(qv1, fma(Cv, qv1, Bqu), Cqu2);
       const float f0 = ex2_ftz(static_cast<float>(e0)), f1 = ex2_ftz(static_cast<float>(e1));
       ap[0] += f0;
       ap[ap_step] += f1;
-      vp += 2u * lines;
       ap += 2u * ap_step;
     }
-    if (v < nV) {
+    if (vp < vend) {
       const double qv = *vp - mean_v;
       const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
       *ap += ex2_ftz(static_cast<float>(e));
@@ -335,7 +340,7 @@ search_region_kernel(
     occd = reinterpret_cast<const uint32_t *>(sp);
     sp += tab_d_bytes;
     thr_x = reinterpret_cast<const double *>(sp);
-    thr_y = thr_x + (mv.g.size_x + 1);
+    thr_y = thr_x + (mv.g.size_x + 2);
     sp += tab_thr_bytes;
     if (threadIdx.x == 0) {
       mbar_init(mbar, 1);
@@ -447,8 +452,9 @@ search_region_kernel(
         // exact candidate coordinates (scan_matcher_ndt.cpp:123-124), lane = column / row
         const double xa = __dadd_rn(pox, my_dlx), ya = __dadd_rn(poy, my_dly);
         // columns / rows still in the first cell: below the next threshold
-        const bool in_x0 = (bx > size_x) || (xa < thr_x[min(bx, size_x)]);
-        const bool in_y0 = (by > size_y) || (ya < thr_y[min(by, size_y)]);
+        // (thr[size + 1] = +inf: beyond the grid nothing crosses)
+        const bool in_x0 = xa < thr_x[bx];
+        const bool in_y0 = ya < thr_y[by];
         const uint32_t nx = __popc(__ballot_sync(0xffffffffu, lane < nxc && in_x0));
         const uint32_t ny = __popc(__ballot_sync(0xffffffffu, lane < nyc && in_y0));
         xs[lane] = xa;
@@ -483,7 +489,7 @@ search_region_kernel(
           const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
           if (Ds.y == 0.0) {
             // orientation with fewer rounds (table lookup)
-            if (kTab.rounds[h][w] <= kTab.rounds[w][h]) {
+            if (kTab.colmode[h][w]) {
               eval_cell<true>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
             } else {
               eval_cell<false>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
@@ -562,7 +568,7 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
   pl.Rw = Rw;
   pl.Q = (n_lin + Rw - 1) / Rw;
   pl.n_jobs = n_theta * pl.Q * pl.Q;
-  pl.thr_doubles = g.size_x + 1 + g.size_y + 1;
+  pl.thr_doubles = g.size_x + 2 + g.size_y + 2;
   const size_t d_bytes = (static_cast<size_t>(g.n_words) * 4 + 15) & ~size_t(15);
   const size_t t_bytes = (static_cast<size_t>(pl.thr_doubles) * 8 + 15) & ~size_t(15);
   pl.smem_tab = d_bytes + t_bytes <= kSmemTabBudget;
