@@ -6,11 +6,14 @@ no CUDA device is present every create() returns NDT2D_ERR_NO_DEVICE.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libndt2d_b200.so"
+# NDT2D_B200_LIB: an alternative build of the same library (kernel A/B experiments)
+_LIB_PATH = Path(os.environ.get("NDT2D_B200_LIB") or
+                 Path(__file__).resolve().parent / "lib" / "libndt2d_b200.so")
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_MAP, ERR_SIZE, ERR_STATE = range(7)
 STATUS_NAMES = {

@@ -48,10 +48,23 @@ namespace
 using namespace ndt2d_dev;
 
 constexpr uint32_t kMaxRw = 25;                 // region side (candidates)
-constexpr uint32_t kWarps = 24;                 // warps per CTA; one persistent CTA per SM
+// Per-candidate totals: float + the running rounding residual kept in the block-sum slot
+// (compensated: the pair carries ~48 bits) -- 5.5 KB of shared memory per warp, so 28 warps
+// fit one SM (measured 28.8 ms at config 4 against 31.3 ms for 24 warps with double totals).
+// -DNDT2D_REGION_DOUBLE_TOTALS -DNDT2D_REGION_WARPS=24 restores plain double totals.
+#ifndef NDT2D_REGION_WARPS
+#define NDT2D_REGION_WARPS 28
+#endif
+#ifdef NDT2D_REGION_DOUBLE_TOTALS
+using total_t = double;
+#else
+using total_t = float;
+#endif
+constexpr uint32_t kWarps = NDT2D_REGION_WARPS;  // warps per CTA; one persistent CTA per SM
 constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
 // per warp: double totals, xs[32], ys[32], float block sums (16-byte rounded)
-constexpr uint32_t kWarpSmemBytes = ((kAccEntries * 8 + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
+constexpr uint32_t kWarpSmemBytes =
+  ((kAccEntries * static_cast<uint32_t>(sizeof(total_t)) + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
 constexpr size_t kSmemTabBudget = 32 * 1024;    // D + thresholds in shared memory up to this
 constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
@@ -210,14 +223,36 @@ __device__ __forceinline__ void eval_cell(
   }
 }
 
-// acc_d += acc_f; acc_f = 0  (per-warp, lanes stride over the region)
+// total += block sum, per warp, lanes stride over the region.  With float totals the
+// rounding residual of the addition (Knuth's TwoSum, exact) stays in the block-sum slot
+// and is carried into the next block, so nothing is lost to the float total.
 __device__ __forceinline__ void flush_block(
-  double * __restrict__ acc_d, float * __restrict__ acc_f, uint32_t RR, uint32_t lane)
+  total_t * __restrict__ acc_d, float * __restrict__ acc_f, uint32_t RR, uint32_t lane)
 {
   for (uint32_t k = lane; k < RR; k += 32) {
+#ifdef NDT2D_REGION_DOUBLE_TOTALS
     acc_d[k] += static_cast<double>(acc_f[k]);
     acc_f[k] = 0.0f;
+#else
+    const float tot = acc_d[k], blk = acc_f[k];
+    const float t = __fadd_rn(tot, blk);
+    const float bb = __fsub_rn(t, tot);
+    const float err = __fadd_rn(__fsub_rn(tot, __fsub_rn(t, bb)), __fsub_rn(blk, bb));
+    acc_d[k] = t;
+    acc_f[k] = err;
+#endif
   }
+}
+
+// Value of candidate k after the last flush (total + the residual still in the slot).
+__device__ __forceinline__ double total_value(
+  const total_t * __restrict__ acc_d, const float * __restrict__ acc_f, uint32_t k)
+{
+#ifdef NDT2D_REGION_DOUBLE_TOTALS
+  return acc_d[k];
+#else
+  return static_cast<double>(acc_d[k]) + static_cast<double>(acc_f[k]);
+#endif
 }
 
 // Pre-pass of the search: for every (theta slice, scan point) the padded cell
@@ -251,8 +286,9 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
 
 // Per-candidate score of one job from its sums, warp argmin + the six covariance
 // sums -> the job's 9-double record.  sums[k], k = a * Rw + b.
+template<typename SUMS>
 __device__ __forceinline__ void job_epilogue(
-  const double * __restrict__ sums, const SearchView & sv, uint32_t job, uint32_t itheta,
+  SUMS sums, const SearchView & sv, uint32_t job, uint32_t itheta,
   uint32_t Rw, uint32_t jx0, uint32_t jy0, uint32_t nxc, uint32_t nyc, uint32_t lane,
   double * __restrict__ job_partials, double * __restrict__ scores)
 {
@@ -264,7 +300,7 @@ __device__ __forceinline__ void job_epilogue(
   for (uint32_t k = lane; k < RR; k += 32) {
     const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
     if (a < nxc && b < nyc) {
-      const double score = -sums[k];
+      const double score = -sums(k);
       const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
       const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
         static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
@@ -313,8 +349,8 @@ __global__ void __launch_bounds__(256) region_chunk_reduce_kernel(
     first[k] = t;
   }
   __syncwarp();
-  job_epilogue(first, sv, job, theta_begin + it * sv.theta_stride, Rw, jx0, jy0, nxc, nyc, lane,
-    job_partials, scores);
+  job_epilogue([first](uint32_t k) {return first[k];}, sv, job,
+    theta_begin + it * sv.theta_stride, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
 }
 
 template<bool SMEM_TAB, bool PRE>
@@ -353,10 +389,11 @@ search_region_kernel(
     thr_x = mv.thr_x;
     thr_y = mv.thr_y;
   }
-  double * acc_d = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
-  double * xs = acc_d + kAccEntries;
+  // per warp: xs[32], ys[32] (double), totals, float block sums
+  double * xs = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
   double * ys = xs + 32;
-  float * acc_f = reinterpret_cast<float *>(ys + 32);
+  total_t * acc_d = reinterpret_cast<total_t *>(ys + 32);
+  float * acc_f = reinterpret_cast<float *>(acc_d + kAccEntries);
 
   const uint32_t n_lin = sv.n_lin;
   const uint32_t pitch = mv.g.pitch;
@@ -403,7 +440,7 @@ search_region_kernel(
     }
 
     for (uint32_t k = lane; k < RR; k += 32) {
-      acc_d[k] = 0.0;
+      acc_d[k] = static_cast<total_t>(0);
       acc_f[k] = 0.0f;
     }
     __syncwarp();
@@ -536,9 +573,10 @@ search_region_kernel(
     if (P > 1) {
       // this chunk's sums; region_chunk_reduce_kernel adds the chunks and finishes the job
       double * out = chunk_sums + static_cast<size_t>(work) * RR;
-      for (uint32_t k = lane; k < RR; k += 32) {out[k] = acc_d[k];}
+      for (uint32_t k = lane; k < RR; k += 32) {out[k] = total_value(acc_d, acc_f, k);}
     } else {
-      job_epilogue(acc_d, sv, job, itheta, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
+      job_epilogue([acc_d, acc_f](uint32_t k) {return total_value(acc_d, acc_f, k);}, sv, job,
+        itheta, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
     }
     __syncwarp();
   }
