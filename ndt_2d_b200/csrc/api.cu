@@ -155,6 +155,8 @@ void axis_thresholds(double origin, double cell, uint32_t size, std::vector<doub
 }  // namespace
 
 // ---------------------------------------------------------------- matcher
+constexpr size_t kBatchLanes = 4;
+
 struct ndt2d_matcher
 {
   std::mutex mu;
@@ -189,6 +191,7 @@ struct ndt2d_matcher
   // Pipelined mode (match_scan_batch): host staging comes from a pinned arena that is
   // only recycled after a stream synchronisation, and no call waits for the device.
   bool pipelined = false;
+  std::vector<ndt2d_matcher *> lanes;   // sub-handles of match_scan_batch (created on first use)
   PinnedBuffer h_arena;
   size_t arena_off = 0;
   DeviceBuffer d_batch_results;
@@ -693,6 +696,8 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
 NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
 {
   if (!m) {return NDT2D_OK;}
+  for (ndt2d_matcher * sub : m->lanes) {ndt2d_matcher_destroy(sub);}
+  m->lanes.clear();
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
@@ -824,49 +829,82 @@ static int match_scan_batch_locked(
     m->has_model = false;
     return NDT2D_OK;
   }
-  // Pipelined: every job's build + search is enqueued on the handle's stream without
-  // waiting for the device (host staging from the pinned arena); the 32-double result
-  // records are collected on the device and fetched with one copy at the end.
-  int rc = m->h_arena.ensure(size_t(8) << 20);
-  if (!rc) {rc = m->d_batch_results.ensure(n_jobs * 32 * sizeof(double));}
-  if (!rc) {rc = m->h_result.ensure(std::max<size_t>(n_jobs * 32, 64) * sizeof(double));}
-  if (rc) {return rc;}
-  m->pipelined = true;
-  m->arena_off = 0;
+  // Pipelined over kBatchLanes internal sub-handles (own stream, own model + scratch
+  // buffers): job j's build + search is enqueued on lane j % kBatchLanes without waiting
+  // for the device (host staging from that lane's pinned arena), so the dependent chains
+  // of small kernels of different jobs overlap; every lane collects its 32-double result
+  // records on the device and they are fetched with one copy per lane at the end.
+  const size_t n_lanes = std::min<size_t>(kBatchLanes, n_jobs);
+  while (m->lanes.size() < n_lanes) {
+    ndt2d_params p = m->prm;
+    p.device = m->device;
+    p.stream = nullptr;
+    ndt2d_matcher * sub = nullptr;
+    const int rc0 = ndt2d_matcher_create(&p, &sub);
+    if (rc0) {return rc0;}
+    m->lanes.push_back(sub);
+  }
+  int rc = NDT2D_OK;
+  const size_t per_lane = (n_jobs + n_lanes - 1) / n_lanes;
+  for (size_t l = 0; l < n_lanes && !rc; ++l) {
+    ndt2d_matcher * s = m->lanes[l];
+    rc = s->h_arena.ensure(size_t(4) << 20);
+    if (!rc) {rc = s->d_batch_results.ensure(per_lane * 32 * sizeof(double));}
+    if (!rc) {rc = s->h_result.ensure(std::max<size_t>(per_lane * 32, 64) * sizeof(double));}
+    s->pipelined = true;
+    s->arena_off = 0;
+  }
   for (size_t j = 0; j < n_jobs && !rc; ++j) {
+    ndt2d_matcher * s = m->lanes[j % n_lanes];
+    const size_t slot = j / n_lanes;
     const uint64_t s0 = job_scan_offsets[j], s1 = job_scan_offsets[j + 1];
-    rc = add_scans_locked(m, static_cast<size_t>(s1 - s0), map_poses + 3 * s0,
+    rc = add_scans_locked(s, static_cast<size_t>(s1 - s0), map_poses + 3 * s0,
         map_pt_offsets + s0, map_pts_xy);
     if (rc) {break;}
     const uint64_t q0 = query_pt_offsets[j], q1 = query_pt_offsets[j + 1];
-    rc = stage_scan_locked(m, query_poses + 3 * j, query_pts_xy + 2 * q0,
+    rc = stage_scan_locked(s, query_poses + 3 * j, query_pts_xy + 2 * q0,
         static_cast<size_t>(q1 - q0));
     if (rc) {break;}
-    rc = ndt2d_launch_search(model_view(m), search_view(m), 0,
-        static_cast<uint32_t>(m->dth.size()), m->prm.kernel_variant, m->d_blockpart.as<double>(),
-        m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr);
+    rc = ndt2d_launch_search(model_view(s), search_view(s), 0,
+        static_cast<uint32_t>(s->dth.size()), m->prm.kernel_variant, s->d_blockpart.as<double>(),
+        s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &m->ctr);
     if (rc) {break;}
-    if (cudaMemcpyAsync(m->d_batch_results.as<double>() + 32 * j, m->d_partial.p,
-      32 * sizeof(double), cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(s->d_batch_results.as<double>() + 32 * slot, s->d_partial.p,
+      32 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) != cudaSuccess)
     {
       rc = NDT2D_ERR_CUDA;
     }
   }
-  m->pipelined = false;
+  for (size_t l = 0; l < n_lanes; ++l) {
+    ndt2d_matcher * s = m->lanes[l];
+    s->pipelined = false;
+    s->has_model = false;
+    s->staged = false;
+    m->ctr.launches += s->ctr.launches;
+    m->ctr.h2d_bytes += s->ctr.h2d_bytes;
+    s->ctr = Counters{0, 0, 0};
+  }
   m->has_model = false;
   m->staged = false;
   m->ev_valid = false;
   if (rc) {
-    cudaStreamSynchronize(m->stream);
+    for (size_t l = 0; l < n_lanes; ++l) {cudaStreamSynchronize(m->lanes[l]->stream);}
     return rc;
   }
-  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->h_result.p, m->d_batch_results.p, n_jobs * 32 * sizeof(double),
-    cudaMemcpyDeviceToHost, m->stream));
-  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  for (size_t l = 0; l < n_lanes; ++l) {
+    ndt2d_matcher * s = m->lanes[l];
+    const size_t mine = (n_jobs - l + n_lanes - 1) / n_lanes;   // jobs l, l + n_lanes, ...
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(s->h_result.p, s->d_batch_results.p, mine * 32 * sizeof(double),
+      cudaMemcpyDeviceToHost, s->stream));
+  }
+  for (size_t l = 0; l < n_lanes; ++l) {
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(m->lanes[l]->stream));
+  }
   m->ctr.d2h_bytes += n_jobs * 32 * sizeof(double);
   for (size_t j = 0; j < n_jobs; ++j) {
+    const double * r32 = m->lanes[j % n_lanes]->h_result.as<double>() + 32 * (j / n_lanes);
     if (delta_written) {delta_written[j] = 0;}
-    unpack_result(m->h_result.as<double>() + 32 * j, out_delta3 ? out_delta3 + 3 * j : nullptr,
+    unpack_result(r32, out_delta3 ? out_delta3 + 3 * j : nullptr,
       delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
       out_score ? out_score + j : nullptr);
   }
