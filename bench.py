@@ -170,6 +170,55 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def cpu_reference_other(out):
+    """The reference's own CPU code (oracle/_ref, else the C restatement) on the same inputs as
+    other_workloads, single thread, one repetition each: context for the device numbers."""
+    import ctypes as C
+    from ndt_2d_b200 import synth
+    from oracle import binding as B
+    lib = B.load_ref()
+    kind = "reference" if lib is not None else "port"
+    if lib is None:
+        lib = B.load_oracle()
+
+    def clock(fn):
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e3
+
+    for beams in (360, 100):
+        w = synth.config1(laser_max_beams=beams)
+        m = lib.new_matcher(w.params)
+        t_add = clock(lambda: m.add_scans(w.map_poses, w.map_offsets, w.map_points))
+        t_match = clock(lambda: m.match_scan(w.query_pose, w.query_points))
+        out[f"config1_local_match_beams{beams}"]["cpu_reference"] = {
+            "kind": kind, "cores": 1, "addScans_ms": t_add, "matchScan_ms": t_match}
+    w = synth.config2()
+    m = lib.new_matcher(w.params)
+    t_build = clock(lambda: m.add_scans(w.map_poses, w.map_offsets, w.map_points))
+    t_meas = clock(lambda: [m.score_points(w.scan_points, p) for p in w.particles[:500]]) * 10.0
+    out["config2_particle_filter"]["cpu_reference"] = {
+        "kind": kind, "cores": 1, "global_ndt_build_ms": t_build,
+        "measure_ms_5000_particles_extrapolated_from_500": t_meas}
+    w = synth.config3()
+    m = lib.new_matcher(w.params)
+
+    def batch(n):
+        for j in range(n):
+            s0, s1 = int(w.job_scan_offsets[j]), int(w.job_scan_offsets[j + 1])
+            offs = w.map_offsets[s0:s1 + 1]
+            m.reset()
+            m.add_scans(w.map_poses[s0:s1], offs - offs[0], w.map_points[int(offs[0]):int(offs[-1])])
+            q0, q1 = int(w.query_offsets[j]), int(w.query_offsets[j + 1])
+            m.match_scan(w.query_poses[j], w.query_points[q0:q1])
+    out["config3_loop_closure_batch"]["cpu_reference"] = {
+        "kind": kind, "cores": 1, "batch_ms_50_jobs_extrapolated_from_10": clock(lambda: batch(10)) * 5.0}
+    w = synth.config5()
+    m = lib.new_matcher(w.params)
+    out["config5_model_build"]["cpu_reference"] = {
+        "kind": kind, "cores": 1, "addScans_ms": clock(lambda: m.add_scans(w.poses, w.offsets, w.points))}
+
+
 def other_workloads(torch, dev_index: int):
     """The remaining BASELINE configs, a few repetitions each (not the headline)."""
     from ndt_2d_b200 import ParticleFilter, Pose2d, Scan, ScanMatcherNDT, synth
@@ -445,6 +494,8 @@ def run_ours(args):
     if world == 1 and not args.no_other:
         try:
             line["other_workloads"] = other_workloads(torch, local_rank)
+            if not args.no_cpu:
+                cpu_reference_other(line["other_workloads"])
         except Exception as e:  # never lose the headline because a side measurement failed
             line["other_workloads"] = {"error": repr(e)}
     print(json.dumps(line))

@@ -393,6 +393,42 @@ def test_close_loop_matches_sequential_reference_loop(o, typical, limit):
     assert m.match_scan_raw(w.query_pose, w.query_points)[4] == L.ERR_NO_MAP
 
 
+def test_two_handles_from_two_threads(o):
+    """local_scan_matcher_ and global_scan_matcher_ live on different threads in the node
+    (ndt_mapper.cpp:508-515 vs :634-643): distinct handles are independent (own stream, own
+    buffers), one handle serialises its own calls."""
+    import threading
+    w1, w4 = synth.config1(), synth.config4(scale=0.04)
+    m1 = ScanMatcherNDT.from_params(w1.params)
+    m4 = ScanMatcherNDT.from_params(w4.params)
+    guess4 = w4.true_pose - np.array([0.05, -0.03, 0.06])
+    m1.add_scans_raw(w1.map_poses, w1.map_offsets, w1.map_points)
+    m4.add_scans_raw(w4.map_poses, w4.map_offsets, w4.map_points)
+    ref1 = m1.match_scan_raw(w1.query_pose, w1.query_points)
+    ref4 = m4.match_scan_raw(guess4, w4.query_points)
+    errors = []
+
+    def worker(m, w, pose, ref, reps, rebuild):
+        try:
+            for _ in range(reps):
+                if rebuild:
+                    m.reset()
+                    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+                s, d, wr, cov, _ = m.match_scan_raw(pose, w.query_points)
+                assert s == ref[0] and np.array_equal(d, ref[1]) and np.array_equal(cov, ref[3])
+        except Exception as e:  # surfaced in the main thread
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(m1, w1, w1.query_pose, ref1, 40, True)),
+          threading.Thread(target=worker, args=(m4, w4, guess4, ref4, 10, False)),
+          threading.Thread(target=worker, args=(m4, w4, guess4, ref4, 10, False))]   # same handle twice
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 # ------------------------------------------------------------------ particle filter
 def test_filter_measure_and_statistics(o):
     w = synth.config2(n_side=12, n_particles=700)
