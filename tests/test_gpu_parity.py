@@ -242,6 +242,44 @@ def test_match_scan_config4_reduced(o):
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
+SWEEP = [
+    # ndt_res, ang_res, ang_size, lin_res, lin_size, beams   -- what it exercises
+    (0.05, 0.01, 0.03, 0.05, 0.25, 360),     # step == cell: one-candidate regions
+    (0.05, 0.01, 0.03, 0.11, 0.30, 360),     # step > cell
+    (0.30, 0.004, 0.02, 0.07, 0.33, 200),    # non-integer cell/step ratio, n_lin not a region multiple
+    (0.25, 0.0025, 0.1, 0.005, 0.05, 100),   # 50 steps per cell: region capped at 25, 21 x 21 lattice
+    (0.25, 0.5, 0.2, 0.01, 0.13, 360),       # a single theta slice (accumulated loop: 1 value)
+    (0.25, 0.01, 0.05, 0.2, 0.1, 360),       # a single (dx, dy) candidate per slice
+    (1.00, 0.01, 0.05, 0.03, 0.30, 37),      # coarse cells, few beams (37 of 360, subsampled)
+    (0.10, 0.002, 0.01, 0.004, 0.06, 1000),  # laser_max_beams > points in the scan
+    (0.25, 0.003, 0.0, 0.01, 0.1, 360),      # angular size 0: no candidates at all
+]
+
+
+@pytest.mark.parametrize("case", range(len(SWEEP)))
+def test_search_parameter_sweep(o, case):
+    res, ares, asize, lres, lsize, beams = SWEEP[case]
+    w = synth.config1()
+    p = dict(ndt_resolution=res, search_angular_resolution=ares, search_angular_size=asize,
+             search_linear_resolution=lres, search_linear_size=lsize, laser_max_beams=beams,
+             range_max=10.0)
+    m = ScanMatcherNDT.from_params(p)
+    mo = o.new_matcher(p)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    assert m.grid_info() == mo.grid()
+    check_cells(m.dump_cells(), mo.dump_cells())
+    guess = w.true_pose - np.array([0.03, -0.02, 0.01])
+    so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+    na, nl = m.search_shape()
+    assert scores_o.shape == (na, nl, nl)                                         # candidate counts
+    if scores_o.size == 0:
+        assert (sg, wg) == (so, wo) and np.all(np.isnan(cg)) and np.all(np.isnan(co))
+        return
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
+
+
 def test_theta_sliced_search_matches_full(o):
     """Partial searches over theta ranges + one combine == the full search (the
     multi-GPU path, exercised on one device)."""
