@@ -339,7 +339,7 @@ def run_ours(args):
     na, nl = m.search_shape()
     n_pts = min(int(w.params["laser_max_beams"]), int(w.query_points.shape[0]))
     total_candidates = na * nl * nl
-    ss = sharded.ShardedSearch(m, rank, world, dev)     # theta slices of this rank + the exchange
+    ss = sharded.ShardedSearch(m, rank, world, dev, exchange=args.exchange)   # theta slices + the exchange
     my_candidates = ss.n_theta * nl * nl
     gathered = ss.gathered
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -394,8 +394,8 @@ def run_ours(args):
     value = total_candidates / (ms_per_step * 1e-3)
     launches = (c1["launches"] - c0["launches"]) // max(args.steps, 1)
 
-    # result of the timed search (every rank combines the same gathered records)
-    score, delta, written, cov = m.combine_device(gathered.data_ptr(), world)
+    # result of the timed search (every rank holds the same combined record)
+    score, delta, written, cov = ss.result()
 
     # ---- end-to-end timing (host buffers, copies inside)
     for _ in range(max(1, args.warmup // 2)):
@@ -459,7 +459,9 @@ def run_ours(args):
                         "@0.25 m, +-2 m @0.01 m, +-pi @0.002 rad" + ("" if args.scale == 1.0 else f", window scale {args.scale}"),
             "candidates_per_step": total_candidates, "n_angular": na, "n_linear": nl, "beams_used": n_pts,
             "point_evaluations_per_step": total_candidates * n_pts,
-            "parallelism": f"theta slices interleaved over {world} ranks, one all-gather of 128 B/rank"
+            "parallelism": (f"theta slices interleaved over {world} ranks; exchange of one 128 B record "
+                            f"per rank: {ss.exchange}" + (" (peer stores from the search's last kernel, "
+                            "CUDA IPC mailboxes)" if ss.exchange == "p2p" else " (all-gather)"))
                            if world > 1 else "single GPU",
             "l2_flush": "256 MiB memset between steps, outside the per-step CUDA event pairs",
             "matchScan_latency_ms": ms_per_step,
@@ -539,6 +541,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the search window (debug only)")
     ap.add_argument("--variant", type=int, default=0, help="search kernel variant (A/B runs)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="cross-GPU exchange of the partial records (N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()

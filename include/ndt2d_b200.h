@@ -202,6 +202,27 @@ NDT2D_API int ndt2d_matcher_search_staged_strided(
   ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, uint64_t theta_stride,
   void * d_partial);
 
+/* ---- fused cross-GPU exchange (one process per GPU, one node) ------------------
+ * Instead of handing the partial records to a collective library, the last kernel of the
+ * search itself stores this rank's 128-byte record into a mailbox in every rank's device
+ * memory (peer stores over NVLink, mapped with CUDA IPC), waits -- bounded -- for the other
+ * ranks' records in its own mailbox and reduces them exactly like ndt2d_combine_partials.
+ *   exchange_init     allocates this rank's mailbox; handle64 = its cudaIpcMemHandle_t
+ *   exchange_connect  handles = world * 64 bytes, rank-ordered (the caller all-gathers them
+ *                     once, e.g. with torch.distributed); maps the peers' mailboxes
+ *   search_exchange   search_staged_strided + publish / wait / reduce; seq > 0 must be the
+ *                     same on every rank and grow by 1 per search
+ *   fetch_result      the combined result (every rank holds the same);
+ *                     NDT2D_ERR_STATE if a rank did not arrive within 10 s */
+NDT2D_API int ndt2d_matcher_exchange_init(
+  ndt2d_matcher * m, uint32_t world, uint32_t rank, unsigned char * handle64);
+NDT2D_API int ndt2d_matcher_exchange_connect(ndt2d_matcher * m, const unsigned char * handles);
+NDT2D_API int ndt2d_matcher_search_exchange(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, uint64_t theta_stride, uint64_t seq);
+NDT2D_API int ndt2d_matcher_fetch_result(
+  ndt2d_matcher * m, double * out_delta3, int * delta_written, double * out_cov9,
+  double * out_score);
+
 /* Synchronises the stream and copies the handle-held partial record out. */
 NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16);
 

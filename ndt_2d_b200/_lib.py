@@ -78,6 +78,10 @@ SIGNATURES = {
     "ndt2d_matcher_stage_scan": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),
     "ndt2d_matcher_search_staged": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "ndt2d_matcher_search_staged_strided": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]),
+    "ndt2d_matcher_exchange_init": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_ubyte)]),
+    "ndt2d_matcher_exchange_connect": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "ndt2d_matcher_search_exchange": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "ndt2d_matcher_fetch_result": (C.c_int, [_vp, _dp, _ip, _dp, _dp]),
     "ndt2d_matcher_fetch_partial": (C.c_int, [_vp, _dp]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_combine_partials_host": (

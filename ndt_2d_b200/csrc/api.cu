@@ -190,6 +190,12 @@ struct ndt2d_matcher
   PinnedBuffer h_stage, h_result;
   // Pipelined mode (match_scan_batch): host staging comes from a pinned arena that is
   // only recycled after a stream synchronisation, and no call waits for the device.
+  // fused cross-GPU exchange (ndt2d_matcher_exchange_*): this rank's mailbox, the peers'
+  // mailboxes mapped through CUDA IPC, and the device table of all of them
+  DeviceBuffer d_mailbox, d_peer_table;
+  std::vector<void *> peer_ptrs;        // index = rank; own rank = d_mailbox.p
+  uint32_t x_world = 0, x_rank = 0;
+  bool x_connected = false;
   bool pipelined = false;
   std::vector<ndt2d_matcher *> lanes;   // sub-handles of match_scan_batch (created on first use)
   PinnedBuffer h_arena;
@@ -587,6 +593,15 @@ static int match_scan_batch_locked(
   const double * map_pts_xy,
   const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
   double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+static void exchange_close(ndt2d_matcher * m)
+{
+  for (uint32_t r = 0; r < m->peer_ptrs.size(); ++r) {
+    if (r != m->x_rank && m->peer_ptrs[r]) {cudaIpcCloseMemHandle(m->peer_ptrs[r]);}
+  }
+  m->peer_ptrs.clear();
+  m->x_connected = false;
+}
+
 
 extern "C" {
 
@@ -698,6 +713,13 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   if (!m) {return NDT2D_OK;}
   for (ndt2d_matcher * sub : m->lanes) {ndt2d_matcher_destroy(sub);}
   m->lanes.clear();
+  {
+    DeviceGuard guard(m->device);
+    if (m->stream) {cudaStreamSynchronize(m->stream);}
+    exchange_close(m);
+    m->d_mailbox.release();
+    m->d_peer_table.release();
+  }
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
@@ -1070,6 +1092,109 @@ NDT2D_API int ndt2d_matcher_search_staged(
   ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, void * d_partial)
 {
   return ndt2d_matcher_search_staged_strided(m, theta_begin, theta_end, 1, d_partial);
+}
+
+NDT2D_API int ndt2d_matcher_exchange_init(
+  ndt2d_matcher * m, uint32_t world, uint32_t rank, unsigned char * handle64)
+{
+  if (!m || !handle64 || world == 0 || world > kExchangeMaxRanks || rank >= world) {
+    return NDT2D_ERR_INVALID;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard(m->device);
+  exchange_close(m);
+  int rc = m->d_mailbox.ensure(kExchangeMailboxBytes);
+  if (!rc) {rc = m->d_peer_table.ensure(kExchangeMaxRanks * sizeof(void *));}
+  if (rc) {return rc;}
+  NDT2D_CUDA_TRY(cudaMemsetAsync(m->d_mailbox.p, 0, kExchangeMailboxBytes, m->stream));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));  // cleared before any peer can learn the handle
+  cudaIpcMemHandle_t h;
+  NDT2D_CUDA_TRY(cudaIpcGetMemHandle(&h, m->d_mailbox.p));
+  memcpy(handle64, &h, 64);
+  m->x_world = world;
+  m->x_rank = rank;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_exchange_connect(ndt2d_matcher * m, const unsigned char * handles)
+{
+  if (!m || !handles) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (m->x_world == 0 || !m->d_mailbox.p) {return NDT2D_ERR_STATE;}
+  DeviceGuard guard(m->device);
+  exchange_close(m);
+  m->peer_ptrs.assign(m->x_world, nullptr);
+  for (uint32_t r = 0; r < m->x_world; ++r) {
+    if (r == m->x_rank) {
+      m->peer_ptrs[r] = m->d_mailbox.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * static_cast<size_t>(r), 64);
+    void * p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      ndt2d_set_error("cudaIpcOpenMemHandle", e, __FILE__, __LINE__);
+      exchange_close(m);
+      return NDT2D_ERR_CUDA;
+    }
+    m->peer_ptrs[r] = p;
+  }
+  NDT2D_CUDA_TRY(cudaMemcpy(m->d_peer_table.p, m->peer_ptrs.data(), m->x_world * sizeof(void *),
+    cudaMemcpyHostToDevice));
+  m->x_connected = true;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_search_exchange(
+  ndt2d_matcher * m, uint64_t theta_begin, uint64_t theta_end, uint64_t theta_stride, uint64_t seq)
+{
+  if (!m || theta_stride == 0 || theta_stride > 0xffffffffull || seq == 0) {
+    return NDT2D_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->has_model) {return NDT2D_ERR_NO_MAP;}
+  if (!m->staged || !m->x_connected) {return NDT2D_ERR_STATE;}
+  const uint64_t n_ang = m->dth.size();
+  if (theta_begin > theta_end || theta_end > n_ang) {return NDT2D_ERR_INVALID;}
+  DeviceGuard guard(m->device);
+  SearchView sv = search_view(m);
+  sv.theta_stride = static_cast<uint32_t>(theta_stride);
+  ExchangeView xv;
+  xv.peers = m->d_peer_table.as<void *>();
+  xv.world = m->x_world;
+  xv.rank = m->x_rank;
+  xv.seq = seq;
+  xv.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+  const int rc = ndt2d_launch_search(model_view(m), sv, static_cast<uint32_t>(theta_begin),
+      static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
+      m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr,
+      m->ev_begin, m->ev_end, &xv);
+  if (rc) {return rc;}
+  m->ev_valid = theta_end > theta_begin;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_fetch_result(
+  ndt2d_matcher * m, double * out_delta3, int * delta_written, double * out_cov9,
+  double * out_score)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (!m->staged) {return NDT2D_ERR_STATE;}
+  DeviceGuard guard(m->device);
+  double r32[32];
+  const int rc = fetch_result_locked(m, r32);
+  if (rc) {return rc;}
+  if (delta_written) {*delta_written = 0;}
+  unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
+  if (r32[31] != 0.0) {
+    snprintf(g_last_error, sizeof(g_last_error),
+      "fused exchange timed out: not every rank published its partial record");
+    return NDT2D_ERR_STATE;
+  }
+  return NDT2D_OK;
 }
 
 NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16)

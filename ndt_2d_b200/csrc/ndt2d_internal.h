@@ -120,6 +120,28 @@ int ndt2d_launch_dump_cells(
 int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
   cudaStream_t stream, Counters * ctr);
 
+// Cross-GPU exchange fused into the last kernel of a search (search.cu:
+// search_finish_kernel).  Every rank owns a MAILBOX in its device memory, mapped
+// into the other ranks' address spaces through CUDA IPC:
+//   records  [2 parities][kExchangeMaxRanks][16] doubles   slot [p][r]: rank r's partial record
+//   flags    [2 parities][kExchangeMaxRanks]     u64       slot [p][r]: sequence number it belongs to
+// A rank finishes its slices, stores its 16-double record into slot [seq & 1][rank] of
+// EVERY mailbox (peer stores over NVLink), fences system-wide, then stores seq into the
+// matching flags (release); it then waits (acquire, bounded) until its own mailbox holds
+// all ranks' flags >= seq and reduces the records like ndt2d_launch_combine.  Two
+// parities are enough: a rank can only publish seq + 2 after every rank published seq + 1,
+// i.e. after every rank has finished reading seq.
+constexpr uint32_t kExchangeMaxRanks = 64;
+constexpr size_t kExchangeRecordBytes = 2 * kExchangeMaxRanks * 16 * sizeof(double);
+constexpr size_t kExchangeMailboxBytes = kExchangeRecordBytes + 2 * kExchangeMaxRanks * 8;
+struct ExchangeView
+{
+  void * const * peers;          // device array: base of every rank's mailbox (this rank's own included)
+  uint32_t world, rank;
+  unsigned long long seq;        // > 0, the same on every rank, +1 per search
+  unsigned long long timeout_ns; // bound of the wait (a rank that never arrives must not hang the GPU)
+};
+
 // ---- search.cu ----------------------------------------------------------
 // Search theta slices [theta_begin, theta_end); writes the 32-double record
 // (partial + finished outputs, see ndt2d_launch_combine) to d_partial32.  d_block_partials: scratch, >= capacity returned by
@@ -152,7 +174,8 @@ int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
   uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin = nullptr,
-  cudaEvent_t ev_end = nullptr);  // events (optional) bracket the search kernel alone
+  cudaEvent_t ev_end = nullptr,   // events (optional) bracket the search kernel alone
+  const ExchangeView * exchange = nullptr);  // non-null: fused cross-GPU exchange + combine
 
 // Combine n 16-double partial records (device) into one 32-double record
 // (device): [0..15] partial, [16..18] delta, [19] delta_written,

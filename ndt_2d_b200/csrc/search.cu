@@ -197,9 +197,89 @@ __global__ void __launch_bounds__(256) search_reduce_kernel(
   block_fold_12(best, acc, stage1 + static_cast<size_t>(blockIdx.x) * kStage1Doubles);
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long * p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Warp 0 of the finish kernel: publish this rank's record to every mailbox, wait for
+// everybody's, reduce (see ExchangeView in ndt2d_internal.h).  out32[0..15] holds this
+// rank's record on entry and the combined record on exit; out32[31] = 1 flags a timeout.
+__device__ void exchange_and_combine(ExchangeView xv, double * out32, const double * dth,
+  const double * dlin, uint32_t n_lin)
+{
+  const uint32_t lane = threadIdx.x;
+  const uint32_t parity = static_cast<uint32_t>(xv.seq & 1ull);
+  const size_t slot_mine = static_cast<size_t>(parity) * kExchangeMaxRanks + xv.rank;
+  if (lane < xv.world) {
+    char * base = static_cast<char *>(xv.peers[lane]);
+    double * dst = reinterpret_cast<double *>(base) + slot_mine * 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {dst[k] = out32[k];}
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(base + kExchangeRecordBytes) + slot_mine,
+      xv.seq);
+  }
+  char * mine = static_cast<char *>(xv.peers[xv.rank]);
+  const unsigned long long * flags =
+    reinterpret_cast<const unsigned long long *>(mine + kExchangeRecordBytes) +
+    static_cast<size_t>(parity) * kExchangeMaxRanks;
+  bool ok = true;
+  if (lane < xv.world) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flags + lane) < xv.seq) {
+      if (global_timer_ns() - t0 > xv.timeout_ns) {
+        ok = false;
+        break;
+      }
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    const double * recs = reinterpret_cast<const double *>(mine) +
+      static_cast<size_t>(parity) * kExchangeMaxRanks * 16;
+    Best best{0.0, kNoIndex};
+    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double cands = 0.0, npts = 0.0;
+    for (uint32_t r = 0; r < xv.world; ++r) {
+      // the reducing thread acquires every flag itself, so the record reads below are
+      // ordered after the peer's release
+      if (ok) {(void)ld_acquire_sys(flags + r);}
+      const volatile double * p = recs + static_cast<size_t>(r) * 16;
+      best_merge(best, p[0], p[1]);
+      for (int k = 0; k < 10; ++k) {s[k] += p[2 + k];}
+      cands += p[12];
+      npts = fmax(npts, p[13]);
+    }
+    out32[0] = best.score;
+    out32[1] = best.index;
+    for (int k = 0; k < 10; ++k) {out32[2 + k] = s[k];}
+    out32[12] = cands;
+    out32[13] = npts;
+    out32[14] = out32[15] = 0.0;
+    finish_record(out32, dth, dlin, n_lin);
+    if (!ok) {
+      out32[29] = nan("");   // a rank never arrived: no valid result
+      out32[31] = 1.0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) search_finish_kernel(
   const double * __restrict__ stage1, uint32_t n_records, SearchView sv, double n_candidates,
-  double * __restrict__ out32)
+  double * __restrict__ out32, ExchangeView xv)
 {
   Best best{0.0, kNoIndex};
   double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -218,18 +298,25 @@ __global__ void __launch_bounds__(256) search_finish_kernel(
     out32[14] = out32[15] = 0.0;
     finish_record(out32, sv.dth, sv.dlin, sv.n_lin);
   }
+  if (xv.world > 1) {
+    __threadfence();
+    __syncthreads();   // this rank's record is complete and visible to warp 0
+    if (threadIdx.x < 32) {exchange_and_combine(xv, out32, sv.dth, sv.dlin, sv.n_lin);}
+  }
 }
 
 // block_partials: n_blocks records of NDT2D_BLOCK_PARTIAL doubles, followed by room for
 // kReduceBlocks stage-1 records (ndt2d_search_scratch_doubles accounts for it).
 int launch_final(const double * d_block_partials, uint32_t n_blocks, double * d_stage1,
   const SearchView & sv, double n_candidates, double * d_partial32, cudaStream_t stream,
-  Counters * ctr)
+  Counters * ctr, const ExchangeView * exchange)
 {
+  ExchangeView xv{};
+  if (exchange) {xv = *exchange;}
   const uint32_t nb = min(kReduceBlocks, max(1u, (n_blocks + 255u) / 256u));
   search_reduce_kernel<<<nb, 256, 0, stream>>>(d_block_partials, n_blocks, d_stage1);
   NDT2D_LAUNCH_CHECK(ctr);
-  search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, sv, n_candidates, d_partial32);
+  search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, sv, n_candidates, d_partial32, xv);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
 }
@@ -324,9 +411,17 @@ int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
   uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin,
-  cudaEvent_t ev_end)
+  cudaEvent_t ev_end, const ExchangeView * exchange)
 {
   if (theta_end <= theta_begin || sv.n_lin == 0) {
+    if (exchange) {
+      // a rank without slices still takes part in the exchange: neutral record through
+      // the same finish kernel (zero stage-1 records)
+      ExchangeView xv = *exchange;
+      search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, 0, sv, 0.0, d_partial32, xv);
+      NDT2D_LAUNCH_CHECK(ctr);
+      return NDT2D_OK;
+    }
     empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
     NDT2D_LAUNCH_CHECK(ctr);
     return NDT2D_OK;
@@ -346,7 +441,7 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_jobs, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr);
+             n_candidates, d_partial32, stream, ctr, exchange);
   }
   if (variant == 2) {
     uint32_t n_blocks = 0;
@@ -356,7 +451,7 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_blocks, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr);
+             n_candidates, d_partial32, stream, ctr, exchange);
   }
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
@@ -373,7 +468,7 @@ int ndt2d_launch_search(
   }
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
-           n_candidates, d_partial32, stream, ctr);
+           n_candidates, d_partial32, stream, ctr, exchange);
 }
 
 int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,

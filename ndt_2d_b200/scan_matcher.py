@@ -270,6 +270,28 @@ class ScanMatcherNDT:
         L.check(L.lib.ndt2d_matcher_search_staged_strided(self.handle, theta_begin, theta_end, stride,
                                                           d_partial or None), "ndt2d_matcher_search_staged")
 
+    # ---- fused cross-GPU exchange
+    def exchange_init(self, world: int, rank: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        L.check(L.lib.ndt2d_matcher_exchange_init(self.handle, world, rank, h), "ndt2d_matcher_exchange_init")
+        return bytes(h)
+
+    def exchange_connect(self, handles) -> None:
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        L.check(L.lib.ndt2d_matcher_exchange_connect(self.handle, buf), "ndt2d_matcher_exchange_connect")
+
+    def search_exchange(self, theta_begin: int, theta_end: int, stride: int, seq: int) -> None:
+        L.check(L.lib.ndt2d_matcher_search_exchange(self.handle, theta_begin, theta_end, stride, seq),
+                "ndt2d_matcher_search_exchange")
+
+    def fetch_result(self):
+        delta, cov = np.zeros(3), np.zeros((3, 3))
+        written, score = C.c_int(0), C.c_double(0.0)
+        L.check(L.lib.ndt2d_matcher_fetch_result(self.handle, L.dptr(delta), C.byref(written), L.dptr(cov),
+                                                 C.byref(score)), "ndt2d_matcher_fetch_result")
+        return float(score.value), delta, bool(written.value), cov
+
     def fetch_partial(self) -> np.ndarray:
         out = np.zeros(L.PARTIAL_DOUBLES)
         L.check(L.lib.ndt2d_matcher_fetch_partial(self.handle, L.dptr(out)), "ndt2d_matcher_fetch_partial")

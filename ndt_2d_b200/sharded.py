@@ -72,9 +72,16 @@ def combine_host(dth: np.ndarray, dlin: np.ndarray, partials: np.ndarray):
 
 
 class ShardedSearch:
-    """matchScan of one query scan split over the ranks of a process group (GPU ranks)."""
+    """matchScan of one query scan split over the ranks of a process group (GPU ranks).
 
-    def __init__(self, matcher, rank: int, world: int, device, group=None):
+    exchange = "p2p"  : the search's last kernel stores this rank's record into every rank's
+                        mailbox over NVLink (CUDA IPC peer memory), waits for the others and
+                        reduces -- no collective call at all (ndt2d_matcher_search_exchange)
+    exchange = "nccl" : all-gather of the records through torch.distributed, then a combine kernel
+    exchange = "auto" : "p2p" if every rank could map its peers' mailboxes, else "nccl"
+    """
+
+    def __init__(self, matcher, rank: int, world: int, device, group=None, exchange: str = "auto"):
         import torch
         self.m, self.rank, self.world, self.group = matcher, rank, world, group
         na, _ = matcher.search_shape()
@@ -82,15 +89,49 @@ class ShardedSearch:
         self.n_theta = n_slices(self.lo, self.hi, self.stride)
         self.gathered = torch.zeros(world * PARTIAL_DOUBLES, dtype=torch.float64, device=device)
         self.mine = self.gathered[rank * PARTIAL_DOUBLES:(rank + 1) * PARTIAL_DOUBLES]
+        self.seq = 0
+        self.exchange = "nccl"
+        if world > 1 and exchange in ("auto", "p2p"):
+            self.exchange = "p2p" if self._connect_p2p(device) else "nccl"
+            if exchange == "p2p" and self.exchange != "p2p":
+                raise RuntimeError("peer mailboxes could not be mapped on every rank (CUDA IPC)")
+        elif world == 1:
+            self.exchange = "none"
+
+    def _connect_p2p(self, device) -> bool:
+        """All-gathers the mailboxes' IPC handles once and maps them; agreed on by all ranks."""
+        import torch
+        import torch.distributed as dist
+        ok = 1
+        try:
+            mine = self.m.exchange_init(self.world, self.rank)
+        except L.Ndt2dError:
+            mine, ok = bytes(64), 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        if ok:
+            try:
+                self.m.exchange_connect(handles)
+            except L.Ndt2dError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
 
     def search_staged(self):
         """Launch this rank's slices of the staged scan + the exchange (asynchronous)."""
+        if self.exchange == "p2p":
+            self.seq += 1
+            self.m.search_exchange(self.lo, self.hi, self.stride, self.seq)
+            return
         self.m.search_staged(self.lo, self.hi, self.mine.data_ptr(), stride=self.stride)
         if self.world > 1:
             exchange_partials(self.mine.clone(), self.gathered, self.group)
 
     def result(self):
-        """Device-side combine of the gathered records -> (score, delta, written, cov)."""
+        """-> (score, delta, written, cov) of the whole search; every rank holds the same."""
+        if self.exchange == "p2p":
+            return self.m.fetch_result()
         return self.m.combine_device(self.gathered.data_ptr(), self.world)
 
     def match_scan(self, pose, points):
