@@ -510,7 +510,7 @@ def cpu_baseline_and_parity(w, m, result, args):
     parity: the reference's matchScan on a window centred on the device's winner must
     find the same candidate with the same score."""
     from oracle import binding as B
-    n_theta = 4
+    n_theta = 16       # ~14 s of single-thread CPU work
     value, dt, kind, cands = reference_sample(w, n_theta, 1)
     cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
            "sample": f"{n_theta} of 3142 theta slices x 400 x 400 candidates x 1080 beams "
