@@ -409,6 +409,29 @@ __device__ __forceinline__ void stats_walk(
   }
 }
 
+// The two packed records of one finished cell (layout: ndt2d_internal.h, ModelView).
+__device__ __forceinline__ void write_records(
+  const CellStats & c, double cell_size, double * __restrict__ rr, double * __restrict__ f)
+{
+  // -0.5 * information: scaling by a power of two is exact, so the device
+  // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
+  rr[0] = c.mean[0];
+  rr[1] = c.mean[1];
+  rr[2] = -0.5 * c.info[0];  // (0,0)
+  rr[3] = -0.5 * c.info[2];  // (1,0)
+  rr[4] = -0.5 * c.info[1];  // (0,1)
+  rr[5] = -0.5 * c.info[3];  // (1,1)
+  // short form of the search kernel
+  constexpr double kLog2e = 1.44269504088896340736;
+  const double mag = fmax(fmax(fabs(c.info[0]), fabs(c.info[3])), fmax(fabs(c.info[1]), fabs(c.info[2])));
+  f[0] = c.mean[0];
+  f[1] = c.mean[1];
+  f[2] = rr[2] * kLog2e;
+  f[3] = (rr[3] + rr[4]) * kLog2e;
+  f[4] = rr[5] * kLog2e;
+  f[5] = (mag * (cell_size * cell_size) <= 1.0e7) ? 0.0 : 1.0;  // NaN -> stiff
+}
+
 // K3b: the cells of the head list replay Cell::addPoint's recurrence and emit their
 // records.  The five running quantities (mean x, mean y, second moments xx, xy, yy) are
 // independent recurrences of the same form v <- (v * n + term) / (n + 1), so a cell is
@@ -478,25 +501,8 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
   const uint2 w = occ[p >> 5];
   const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
   if (rank >= rec_cap) {return;}
-  double * rr = rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
-  // -0.5 * information: scaling by a power of two is exact, so the device
-  // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
-  rr[0] = c.mean[0];
-  rr[1] = c.mean[1];
-  rr[2] = -0.5 * c.info[0];  // (0,0)
-  rr[3] = -0.5 * c.info[2];  // (1,0)
-  rr[4] = -0.5 * c.info[1];  // (0,1)
-  rr[5] = -0.5 * c.info[3];  // (1,1)
-  // short-form record of the search kernel (ndt2d_internal.h, ModelView::rec_fast)
-  constexpr double kLog2e = 1.44269504088896340736;
-  double * f = rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES;
-  const double mag = fmax(fmax(fabs(c.info[0]), fabs(c.info[3])), fmax(fabs(c.info[1]), fabs(c.info[2])));
-  f[0] = c.mean[0];
-  f[1] = c.mean[1];
-  f[2] = rr[2] * kLog2e;
-  f[3] = (rr[3] + rr[4]) * kLog2e;
-  f[4] = rr[5] * kLog2e;
-  f[5] = (mag * (g.cell_size * g.cell_size) <= 1.0e7) ? 0.0 : 1.0;  // NaN -> stiff
+  write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+    rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
 }
 
 // Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.
@@ -560,6 +566,184 @@ __global__ void __launch_bounds__(256) dilate_kernel(
     occ_bits_at(occ, g.n_words, pos + g.pitch) | occ_bits_at(occ, g.n_words, pos + g.pitch + 1);
 }
 
+
+// ------------------------------------------------------------------ small models
+// A rolling-window model (config 1: 10 scans, 3,600 points; a loop-closure window:
+// 1-2 scans) is far too small for the multi-launch pipeline above: ~15 dependent
+// launches of a few microseconds each.  build_small_kernel does the whole build in ONE
+// CTA: transform + key, a stable in-shared-memory bitonic sort of (key << 32 | point
+// index), run lengths, occupancy bitmap + rank prefix + dilated bitmap, and the same
+// 8-lanes-per-cell moment recurrences -- identical results (the sort is stable because
+// the point index is part of the sort item; the recurrence walks the points in order).
+constexpr uint32_t kSmallMaxPoints = 4096;
+constexpr uint32_t kSmallMaxWords = 2048;   // padded cells <= 65,536
+constexpr uint32_t kSmallThreads = 1024;
+constexpr uint32_t kSmallMaxHeads = kSmallMaxPoints / 5 + 1;
+
+struct SmallSmem
+{
+  unsigned long long items[kSmallMaxPoints];
+  double wx[kSmallMaxPoints];
+  double wy[kSmallMaxPoints];
+  uint32_t occw[kSmallMaxWords];
+  uint32_t pref[kSmallMaxWords];
+  uint2 heads[kSmallMaxHeads];
+  uint32_t n_heads;
+  uint32_t total;
+};
+
+__device__ __forceinline__ uint32_t small_bits_at(const uint32_t * occw, uint32_t n_words, uint32_t pos)
+{
+  const uint32_t w = pos >> 5, sh = pos & 31u;
+  const uint32_t lo = w < n_words ? occw[w] : 0u;
+  const uint32_t hi = (w + 1) < n_words ? occw[w + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(
+  GridDesc g, const double4 * __restrict__ scan_tf, const uint64_t * __restrict__ offsets,
+  uint32_t n_scans, const double2 * __restrict__ pts, uint32_t n_points,
+  uint32_t * __restrict__ key_out, uint32_t * __restrict__ val_out, uint32_t * __restrict__ seglen,
+  double * __restrict__ sx, double * __restrict__ sy, uint2 * __restrict__ occ,
+  uint32_t * __restrict__ occ_dilated, double * __restrict__ rec, double * __restrict__ rec_fast,
+  uint32_t rec_cap, uint32_t * __restrict__ n_valid)
+{
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  SmallSmem & sm = *reinterpret_cast<SmallSmem *>(small_raw);
+  const uint32_t tid = threadIdx.x;
+  uint32_t n2 = 32;
+  while (n2 < n_points) {n2 <<= 1;}
+
+  for (uint32_t w = tid; w < g.n_words; w += kSmallThreads) {sm.occw[w] = 0u;}
+  if (tid == 0) {sm.n_heads = 0u;}
+  // ---- K1: transform + key (NDT::addScan, ndt_model.cpp:132-152)
+  for (uint32_t p = tid; p < n2; p += kSmallThreads) {
+    if (p < n_points) {
+      uint32_t lo = 0, hi = n_scans;          // scan s with offsets[s] <= p < offsets[s + 1]
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= p) {lo = mid;} else {hi = mid;}
+      }
+      const double4 tf = scan_tf[lo];
+      const double2 pt = pts[p];
+      const double X = __dadd_rn(tf.x, __dsub_rn(__dmul_rn(pt.x, tf.z), __dmul_rn(pt.y, tf.w)));
+      const double Y = __dadd_rn(tf.y, __dadd_rn(__dmul_rn(pt.x, tf.w), __dmul_rn(pt.y, tf.z)));
+      sm.wx[p] = X;
+      sm.wy[p] = Y;
+      sm.items[p] = (static_cast<unsigned long long>(cell_key(g, X, Y)) << 32) | p;
+    } else {
+      sm.items[p] = ~0ull;
+    }
+  }
+  __syncthreads();
+  // ---- K2: bitonic sort (ascending); the point index in the low word makes it stable
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < (n2 >> 1); t += kSmallThreads) {
+        const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // index with bit j clear
+        const uint32_t l = i | j;
+        const bool up = (i & k) == 0u;
+        const unsigned long long a = sm.items[i], b = sm.items[l];
+        if ((a > b) == up) {
+          sm.items[i] = b;
+          sm.items[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- K3a: run lengths, occupancy bits, head list; sorted copies for the parity dumps
+  for (uint32_t i = tid; i < n_points; i += kSmallThreads) {
+    const unsigned long long it = sm.items[i];
+    const uint32_t k = static_cast<uint32_t>(it >> 32), p = static_cast<uint32_t>(it);
+    key_out[i] = k;
+    val_out[i] = p;
+    sx[i] = sm.wx[p];
+    sy[i] = sm.wy[p];
+    if (k >= g.n_cells) {continue;}
+    if (i > 0 && static_cast<uint32_t>(sm.items[i - 1] >> 32) == k) {continue;}
+    uint32_t lo = i, step = 1, hi = n_points;
+    while (lo + step < n_points) {
+      if (static_cast<uint32_t>(sm.items[lo + step] >> 32) == k) {
+        lo += step;
+        step <<= 1;
+      } else {
+        hi = lo + step;
+        break;
+      }
+    }
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (static_cast<uint32_t>(sm.items[mid] >> 32) == k) {lo = mid;} else {hi = mid;}
+    }
+    const uint32_t len = hi - i;
+    seglen[i] = len;
+    if (len >= 5) {
+      const uint32_t pi = padded_index(g, k);
+      atomicOr(&sm.occw[pi >> 5], 1u << (pi & 31u));
+      sm.heads[atomicAdd(&sm.n_heads, 1u)] = make_uint2(i, len);
+    }
+  }
+  __syncthreads();
+  // ---- rank prefix over the occupancy words (<= 2 words per thread), dilated bitmap
+  {
+    const uint32_t w0 = 2u * tid, w1 = w0 + 1u;
+    const uint32_t c0 = w0 < g.n_words ? __popc(sm.occw[w0]) : 0u;
+    const uint32_t c1 = w1 < g.n_words ? __popc(sm.occw[w1]) : 0u;
+    // (the scan helper has one thread store the block total; it syncs before returning)
+    const uint32_t ex = block_exclusive_scan_1024(c0 + c1, &sm.total);
+    if (w0 < g.n_words) {sm.pref[w0] = ex;}
+    if (w1 < g.n_words) {sm.pref[w1] = ex + c0;}
+  }
+  __syncthreads();
+  if (tid == 0) {*n_valid = sm.total;}
+  for (uint32_t w = tid; w < g.n_words; w += kSmallThreads) {
+    occ[w] = make_uint2(sm.occw[w], sm.pref[w]);
+    const uint32_t pos = w << 5;
+    occ_dilated[w] = small_bits_at(sm.occw, g.n_words, pos) | small_bits_at(sm.occw, g.n_words, pos + 1) |
+      small_bits_at(sm.occw, g.n_words, pos + g.pitch) |
+      small_bits_at(sm.occw, g.n_words, pos + g.pitch + 1);
+  }
+  // ---- K3b: moment recurrences, 8 lanes per listed cell (see segment_moments_kernel)
+  const uint32_t group = tid >> 3, r = tid & 7u;
+  const uint32_t n_heads = sm.n_heads;
+  for (uint32_t base = 0; base < n_heads; base += kSmallThreads / 8) {
+    const uint32_t cell = base + group;
+    const bool have = cell < n_heads;
+    const uint2 h = have ? sm.heads[cell] : make_uint2(0u, 0u);
+    double v = 0.0, n = 0.0;
+    if (have && r < 5u) {
+      for (uint32_t j = 0; j < h.y; ++j) {
+        const uint32_t p = static_cast<uint32_t>(sm.items[h.x + j]);
+        const double x = sm.wx[p], y = sm.wy[p];
+        const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
+          r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
+        const double n1 = __dadd_rn(n, 1.0);
+        v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+        n = n1;
+      }
+    }
+    CellStats c;
+    c.n = static_cast<double>(h.y);
+    c.mean[0] = __shfl_sync(0xffffffffu, v, 0, 8);
+    c.mean[1] = __shfl_sync(0xffffffffu, v, 1, 8);
+    c.corr[0] = __shfl_sync(0xffffffffu, v, 2, 8);
+    c.corr[1] = __shfl_sync(0xffffffffu, v, 3, 8);
+    c.corr[2] = __shfl_sync(0xffffffffu, v, 4, 8);
+    if (have && r == 0u) {
+      stats_finalize(c);
+      const uint32_t k = static_cast<uint32_t>(sm.items[h.x] >> 32);
+      const uint32_t pi = padded_index(g, k);
+      const uint32_t bits = sm.occw[pi >> 5];
+      const uint32_t rank = sm.pref[pi >> 5] + __popc(bits & ((1u << (pi & 31u)) - 1u));
+      if (rank < rec_cap) {
+        write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+      }
+    }
+  }
+}
+
 int bits_needed(uint32_t max_value)
 {
   int b = 1;
@@ -581,6 +765,22 @@ int ndt2d_launch_build(
   double * d_rec, double * d_rec_fast, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream,
   Counters * ctr, int * sorted_buf)
 {
+  if (n_points > 0 && n_points <= kSmallMaxPoints && g.n_words <= kSmallMaxWords) {
+    // small model: the whole build in one CTA / one launch
+    static bool configured = false;
+    if (!configured) {
+      NDT2D_CUDA_TRY(cudaFuncSetAttribute(build_small_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallSmem))));
+      configured = true;
+    }
+    build_small_kernel<<<1, kSmallThreads, sizeof(SmallSmem), stream>>>(
+      g, d_scan_tf, d_offsets, static_cast<uint32_t>(n_scans), d_pts, static_cast<uint32_t>(n_points),
+      s.key[0], s.val[0], s.seglen, s.sx, s.sy, d_occ, d_occ_dilated, d_rec, d_rec_fast, rec_cap,
+      d_n_valid);
+    NDT2D_LAUNCH_CHECK(ctr);
+    *sorted_buf = 0;
+    return NDT2D_OK;
+  }
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint2), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ_dilated, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, sizeof(uint32_t), stream));
