@@ -200,6 +200,9 @@ def cpu_reference_other(out):
     out["config2_particle_filter"]["cpu_reference"] = {
         "kind": kind, "cores": 1, "global_ndt_build_ms": t_build,
         "measure_ms_5000_particles_extrapolated_from_500": t_meas}
+    g = B.OccupancyGrid(lib, 0.05, 0.25)
+    out["occupancy_grid_config2_map"]["cpu_reference"] = {
+        "kind": kind, "cores": 1, "getMsg_ms": clock(lambda: g.get_msg(w.map_poses, w.map_offsets, w.map_points))}
     w = synth.config3()
     m = lib.new_matcher(w.params)
 
@@ -278,6 +281,17 @@ def other_workloads(torch, dev_index: int):
         "resampled_size": f.size()}
     f.close()
     m.close()
+    # occupancy-grid export of the config-2 map: 2,500 scans, 704k rays
+    from ndt_2d_b200 import OccupancyGrid
+    og = OccupancyGrid(0.05, 0.25, device=dev_index)
+    t_og = timed(lambda: og.getMsg(w.map_poses, w.map_offsets, w.map_points), reps=3, warm=1)
+    t_og_dev = timed(lambda: og.getMsg(w.map_poses, w.map_offsets, w.map_points, fetch=False), reps=3, warm=1)
+    meta, _ = og.getMsg(w.map_poses, w.map_offsets, w.map_points, fetch=False)
+    out["occupancy_grid_config2_map"] = {
+        "scans": int(w.map_poses.shape[0]), "rays": int(w.map_points.shape[0]),
+        "grid": [meta["width"], meta["height"]], "getMsg_ms": t_og * 1e3,
+        "getMsg_without_d2h_of_the_grid_ms": t_og_dev * 1e3, "rays_per_s": w.map_points.shape[0] / t_og}
+    og.close()
     # config 3: loop-closure batch
     w = synth.config3()
     m = ScanMatcherNDT.from_params(w.params, device=dev_index)

@@ -339,6 +339,47 @@ NDT2D_API int ndt2d_filter_set_cov(ndt2d_filter * f, const double * cov9);
 NDT2D_API int ndt2d_filter_last_draws(ndt2d_filter * f, uint64_t * out);
 
 /* ------------------------------------------------------------------------
+ * The step before the path
+ * ---------------------------------------------------------------------- */
+
+/* replaces the LaserScan -> ndt_2d::Scan conversion of Mapper::laserCallback
+ * (ndt_mapper.cpp:385-453): beams that are NaN or beyond range_max are dropped, the rest
+ * are projected in the laser frame (angle = angle_min + i * angle_increment, float
+ * arithmetic as in the reference), moved to the robot frame by laser_tf3 = {x, y, theta}
+ * and de-skewed with the motion during the scan: translation3 = end-of-scan odometry
+ * pose minus start-of-scan pose, spread linearly over the n beams.  laser_inverted
+ * walks the beams backwards with negated angles (index 0 is never visited, :411).
+ * out_pts_xy needs room for n points; *n_out = points kept, in the reference's order.
+ * Which beams are kept is exact; coordinates agree with the reference to ~1e-15
+ * relative (device cos / sin). */
+NDT2D_API int ndt2d_laser_to_points(
+  int device, const float * ranges, size_t n, float angle_min, float angle_increment,
+  double range_max, const double * laser_tf3, const double * translation3, int laser_inverted,
+  double * out_pts_xy, size_t * n_out);
+
+/* ------------------------------------------------------------------------
+ * Occupancy-grid export: ndt_2d::OccupancyGrid
+ * (include/ndt_2d/occupancy_grid.hpp:40-68, src/occupancy_grid.cpp)
+ * ---------------------------------------------------------------------- */
+typedef struct ndt2d_occupancy ndt2d_occupancy;
+
+/* replaces OccupancyGrid::OccupancyGrid(resolution, occ_thresh) (occupancy_grid.cpp:35-45) */
+NDT2D_API int ndt2d_occupancy_create(
+  double resolution, double occ_thresh, int device, ndt2d_occupancy ** out);
+NDT2D_API int ndt2d_occupancy_destroy(ndt2d_occupancy * g);
+/* replaces OccupancyGrid::getMsg (:47-152) incl. updateBounds (:155-185): the bounds
+ * persist across calls and grow with the scans not seen before (only when the number of
+ * scans changed, as in the reference); every scan is ray-traced into hit / empty counters;
+ * info5 = {width, height, origin_x, origin_y, resolution} (grid.info).  The cell data
+ * stays on the device until fetched. */
+NDT2D_API int ndt2d_occupancy_render(
+  ndt2d_occupancy * g, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy, double * info5);
+/* grid.data of the last render: width * height int8 (-1 unknown, 0 free, 100 occupied),
+ * row-major, index = x + y * width (:112). */
+NDT2D_API int ndt2d_occupancy_fetch(ndt2d_occupancy * g, int8_t * data, size_t capacity);
+
+/* ------------------------------------------------------------------------
  * Roofline probes (bench.py): measured on the device the bench runs on.
  * ---------------------------------------------------------------------- */
 

@@ -14,7 +14,7 @@ _EXPORTS = {
     "Ndt2dError": "._lib", "lib": "._lib", "lib_path": "._lib",
     "MotionModel": ".particle_filter", "ParticleFilter": ".particle_filter",
     "ParameterNode": ".scan_matcher", "Pose2d": ".scan_matcher", "Scan": ".scan_matcher",
-    "ScanMatcherNDT": ".scan_matcher",
+    "ScanMatcherNDT": ".scan_matcher", "laser_to_points": ".scan_matcher", "OccupancyGrid": ".scan_matcher",
 }
 
 __all__ = sorted(_EXPORTS)

@@ -96,6 +96,13 @@ SIGNATURES = {
     "ndt2d_matcher_search_stats": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_build_stats": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_stream": (_vp, [_vp]),
+    "ndt2d_occupancy_create": (C.c_int, [C.c_double, C.c_double, C.c_int, C.POINTER(_vp)]),
+    "ndt2d_occupancy_destroy": (C.c_int, [_vp]),
+    "ndt2d_occupancy_render": (C.c_int, [_vp, C.c_size_t, _dp, _u64p, _dp, _dp]),
+    "ndt2d_occupancy_fetch": (C.c_int, [_vp, C.POINTER(C.c_int8), C.c_size_t]),
+    "ndt2d_laser_to_points": (
+        C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_float, C.c_double, _dp, _dp,
+                  C.c_int, _dp, C.POINTER(C.c_size_t)]),
     "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_filter_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, _vp, C.POINTER(_vp)]),

@@ -68,6 +68,56 @@ def _pose3(pose) -> np.ndarray:
     return L.f64(pose).reshape(3)
 
 
+class OccupancyGrid:
+    """Mirror of ndt_2d::OccupancyGrid (occupancy_grid.hpp:40-68) on the device."""
+
+    def __init__(self, resolution: float, occ_thresh: float, device: int = -1):
+        self._h = C.c_void_p()
+        L.check(L.lib.ndt2d_occupancy_create(resolution, occ_thresh, device, C.byref(self._h)),
+                "ndt2d_occupancy_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.ndt2d_occupancy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def getMsg(self, poses, offsets, points, fetch: bool = True):
+        """-> (info dict, data int8[height, width])  (occupancy_grid.cpp:47-152)"""
+        p = L.f64(poses).reshape(-1, 3)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        pts = L.f64(points).reshape(-1, 2)
+        info = np.zeros(5)
+        L.check(L.lib.ndt2d_occupancy_render(self._h, p.shape[0], L.dptr(p), L.u64ptr(o), L.dptr(pts),
+                                             L.dptr(info)), "ndt2d_occupancy_render")
+        w, h = int(info[0]), int(info[1])
+        meta = dict(width=w, height=h, origin_x=info[2], origin_y=info[3], resolution=info[4])
+        if not fetch:
+            return meta, None
+        data = np.zeros(max(w * h, 1), dtype=np.int8)
+        L.check(L.lib.ndt2d_occupancy_fetch(self._h, data.ctypes.data_as(C.POINTER(C.c_int8)), data.shape[0]),
+                "ndt2d_occupancy_fetch")
+        return meta, data[:w * h].reshape(h, w)
+
+
+def laser_to_points(ranges, angle_min: float, angle_increment: float, range_max: float, laser_tf,
+                    translation, inverted: bool = False, device: int = -1) -> np.ndarray:
+    """LaserScan -> ndt_2d::Scan points on the device (Mapper::laserCallback, ndt_mapper.cpp:385-453)."""
+    r = np.ascontiguousarray(ranges, dtype=np.float32)
+    out = np.zeros((max(r.shape[0], 1), 2))
+    lt, tr = _pose3(laser_tf), _pose3(translation)
+    n = C.c_size_t(0)
+    L.check(L.lib.ndt2d_laser_to_points(device, r.ctypes.data_as(C.POINTER(C.c_float)), r.shape[0],
+                                        angle_min, angle_increment, range_max, L.dptr(lt), L.dptr(tr),
+                                        int(bool(inverted)), L.dptr(out), C.byref(n)), "ndt2d_laser_to_points")
+    return out[:n.value].copy()
+
+
 class ScanMatcherNDT:
     """B200 backend behind the reference's ScanMatcher interface."""
 

@@ -68,6 +68,9 @@ class OracleLib:
             "normalize_angle": (C.c_double, [C.c_double]),
             "shortest_angular_distance": (C.c_double, [C.c_double, C.c_double]),
             "kd_leaf_counts": (None, [_dp, C.c_size_t, _dp, _u64p]),
+            "occ_create": (_vp, [C.c_double, C.c_double]), "occ_destroy": (None, [_vp]),
+            "occ_render": (C.c_size_t, [_vp, C.c_size_t, _dp, _u64p, _dp, _dp, C.POINTER(C.c_int8),
+                                        C.c_size_t]),
         }
         if prefix == "orc_":
             sig.update({
@@ -75,6 +78,8 @@ class OracleLib:
                 "matcher_match_scan_window": (
                     C.c_double, [_vp, _dp, _dp, C.c_size_t, _dp, C.POINTER(C.c_int), _dp, _dp,
                                  C.c_size_t, C.c_size_t, _u64p]),
+                "laser_to_points": (C.c_size_t, [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_float,
+                                                 C.c_double, _dp, _dp, C.c_int, _dp]),
                 "matcher_partial": (None, [_vp, _dp, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _dp]),
                 "pf_measure": (None, [_vp, _dp, C.c_size_t, _dp, C.c_size_t, _dp]),
                 "pf_update_statistics": (None, [_dp, _dp, C.c_size_t, _dp, _dp]),
@@ -210,6 +215,42 @@ class Matcher:
         return self.o.matcher_score_points(self.h, _d(points), points.shape[0], _d(pose))
 
 
+class OccupancyGrid:
+    """ndt_2d::OccupancyGrid of either oracle library (state persists across getMsg calls)."""
+
+    def __init__(self, olib: OracleLib, resolution: float, occ_thresh: float):
+        self.o = olib
+        self.h = olib.occ_create(resolution, occ_thresh)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.o.occ_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def get_msg(self, poses, offsets, points):
+        """-> (info dict, data int8[height, width])"""
+        poses = _f64(poses).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        points = _f64(points).reshape(-1, 2)
+        info = np.zeros(5)
+        cap = 1 << 16
+        while True:
+            data = np.zeros(cap, dtype=np.int8)
+            # NB: a second call with the same number of scans does not update the bounds, like the
+            # reference; calling again only to size the buffer is therefore harmless
+            n = self.o.occ_render(self.h, poses.shape[0], _d(poses), offsets.ctypes.data_as(_u64p),
+                                  _d(points), _d(info), data.ctypes.data_as(C.POINTER(C.c_int8)), cap)
+            if n <= cap:
+                break
+            cap = int(n)
+        w, h = int(info[0]), int(info[1])
+        return dict(width=w, height=h, origin_x=info[2], origin_y=info[3], resolution=info[4]), \
+            data[:w * h].reshape(h, w).copy()
+
+
 def load_oracle() -> OracleLib:
     if not ORACLE_SO.exists():
         build()
@@ -221,6 +262,17 @@ def load_ref():
     if not REF_SO.exists():
         return None
     return OracleLib(REF_SO, "ref_")
+
+
+def laser_to_points(o: OracleLib, ranges, angle_min, angle_increment, range_max, laser_tf, translation,
+                    inverted: bool) -> np.ndarray:
+    """Mapper::laserCallback's LaserScan -> points conversion (oracle restatement only)."""
+    r = np.ascontiguousarray(ranges, dtype=np.float32)
+    out = np.zeros((max(r.shape[0], 1), 2))
+    lt, tr = _f64(laser_tf).reshape(3), _f64(translation).reshape(3)
+    n = o.laser_to_points(r.ctypes.data_as(C.POINTER(C.c_float)), r.shape[0], angle_min, angle_increment,
+                          range_max, _d(lt), _d(tr), int(bool(inverted)), _d(out))
+    return out[:n].copy()
 
 
 # ---- oracle-only particle-filter helpers ---------------------------------

@@ -794,3 +794,169 @@ ORC_API size_t orc_pf_resample(
   free(cp);
   return size;
 }
+
+/* ------------------------------------------------------------------ */
+/* LaserScan -> Scan points (Mapper::laserCallback, src/ndt_mapper.cpp:385-453)   */
+/* SURVEY.md section 8(f) rank 3.  The reference code sits inside the ROS node and */
+/* cannot be compiled here, and no reference test covers it: this restatement is   */
+/* PARITY UNPINNED (checked only against hand-computed cases).                     */
+/* ------------------------------------------------------------------ */
+ORC_API size_t orc_laser_to_points(
+  const float * ranges, size_t n, float angle_min, float angle_increment, double range_max,
+  const double * laser_tf3, const double * translation3, int laser_inverted, double * out_xy)
+{
+  /* :392-395 */
+  const double pm_x = translation3[0] / n, pm_y = translation3[1] / n, pm_th = translation3[2] / n;
+  /* :403-404 */
+  const double cos_lt = cos(laser_tf3[2]), sin_lt = sin(laser_tf3[2]);
+  size_t m = 0;
+  if (laser_inverted) {
+    for (size_t i = n - 1; i > 0 && n > 0; --i) { /* :411 -- index 0 is never visited */
+      if (isnan(ranges[i]) || ranges[i] > range_max) {continue;} /* :414 */
+      const double angle = -(angle_min + i * angle_increment);   /* float arithmetic, :416 */
+      const double lx = cos(angle) * ranges[i], ly = sin(angle) * ranges[i];
+      const double px = cos_lt * lx - sin_lt * ly + laser_tf3[0];
+      const double py = sin_lt * lx + cos_lt * ly + laser_tf3[1];
+      const double cos_tt = cos(translation3[2] - (pm_th * i));
+      const double sin_tt = sin(translation3[2] - (pm_th * i));
+      out_xy[2 * m] = cos_tt * px - sin_tt * py + (translation3[0] - (pm_x * i));
+      out_xy[2 * m + 1] = sin_tt * px + cos_tt * py + (translation3[1] - (pm_y * i));
+      ++m;
+    }
+  } else {
+    for (size_t i = 0; i < n; ++i) {
+      if (isnan(ranges[i]) || ranges[i] > range_max) {continue;} /* :436 */
+      const double angle = (angle_min + i * angle_increment);    /* float arithmetic, :438 */
+      const double lx = cos(angle) * ranges[i], ly = sin(angle) * ranges[i];
+      const double px = cos_lt * lx - sin_lt * ly + laser_tf3[0];
+      const double py = sin_lt * lx + cos_lt * ly + laser_tf3[1];
+      const double cos_tt = cos(pm_th * i);
+      const double sin_tt = sin(pm_th * i);
+      out_xy[2 * m] = cos_tt * px - sin_tt * py + (pm_x * i);
+      out_xy[2 * m + 1] = sin_tt * px + cos_tt * py + (pm_y * i);
+      ++m;
+    }
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------ */
+/* OccupancyGrid (src/occupancy_grid.cpp:35-185), SURVEY.md 8(f) rank 4 */
+/* ------------------------------------------------------------------ */
+typedef struct
+{
+  double resolution, occ_thresh;
+  double min_x, max_x, min_y, max_y;
+  size_t num_scans;
+} orc_occ;
+
+ORC_API void * orc_occ_create(double resolution, double occ_thresh)
+{
+  orc_occ * g = (orc_occ *)calloc(1, sizeof(orc_occ)); /* bounds and num_scans start at 0 (:38-43) */
+  g->resolution = resolution;
+  g->occ_thresh = occ_thresh;
+  return g;
+}
+ORC_API void orc_occ_destroy(void * g) {free(g);}
+
+/* updateBounds (:155-185) */
+static void occ_update_bounds(
+  orc_occ * g, size_t n_scans, const double * poses, const uint64_t * offsets, const double * pts)
+{
+  const size_t start_idx = g->num_scans;
+  g->num_scans = n_scans;
+  for (size_t i = start_idx; i < g->num_scans; ++i) {
+    const double x = poses[3 * i], y = poses[3 * i + 1];
+    const double cos_th = cos(poses[3 * i + 2]), sin_th = sin(poses[3 * i + 2]);
+    for (uint64_t p = offsets[i]; p < offsets[i + 1]; ++p) {
+      double px = x, py = y;
+      px += pts[2 * p] * cos_th - pts[2 * p + 1] * sin_th;
+      py += pts[2 * p] * sin_th + pts[2 * p + 1] * cos_th;
+      g->min_x = px < g->min_x ? px : g->min_x; /* std::min(p.x, min_x_) */
+      g->max_x = g->max_x < px ? px : g->max_x; /* std::max(p.x, max_x_) */
+      g->min_y = py < g->min_y ? py : g->min_y;
+      g->max_y = g->max_y < py ? py : g->max_y;
+    }
+  }
+  g->min_x = floor(g->min_x / g->resolution) * g->resolution;
+  g->max_x = ceil(g->max_x / g->resolution) * g->resolution;
+  g->min_y = floor(g->min_y / g->resolution) * g->resolution;
+  g->max_y = ceil(g->max_y / g->resolution) * g->resolution;
+}
+
+/* getMsg (:47-152); info5 = {width, height, origin_x, origin_y, (float)resolution};
+ * data (capacity cells) filled if large enough; returns the number of cells. */
+ORC_API size_t orc_occ_render(
+  void * gv, size_t n_scans, const double * poses, const uint64_t * offsets, const double * pts,
+  double * info5, int8_t * data, size_t capacity)
+{
+  orc_occ * g = (orc_occ *)gv;
+  if (n_scans != g->num_scans) {occ_update_bounds(g, n_scans, poses, offsets, pts);} /* :51-54 */
+  const double pad = 5 * g->resolution;
+  const uint32_t width = (uint32_t)((g->max_x - g->min_x + 2 * pad) / g->resolution);
+  const uint32_t height = (uint32_t)((g->max_y - g->min_y + 2 * pad) / g->resolution);
+  const double origin_x = g->min_x - pad, origin_y = g->min_y - pad;
+  info5[0] = width;
+  info5[1] = height;
+  info5[2] = origin_x;
+  info5[3] = origin_y;
+  info5[4] = (float)g->resolution;
+  const size_t n_cells = (size_t)width * height;
+  if (!data || capacity < n_cells) {return n_cells;}
+  int * hit = (int *)calloc(n_cells ? n_cells : 1, sizeof(int));
+  int * empty = (int *)calloc(n_cells ? n_cells : 1, sizeof(int));
+  for (size_t s = 0; s < n_scans; ++s) {
+    const double pose_x = poses[3 * s], pose_y = poses[3 * s + 1];
+    const double cos_th = cos(poses[3 * s + 2]), sin_th = sin(poses[3 * s + 2]);
+    const int start_x = (int)((pose_x - origin_x) / g->resolution);
+    const int start_y = (int)((pose_y - origin_y) / g->resolution);
+    for (uint64_t p = offsets[s]; p < offsets[s + 1]; ++p) {
+      const double point_x = pts[2 * p] * cos_th - pts[2 * p + 1] * sin_th + pose_x;
+      const double point_y = pts[2 * p] * sin_th + pts[2 * p + 1] * cos_th + pose_y;
+      const int end_x = (int)((point_x - origin_x) / g->resolution);
+      const int end_y = (int)((point_y - origin_y) / g->resolution);
+      int dx = abs(end_x - start_x);
+      int sx = (start_x < end_x) ? 1 : -1;
+      int dy = -abs(end_y - start_y);
+      int sy = (start_y < end_y) ? 1 : -1;
+      int error = dx + dy;
+      int x = start_x, y = start_y;
+      while (1) {
+        const int index = x + y * (int)width;
+        /* the reference does not bounds-check; stale bounds could leave the grid */
+        const int inside = x >= 0 && y >= 0 && (uint32_t)x < width && (uint32_t)y < height;
+        if (x == end_x && y == end_y) {
+          if (inside) {++hit[index];}
+          break;
+        }
+        if (inside) {++empty[index];}
+        if (2 * error >= dy) {
+          if (x == end_x) {
+            if (inside) {++hit[index];}
+            break;
+          }
+          error = error + dy;
+          x += sx;
+        }
+        if (2 * error <= dx) {
+          if (y == end_y) {
+            if (inside) {++hit[index];}
+            break;
+          }
+          error = error + dx;
+          y += sy;
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < n_cells; ++i) {
+    const double touches = hit[i] + empty[i];
+    data[i] = -1;
+    if (touches > 0.5) {
+      data[i] = ((double)hit[i] / touches > g->occ_thresh) ? 100 : 0;
+    }
+  }
+  free(hit);
+  free(empty);
+  return n_cells;
+}

@@ -30,6 +30,7 @@
 #include <ndt_2d/kd_tree.hpp>
 #include <ndt_2d/motion_model.hpp>
 #include <ndt_2d/ndt_model.hpp>
+#include <ndt_2d/occupancy_grid.hpp>
 #include <ndt_2d/particle_filter.hpp>
 #include <ndt_2d/scan.hpp>
 #include <ndt_2d/scan_matcher_ndt.hpp>
@@ -369,4 +370,33 @@ REF_API uint64_t ref_matcher_candidate_count(void * mv)
   for (double d = -m.angular_size_; d < m.angular_size_; d += m.angular_res_) {++na;}
   for (double d = -m.linear_size_; d < m.linear_size_; d += m.linear_res_) {++nl;}
   return na * nl * nl;
+}
+
+// ---------------------------------------------------------------- occupancy grid
+REF_API void * ref_occ_create(double resolution, double occ_thresh)
+{
+  return new ndt_2d::OccupancyGrid(resolution, occ_thresh);
+}
+REF_API void ref_occ_destroy(void * g) {delete static_cast<ndt_2d::OccupancyGrid *>(g);}
+// getMsg: info5 = {width, height, origin_x, origin_y, resolution (float)}; data copied to
+// `data` if it has room (capacity cells); returns the number of cells.
+REF_API size_t ref_occ_render(
+  void * g, size_t n_scans, const double * poses, const uint64_t * offsets, const double * pts_xy,
+  double * info5, int8_t * data, size_t capacity)
+{
+  std::vector<ndt_2d::ScanPtr> scans;
+  for (size_t k = 0; k < n_scans; ++k) {
+    scans.push_back(make_scan(poses + 3 * k, pts_xy + 2 * offsets[k], offsets[k + 1] - offsets[k]));
+  }
+  nav_msgs::msg::OccupancyGrid grid;
+  static_cast<ndt_2d::OccupancyGrid *>(g)->getMsg(scans, grid);
+  info5[0] = grid.info.width;
+  info5[1] = grid.info.height;
+  info5[2] = grid.info.origin.position.x;
+  info5[3] = grid.info.origin.position.y;
+  info5[4] = grid.info.resolution;
+  if (data && capacity >= grid.data.size()) {
+    memcpy(data, grid.data.data(), grid.data.size());
+  }
+  return grid.data.size();
 }

@@ -23,6 +23,8 @@
 #include <ndt_2d/motion_model.hpp>
 #include <ndt_2d/scan_matcher_ndt.hpp>
 
+#include <ndt_2d/occupancy_grid.hpp>
+#include <ndt_2d_b200/occupancy_grid.hpp>
 #include <ndt_2d_b200/particle_filter.hpp>
 #include <ndt_2d_b200/scan_matcher_ndt.hpp>
 
@@ -318,6 +320,27 @@ int main(int argc, char ** argv)
     df.resample(0.01, 2.3);
     expect(df.size() >= 100 && df.size() <= P, "resample keeps min <= n <= max");
     (void)kPi;
+  }
+
+  // ---- occupancy grid: two calls on one instance (the bounds persist), bit-exact grid
+  {
+    ndt_2d::OccupancyGrid rg(0.05, 0.25);
+    ndt_2d_b200::OccupancyGrid dg(0.05, 0.25);
+    for (size_t n : {size_t(4), scans.size()}) {
+      std::vector<ndt_2d::ScanPtr> some(scans.begin(), scans.begin() + n);
+      nav_msgs::msg::OccupancyGrid a, b;
+      rg.getMsg(some, a);
+      dg.getMsg(some, b);
+      expect(a.info.width == b.info.width && a.info.height == b.info.height &&
+        a.info.resolution == b.info.resolution &&
+        a.info.origin.position.x == b.info.origin.position.x &&
+        a.info.origin.position.y == b.info.origin.position.y, "occupancy grid meta data identical");
+      expect(a.data == b.data, "occupancy grid data bit-identical");
+      size_t occ = 0;
+      for (auto v : b.data) {occ += v == 100 ? 1 : 0;}
+      std::printf("occupancy grid: %zu scans -> %u x %u, %zu occupied cells\n", n, b.info.width,
+        b.info.height, occ);
+    }
   }
 
   std::printf("{\"plugin_parity\": \"%s\", \"failures\": %d}\n", g_failures ? "FAILED" : "ok",

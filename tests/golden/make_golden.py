@@ -4,7 +4,7 @@
     python tests/golden/make_golden.py          (needs /root/reference -> oracle/_ref)
 
 Every output in these files was produced by the reference's own sources
-(src/ndt_model.cpp, src/scan_matcher_ndt.cpp, src/particle_filter.cpp, compiled
+(src/ndt_model.cpp, src/scan_matcher_ndt.cpp, src/particle_filter.cpp, src/occupancy_grid.cpp, compiled
 unmodified and in place by oracle/Makefile into oracle/_ref/libndt2d_ref.so, g++ -O3
 -DNDEBUG, no -march -- the reference's Release flags).  The inputs are stored next to
 the outputs so the fixtures do not depend on the synthetic generator staying unchanged.
@@ -128,6 +128,22 @@ def kd_case(r, name):
     print(f"{name}: leaf counts {counts[:5].tolist()} ... {int(counts[-1])}")
 
 
+def occupancy_case(r, name):
+    """ndt_2d::OccupancyGrid::getMsg twice on one instance: 6 scans, then 10 (the bounds persist)."""
+    w = synth.config1()
+    g = B.OccupancyGrid(r, 0.05, 0.25)
+    out = dict(poses=w.map_poses, offsets=w.map_offsets.astype(np.uint64), points=w.map_points)
+    for k, n in enumerate((6, 10)):
+        info, data = g.get_msg(w.map_poses[:n], w.map_offsets[:n + 1], w.map_points)
+        out[f"c{k}_n"] = np.array([n])
+        out[f"c{k}_info"] = np.array([info["width"], info["height"], info["origin_x"], info["origin_y"],
+                                      info["resolution"]])
+        out[f"c{k}_data"] = data
+        print(f"{name}: {n} scans -> {info['width']} x {info['height']}, "
+              f"{int((data == 100).sum())} occupied, {int((data == 0).sum())} free")
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+
+
 def main():
     B.build(quiet=True)
     r = B.load_ref()
@@ -166,6 +182,7 @@ def main():
     matcher_case(r, "bbox_quirk", p, poses, offs, pts, [(poses[0], q)], [poses[0], poses[1]])
     filter_case(r, "particle_filter")
     kd_case(r, "kd_tree")
+    occupancy_case(r, "occupancy_grid")
 
 
 if __name__ == "__main__":
