@@ -186,6 +186,7 @@ struct ndt2d_matcher
   DeviceBuffer d_pts, d_trig, d_blockpart, d_partial, d_pose_tf, d_out, d_counter, d_coords, d_chunk;
   double pose_x = 0, pose_y = 0;
   uint32_t n_pts = 0;
+  size_t trig_offset_bytes = 0;     // (cos, sin) table inside d_pts, after the points
 
   PinnedBuffer h_stage, h_result;
   // Pipelined mode (match_scan_batch): host staging comes from a pinned arena that is
@@ -228,7 +229,7 @@ SearchView search_view(const ndt2d_matcher * m)
 {
   SearchView sv;
   sv.pts = m->d_pts.as<double2>();
-  sv.trig = m->d_trig.as<double2>();
+  sv.trig = reinterpret_cast<const double2 *>(m->d_pts.as<char>() + m->trig_offset_bytes);
   sv.dth = m->d_dth.as<double>();
   sv.dlin = m->d_dlin.as<double>();
   sv.pose_x = m->pose_x;
@@ -290,8 +291,7 @@ int add_scans_locked(
   ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
   const double * pts_xy)
 {
-  m->has_model = false;
-  m->staged = m->staged;  // a staged scan stays valid across rebuilds
+  m->has_model = false;  // (a staged scan stays valid across rebuilds)
   // bounding box (scan_matcher_ndt.cpp:53-64); max_* start at DBL_MIN (> 0)
   double min_x = DBL_MAX, max_x = DBL_MIN, min_y = DBL_MAX, max_y = DBL_MIN;
   for (size_t k = 0; k < n_scans; ++k) {
@@ -445,8 +445,8 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   char * hs = nullptr;
   int rc = stage_alloc(m, pts_bytes + trig_bytes + 64, &hs);
   if (rc) {return rc;}
-  if ((rc = m->d_pts.ensure(pts_bytes ? pts_bytes : 16))) {return rc;}
-  if ((rc = m->d_trig.ensure(trig_bytes ? trig_bytes : 16))) {return rc;}
+  // points and per-theta (cos, sin) share one device buffer: one H2D copy per scan
+  if ((rc = m->d_pts.ensure(pts_bytes + trig_bytes + 16))) {return rc;}
   double * h_pts = reinterpret_cast<double *>(hs);
   double * h_trig = h_pts + 2 * n_use;
   if (n_use) {subsample_points(pts_xy, npts, n_use, h_pts);}
@@ -456,12 +456,11 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
     h_trig[2 * k + 1] = sin(pose3[2] + m->dth[k]);
   }
   cudaStream_t st = m->stream;
-  if (pts_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes, cudaMemcpyHostToDevice, st));
+  if (pts_bytes + trig_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes + trig_bytes, cudaMemcpyHostToDevice,
+      st));
   }
-  if (trig_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_trig.p, h_trig, trig_bytes, cudaMemcpyHostToDevice, st));
-  }
+  m->trig_offset_bytes = pts_bytes;
   m->ctr.h2d_bytes += pts_bytes + trig_bytes;
   m->pose_x = pose3[0];
   m->pose_y = pose3[1];
@@ -472,7 +471,14 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
     m->prm.search_linear_resolution);
   if ((rc = m->d_blockpart.ensure(scratch * sizeof(double)))) {return rc;}
   if ((rc = m->d_partial.ensure(32 * sizeof(double)))) {return rc;}
-  if ((rc = m->d_counter.ensure(64))) {return rc;}
+  {
+    void * before = m->d_counter.p;
+    if ((rc = m->d_counter.ensure(64))) {return rc;}
+    if (m->d_counter.p != before) {
+      // job counter + statistics start at zero; every search's finish kernel re-zeroes them
+      NDT2D_CUDA_TRY(cudaMemsetAsync(m->d_counter.p, 0, m->d_counter.cap, m->stream));
+    }
+  }
   {
     // coordinate pre-pass table of the search kernel (skipped above 512 MiB)
     const size_t cb = ndt2d_region_coords_bytes(m->prm.ndt_resolution, static_cast<uint32_t>(n_ang),
@@ -887,15 +893,12 @@ static int match_scan_batch_locked(
     rc = stage_scan_locked(s, query_poses + 3 * j, query_pts_xy + 2 * q0,
         static_cast<size_t>(q1 - q0));
     if (rc) {break;}
+    // the search's finish kernel writes the job's 32-double record straight into its slot
     rc = ndt2d_launch_search(model_view(s), search_view(s), 0,
         static_cast<uint32_t>(s->dth.size()), m->prm.kernel_variant, s->d_blockpart.as<double>(),
-        s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &m->ctr);
+        s->d_batch_results.as<double>() + 32 * slot, nullptr, s->d_counter.as<uint32_t>(),
+        s->stream, &m->ctr);
     if (rc) {break;}
-    if (cudaMemcpyAsync(s->d_batch_results.as<double>() + 32 * slot, s->d_partial.p,
-      32 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) != cudaSuccess)
-    {
-      rc = NDT2D_ERR_CUDA;
-    }
   }
   for (size_t l = 0; l < n_lanes; ++l) {
     ndt2d_matcher * s = m->lanes[l];
@@ -1415,12 +1418,13 @@ NDT2D_API int ndt2d_matcher_search_stats(ndt2d_matcher * m, uint64_t * out4)
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
   if (!m->d_counter.p) {return NDT2D_ERR_STATE;}
   DeviceGuard guard(m->device);
-  uint64_t h[4] = {0, 0, 0, 0};
+  uint64_t h[6] = {0, 0, 0, 0, 0, 0};
   NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
-  NDT2D_CUDA_TRY(cudaMemcpy(h, m->d_counter.p, 32, cudaMemcpyDeviceToHost));
-  out4[0] = h[1];                  // useful evaluations
-  out4[1] = h[2];                  // (point, region) items
-  out4[2] = h[0] & 0xffffffffu;    // job counter at exit (>= jobs)
+  NDT2D_CUDA_TRY(cudaMemcpy(h, m->d_counter.p, sizeof(h), cudaMemcpyDeviceToHost));
+  // the finish kernel moved the launch's tallies to the "last search" slots [3..5]
+  out4[0] = h[3];                  // useful evaluations
+  out4[1] = h[4];                  // (point, region) items
+  out4[2] = h[5] & 0xffffffffu;    // job counter at exit (>= jobs)
   if (m->ev_valid && m->ev_begin && m->ev_end) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end) == cudaSuccess) {

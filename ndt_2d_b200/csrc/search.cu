@@ -277,17 +277,43 @@ __device__ void exchange_and_combine(ExchangeView xv, double * out32, const doub
   }
 }
 
+// `direct`: the records are the 9-double job records themselves (few jobs: stage 1 skipped).
+// `counters` (may be null): the job counter / statistics block of the production kernel,
+// cleared here for the next search after the statistics were moved to their "last" slots.
 __global__ void __launch_bounds__(256) search_finish_kernel(
-  const double * __restrict__ stage1, uint32_t n_records, SearchView sv, double n_candidates,
-  double * __restrict__ out32, ExchangeView xv)
+  const double * __restrict__ stage1, uint32_t n_records, int direct, SearchView sv,
+  double n_candidates, double * __restrict__ out32, ExchangeView xv,
+  unsigned long long * __restrict__ counters)
 {
   Best best{0.0, kNoIndex};
   double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (threadIdx.x == 0 && counters) {
+    counters[3] = counters[1];
+    counters[4] = counters[2];
+    counters[5] = counters[0];
+    counters[0] = counters[1] = counters[2] = 0ull;
+  }
   for (uint32_t b = threadIdx.x; b < n_records; b += blockDim.x) {
-    const double * p = stage1 + static_cast<size_t>(b) * kStage1Doubles;
-    best_merge(best, p[0], p[1]);
+    if (direct) {
+      const double * p = stage1 + static_cast<size_t>(b) * NDT2D_BLOCK_PARTIAL;
+      best_merge(best, p[0], p[1]);
+      const double S = p[2], Sx = p[3], Sy = p[4], Sxx = p[5], Sxy = p[6], Syy = p[7], t = p[8];
+      acc[0] += Sxx;
+      acc[1] += Sxy;
+      acc[2] += t * Sx;
+      acc[3] += Syy;
+      acc[4] += t * Sy;
+      acc[5] += (t * t) * S;
+      acc[6] += Sx;
+      acc[7] += Sy;
+      acc[8] += t * S;
+      acc[9] += S;
+    } else {
+      const double * p = stage1 + static_cast<size_t>(b) * kStage1Doubles;
+      best_merge(best, p[0], p[1]);
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {acc[k] += p[2 + k];}
+      for (int k = 0; k < 10; ++k) {acc[k] += p[2 + k];}
+    }
   }
   __shared__ double folded[12];
   block_fold_12(best, acc, folded);
@@ -307,16 +333,26 @@ __global__ void __launch_bounds__(256) search_finish_kernel(
 
 // block_partials: n_blocks records of NDT2D_BLOCK_PARTIAL doubles, followed by room for
 // kReduceBlocks stage-1 records (ndt2d_search_scratch_doubles accounts for it).
+constexpr uint32_t kDirectFinishMax = 4096;   // job records one block folds without stage 1
+
 int launch_final(const double * d_block_partials, uint32_t n_blocks, double * d_stage1,
   const SearchView & sv, double n_candidates, double * d_partial32, cudaStream_t stream,
-  Counters * ctr, const ExchangeView * exchange)
+  Counters * ctr, const ExchangeView * exchange, uint32_t * d_counter)
 {
   ExchangeView xv{};
   if (exchange) {xv = *exchange;}
+  unsigned long long * counters = reinterpret_cast<unsigned long long *>(d_counter);
+  if (n_blocks <= kDirectFinishMax) {
+    search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_blocks, 1, sv, n_candidates,
+      d_partial32, xv, counters);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
   const uint32_t nb = min(kReduceBlocks, max(1u, (n_blocks + 255u) / 256u));
   search_reduce_kernel<<<nb, 256, 0, stream>>>(d_block_partials, n_blocks, d_stage1);
   NDT2D_LAUNCH_CHECK(ctr);
-  search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, sv, n_candidates, d_partial32, xv);
+  search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, 0, sv, n_candidates, d_partial32, xv,
+    counters);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
 }
@@ -418,7 +454,8 @@ int ndt2d_launch_search(
       // a rank without slices still takes part in the exchange: neutral record through
       // the same finish kernel (zero stage-1 records)
       ExchangeView xv = *exchange;
-      search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, 0, sv, 0.0, d_partial32, xv);
+      search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, 0, 1, sv, 0.0, d_partial32, xv,
+        nullptr);
       NDT2D_LAUNCH_CHECK(ctr);
       return NDT2D_OK;
     }
@@ -441,7 +478,7 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_jobs, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr, exchange);
+             n_candidates, d_partial32, stream, ctr, exchange, d_counter);
   }
   if (variant == 2) {
     uint32_t n_blocks = 0;
@@ -451,7 +488,7 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_blocks, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr, exchange);
+             n_candidates, d_partial32, stream, ctr, exchange, d_counter);
   }
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
@@ -468,7 +505,7 @@ int ndt2d_launch_search(
   }
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
-           n_candidates, d_partial32, stream, ctr, exchange);
+           n_candidates, d_partial32, stream, ctr, exchange, nullptr);
 }
 
 int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,

@@ -659,8 +659,9 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   // one persistent CTA per SM; small searches still spread over all SMs (the
   // warps of every CTA draw jobs from the same counter)
   pl.grid = min(pl.n_jobs * pl.P, static_cast<uint32_t>(sms));
-  // d_counter: [0] job counter (u32, + pad), [1..2] u64 statistics of this launch
-  NDT2D_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 32, stream));
+  // d_counter: [0] job counter (u32, + pad), [1..2] u64 statistics of this launch; zero on
+  // entry -- cleared at allocation and again by the finish kernel of every search, which
+  // first moves the statistics to [3..4] for ndt2d_matcher_search_stats
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
   if (PRE) {
     dim3 grid((sv.n_pts + 127u) / 128u, min(n_theta, 65535u));
@@ -720,7 +721,7 @@ size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_li
   // sized for the full theta range; a launch over a sub-range (other region plan)
   // uses the table only if its own needs fit (ndt2d_launch_search_region)
   const RegionPlan pl = make_plan(g, n_ang ? n_ang : 1, n_lin ? n_lin : 1, linear_res);
-  const size_t worst = pl.Q >= 2 ? coords_bytes(pl, n_ang ? n_ang : 1, n_pts) : 0;
+  const size_t worst = pl.Q >= 3 ? coords_bytes(pl, n_ang ? n_ang : 1, n_pts) : 0;
   return worst <= cap_bytes ? worst : 0;  // 0: the search computes coordinates per job
 }
 
@@ -747,7 +748,7 @@ int ndt2d_launch_search_region(
   *n_jobs = pl.n_jobs;
   plan_chunks(pl, sv.n_pts, sv.chunk_sums ? sv.chunk_cap_doubles : 0);
   // the pre-pass pays off when a slice has several regions per axis to share it
-  const bool pre = d_coords && pl.Q >= 2 && sv.n_pts > 0 &&
+  const bool pre = d_coords && pl.Q >= 3 && sv.n_pts > 0 &&
     coords_bytes(pl, n_theta, sv.n_pts) <= coords_cap_bytes;
 #define NDT2D_REGION_LAUNCH(S, P) \
   launch_one<S, P>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
