@@ -280,6 +280,49 @@ def test_search_parameter_sweep(o, case):
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_worlds(o, seed):
+    """Randomised worlds, poses (negative coordinates included), scan counts and matcher
+    parameters: build bit-exact, full score volume within 1e-5, same best pose."""
+    rng = np.random.default_rng(1000 + seed)
+    arena = float(rng.choice([12.0, 25.0, 60.0]))
+    rects = synth.world(seed=700 + seed, arena=arena, n_obstacles=int(rng.integers(3, 25)),
+                        side_min=0.3, side_max=3.0)
+    n_scans = int(rng.integers(1, 9))
+    beams = int(rng.choice([45, 180, 360, 720]))
+    rmax = float(rng.choice([3.5, 8.0, 20.0]))
+    centre = rng.uniform(0.2 * arena, 0.8 * arena, size=2)
+    poses = np.column_stack([centre[0] + rng.normal(0, 0.4, n_scans + 1), centre[1] + rng.normal(0, 0.4, n_scans + 1),
+                             rng.uniform(-np.pi, np.pi, n_scans + 1)])
+    offs, pts = synth.scans(rects, poses, beams, rmax, seed=900 + seed, noise_sigma=float(rng.choice([0.0, 0.01, 0.05])),
+                            arena=arena)
+    shift = rng.choice([0.0, -arena, -3.0 * arena])          # all-negative / mixed-sign coordinates
+    poses[:, :2] += shift
+    lres = float(rng.choice([0.01, 0.02, 0.05, 0.1]))
+    p = dict(ndt_resolution=float(rng.choice([0.1, 0.25, 0.5, 1.0])),
+             search_angular_resolution=float(rng.choice([0.002, 0.005, 0.02])),
+             search_angular_size=float(rng.choice([0.01, 0.05, 0.1])),
+             search_linear_resolution=lres, search_linear_size=lres * float(rng.choice([1.5, 4.0, 9.5])),
+             laser_max_beams=int(rng.choice([30, 100, 360, 1000])), range_max=rmax)
+    m = ScanMatcherNDT.from_params(p)
+    mo = o.new_matcher(p)
+    map_offs = offs[: n_scans + 1]
+    map_pts = pts[: int(offs[n_scans])]
+    m.add_scans_raw(poses[:n_scans], map_offs, map_pts)
+    mo.add_scans(poses[:n_scans], map_offs, map_pts)
+    assert m.grid_info() == mo.grid()
+    check_cells(m.dump_cells(), mo.dump_cells())
+    q = pts[int(offs[n_scans]):int(offs[n_scans + 1])]
+    guess = poses[n_scans] + np.array([0.5 * lres, -1.2 * lres, 0.004])
+    so, do, wo, co, scores_o = mo.match_scan(guess, q, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, q)
+    if scores_o.size == 0 or q.shape[0] == 0:
+        assert wg == wo
+        return
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, q), scores_o)
+    np.testing.assert_allclose(m.scorePoints(q, guess), mo.score_points(q, guess), rtol=RTOL, atol=ATOL_SCORE)
+
+
 def test_theta_sliced_search_matches_full(o):
     """Partial searches over theta ranges + one combine == the full search (the
     multi-GPU path, exercised on one device)."""
