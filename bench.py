@@ -196,10 +196,26 @@ def cpu_reference_other(out):
     w = synth.config2()
     m = lib.new_matcher(w.params)
     t_build = clock(lambda: m.add_scans(w.map_poses, w.map_offsets, w.map_points))
-    t_meas = clock(lambda: [m.score_points(w.scan_points, p) for p in w.particles[:500]]) * 10.0
-    out["config2_particle_filter"]["cpu_reference"] = {
-        "kind": kind, "cores": 1, "global_ndt_build_ms": t_build,
-        "measure_ms_5000_particles_extrapolated_from_500": t_meas}
+    out["config2_particle_filter"]["cpu_reference"] = {"kind": kind, "cores": 1, "global_ndt_build_ms": t_build}
+    if kind == "reference":
+        # the reference's own ParticleFilter: update + measure + resample, 5,000 particles
+        d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        alphas = np.full(5, 0.2)
+        P = w.particles.shape[0]
+        pf = lib.pf_create(w.min_particles, w.max_particles, d(alphas))
+        w0 = np.full(P, 1.0 / P)
+        lib.pf_set(pf, d(w.particles), d(w0), P)
+
+        out["config2_particle_filter"]["cpu_reference"]["measure_ms"] = clock(
+            lambda: lib.pf_measure(pf, m.h, d(w.scan_points), w.scan_points.shape[0]))
+
+        def ref_step():
+            lib.pf_update(pf, 0.05, 0.0, 0.01)
+            lib.pf_measure(pf, m.h, d(w.scan_points), w.scan_points.shape[0])
+            lib.pf_resample(pf, w.kld_err, w.kld_z)
+        out["config2_particle_filter"]["cpu_reference"]["update_measure_resample_ms"] = clock(ref_step)
+        out["config2_particle_filter"]["cpu_reference"]["particles_after_step"] = int(lib.pf_size(pf))
+        lib.pf_destroy(pf)
     g = B.OccupancyGrid(lib, 0.05, 0.25)
     out["occupancy_grid_config2_map"]["cpu_reference"] = {
         "kind": kind, "cores": 1, "getMsg_ms": clock(lambda: g.get_msg(w.map_poses, w.map_offsets, w.map_points))}
@@ -274,11 +290,22 @@ def other_workloads(torch, dev_index: int):
         f.measure(m, scan)
         f.resample(w.kld_err, w.kld_z, seed=9)
     t_res = timed(resample) - t_meas
+    # one localisation step with the particle set resident on the device, as the node runs it
+    # (ndt_mapper.cpp:473-475): update (motion model) + measure + resample
+    f.set_particles(w.particles, np.full(P, 1.0 / P))
+    seeds = iter(range(100, 100000))
+
+    def pf_step():
+        f.update(0.05, 0.0, 0.01, seed=next(seeds))
+        f.measure(m, scan)
+        f.resample(w.kld_err, w.kld_z, seed=next(seeds))
+    t_step = timed(pf_step, reps=20, warm=3)
     out["config2_particle_filter"] = {
         "particles": P, "beams": int(w.scan_points.shape[0]), "map_points": int(w.map_points.shape[0]),
         "global_ndt_build_ms": t_build * 1e3, "set_particles_plus_measure_ms": t_meas * 1e3,
         "resample_ms": max(t_res, 0.0) * 1e3, "particles_per_s": P / t_meas,
-        "resampled_size": f.size()}
+        "resampled_size": f.size(), "update_measure_resample_ms_device_resident": t_step * 1e3,
+        "particles_after_steps": f.size()}
     f.close()
     m.close()
     # occupancy-grid export of the config-2 map: 2,500 scans, 704k rays
