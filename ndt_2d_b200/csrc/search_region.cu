@@ -65,7 +65,7 @@ constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
 // per warp: double totals, xs[32], ys[32], float block sums (16-byte rounded)
 constexpr uint32_t kWarpSmemBytes =
   ((kAccEntries * static_cast<uint32_t>(sizeof(total_t)) + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
-constexpr size_t kSmemTabBudget = 32 * 1024;    // D + thresholds in shared memory up to this
+constexpr size_t kSmemTabBudget = 64 * 1024;    // D + thresholds in shared memory up to this
 constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight

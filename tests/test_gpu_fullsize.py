@@ -67,6 +67,39 @@ def test_config2_full_filter(o):
     assert np.array_equal(f.get_particles()[0], po)
 
 
+# ------------------------------------------------------------------ localisation against a global map
+@pytest.mark.parametrize("which", ["config2_map", "config5_map"])
+def test_match_scan_against_global_map(o, which):
+    """Scan-matching localisation (ndt_mapper.cpp:547-566): matchScan against the NDT of the whole
+    map.  config 2's map (473 x 473 cells) still stages its bitmap / thresholds in shared memory,
+    config 5's (1200 x 1200 cells, 0.1 m) does not fit and takes the global-memory path."""
+    if which == "config2_map":
+        w = synth.config2()
+        poses, offs, pts, params = w.map_poses, w.map_offsets, w.map_points, dict(w.params)
+        params.update(laser_max_beams=100)
+        query_pose, query_pts = w.true_pose, w.scan_points
+    else:
+        w = synth.config5(n_scans=6000)
+        poses, offs, pts, params = w.poses, w.offsets, w.points, dict(w.params)
+        params.update(search_linear_resolution=0.02, search_linear_size=0.2, laser_max_beams=180)
+        k = 1234
+        query_pose, query_pts = poses[k], pts[int(offs[k]):int(offs[k + 1])]
+    m = ScanMatcherNDT.from_params(params)
+    mo = o.new_matcher(params)
+    m.add_scans_raw(poses, offs, pts)
+    mo.add_scans(poses, offs, pts)
+    assert m.grid_info() == mo.grid()
+    guess = query_pose - np.array([0.02, -0.015, 0.03])
+    so, do, wo, co, scores_o = mo.match_scan(guess, query_pts, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, query_pts)
+    sc = m.dump_scores(guess, query_pts)
+    assert sc.shape == scores_o.shape
+    np.testing.assert_allclose(sc, scores_o, rtol=RTOL, atol=ATOL_SCORE)
+    assert wg == wo and np.array_equal(dg, do)
+    np.testing.assert_allclose(sg, so, rtol=RTOL)
+    np.testing.assert_allclose(cg, co, rtol=RTOL, atol=RTOL * np.abs(co).max())
+
+
 # ------------------------------------------------------------------ config 3: 50 loop-closure jobs
 def test_config3_full_batch(o):
     w = synth.config3()
