@@ -66,6 +66,7 @@ constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
 constexpr uint32_t kWarpSmemBytes =
   ((kAccEntries * static_cast<uint32_t>(sizeof(total_t)) + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
 constexpr size_t kSmemTabBudget = 64 * 1024;    // D + thresholds in shared memory up to this
+constexpr uint32_t kBatchSlotBytes = 320;        // per-warp BatchEntry slot of the batch kernel (>= sizeof)
 constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight
@@ -368,26 +369,26 @@ search_region_kernel(
   unsigned long long n_useful = 0, n_items = 0;  // warp-uniform tallies (lane 0 reports)
 
   // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc_d / xs / ys / acc_f]
-  const uint32_t * occd;
-  const double * thr_x;
-  const double * thr_y;
+  const uint32_t * occd_tab;
+  const double * thr_x_tab;
+  const double * thr_y_tab;
   unsigned char * sp = smem_raw + 16;
   if (SMEM_TAB) {
-    occd = reinterpret_cast<const uint32_t *>(sp);
+    occd_tab = reinterpret_cast<const uint32_t *>(sp);
     sp += tab_d_bytes;
-    thr_x = reinterpret_cast<const double *>(sp);
-    thr_y = thr_x + (mv.g.size_x + 2);
+    thr_x_tab = reinterpret_cast<const double *>(sp);
+    thr_y_tab = thr_x_tab + (mv.g.size_x + 2);
     sp += tab_thr_bytes;
     if (threadIdx.x == 0) {
       mbar_init(mbar, 1);
       mbar_expect_tx(mbar, tab_d_bytes + tab_thr_bytes);
-      bulk_copy_g2s(const_cast<uint32_t *>(occd), mv.occ_dilated, tab_d_bytes, mbar);
-      bulk_copy_g2s(const_cast<double *>(thr_x), mv.thr_x, tab_thr_bytes, mbar);
+      bulk_copy_g2s(const_cast<uint32_t *>(occd_tab), mv.occ_dilated, tab_d_bytes, mbar);
+      bulk_copy_g2s(const_cast<double *>(thr_x_tab), mv.thr_x, tab_thr_bytes, mbar);
     }
   } else {
-    occd = mv.occ_dilated;
-    thr_x = mv.thr_x;
-    thr_y = mv.thr_y;
+    occd_tab = mv.occ_dilated;
+    thr_x_tab = mv.thr_x;
+    thr_y_tab = mv.thr_y;
   }
   // per warp: xs[32], ys[32] (double), totals, float block sums
   double * xs = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
@@ -395,195 +396,90 @@ search_region_kernel(
   total_t * acc_d = reinterpret_cast<total_t *>(ys + 32);
   float * acc_f = reinterpret_cast<float *>(acc_d + kAccEntries);
 
-  const uint32_t n_lin = sv.n_lin;
-  const uint32_t pitch = mv.g.pitch;
-  const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y;
-  const double inv_cell = 1.0 / mv.g.cell_size;
-  const double origin_x = mv.g.origin_x, origin_y = mv.g.origin_y;
-  const uint32_t QQ = Q * Q;
-  const uint32_t RR = Rw * Rw;
-
   if (SMEM_TAB) {
     __syncthreads();       // mbarrier initialised before anyone polls it
     mbar_wait(mbar, 0);
   }
 
-  for (;;) {
-    uint32_t job = 0;
-    if (lane == 0) {job = atomicAdd(job_counter, 1u);}
-    job = __shfl_sync(0xffffffffu, job, 0);
-    if (job >= n_jobs * P) {break;}
-    // with P > 1 the counter enumerates (job, point chunk) pairs, chunks of a job adjacent
-    const uint32_t work = job;
-    uint32_t chunk = 0;
-    if (P > 1) {
-      chunk = work % P;
-      job = work / P;
-    }
-    const uint32_t p_begin = chunk * chunk_points;
-    const uint32_t p_end = (P > 1) ? min(sv.n_pts, p_begin + chunk_points) : sv.n_pts;
-    const uint32_t it = job / QQ, rr = job - it * QQ;
-    const uint32_t rx = rr / Q, ry = rr - rx * Q;
-    const uint32_t itheta = theta_begin + it * sv.theta_stride;
-    const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
-    const uint32_t nxc = min(Rw, n_lin - jx0), nyc = min(Rw, n_lin - jy0);  // columns / rows
-    const double2 cs = sv.trig[itheta];
-    const double my_dlx = sv.dlin[jx0 + min(lane, nxc - 1u)];
-    const double my_dly = sv.dlin[jy0 + min(lane, nyc - 1u)];
-    const double dlx0 = __shfl_sync(0xffffffffu, my_dlx, 0);
-    const double dly0 = __shfl_sync(0xffffffffu, my_dly, 0);
-    const uint16_t * cx_tab = nullptr;
-    const uint16_t * cy_tab = nullptr;
-    if (PRE) {
-      cx_tab = coords + (static_cast<size_t>(it) * 2 * Q + rx) * n_pts_pad;
-      cy_tab = coords + (static_cast<size_t>(it) * 2 * Q + Q + ry) * n_pts_pad;
-    }
+#define MV mv
+#define SV sv
+#define NDT2D_BODY_BATCH 0
+#define NDT2D_BODY_TOTAL_WORK (n_jobs * P)
+#define NDT2D_BODY_OCCD occd_tab
+#define NDT2D_BODY_THRX thr_x_tab
+#define NDT2D_BODY_THRY thr_y_tab
+#define NDT2D_BODY_JOBP job_partials
+#define NDT2D_BODY_CHUNKS chunk_sums
+#include "search_region_body.inc"
+#undef MV
+#undef SV
+#undef NDT2D_BODY_BATCH
+#undef NDT2D_BODY_TOTAL_WORK
+#undef NDT2D_BODY_OCCD
+#undef NDT2D_BODY_THRX
+#undef NDT2D_BODY_THRY
+#undef NDT2D_BODY_JOBP
+#undef NDT2D_BODY_CHUNKS
+}
 
-    for (uint32_t k = lane; k < RR; k += 32) {
-      acc_d[k] = static_cast<total_t>(0);
-      acc_f[k] = 0.0f;
-    }
-    __syncwarp();
+// One search of a batch (ndt2d_matcher_match_scan_batch): its own model, scan and outputs.
+struct BatchEntry
+{
+  ModelView mv;
+  SearchView sv;
+  double * job_partials;   // n_jobs records of NDT2D_BLOCK_PARTIAL doubles
+  double * chunk_sums;     // n_jobs * P * Rw^2 doubles (P > 1)
+};
 
-    uint32_t dirty_steps = 0;  // steps with hits since the last flush
-    uint32_t job_useful = 0;
-    for (uint32_t p0 = p_begin; p0 < p_end; p0 += 32) {
-      const uint32_t i = p0 + lane;
-      double ox = 0.0, oy = 0.0;
-      uint32_t pcx = 0, pcy = 0;
-      bool hit = false;
-      if (PRE) {
-        // coordinates of the region's first column / row from the pre-pass table
-        if (i < p_end) {
-          pcx = cx_tab[i];
-          pcy = cy_tab[i];
-          const uint32_t idx = pcy * pitch + pcx;
-          hit = ((occd[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
-        }
-        if (hit) {
-          const double2 p = sv.pts[i];
-          ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
-          oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-        }
-      } else if (i < p_end) {
-        const double2 p = sv.pts[i];
-        // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
-        ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
-        oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-        pcx = padded_coord<SMEM_TAB>(__dadd_rn(ox, dlx0), thr_x, size_x, origin_x, inv_cell);
-        pcy = padded_coord<SMEM_TAB>(__dadd_rn(oy, dly0), thr_y, size_y, origin_y, inv_cell);
-        const uint32_t idx = pcy * pitch + pcx;
-        hit = ((occd[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      if (mask) {++dirty_steps;}
-      while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        ++n_items;
-        // ---- item: scan point (p0 + src) against this region
-        const double pox = __shfl_sync(0xffffffffu, ox, src);
-        const double poy = __shfl_sync(0xffffffffu, oy, src);
-        const uint32_t bx = __shfl_sync(0xffffffffu, pcx, src);
-        const uint32_t by = __shfl_sync(0xffffffffu, pcy, src);
-        // exact candidate coordinates (scan_matcher_ndt.cpp:123-124), lane = column / row
-        const double xa = __dadd_rn(pox, my_dlx), ya = __dadd_rn(poy, my_dly);
-        // columns / rows still in the first cell: below the next threshold
-        // (thr[size + 1] = +inf: beyond the grid nothing crosses)
-        const bool in_x0 = xa < thr_x[bx];
-        const bool in_y0 = ya < thr_y[by];
-        const uint32_t nx = __popc(__ballot_sync(0xffffffffu, lane < nxc && in_x0));
-        const uint32_t ny = __popc(__ballot_sync(0xffffffffu, lane < nyc && in_y0));
-        xs[lane] = xa;
-        ys[lane] = ya;
-        // the 2 x 2 cells are probed by lanes 0..3 in parallel: occupancy + record rank
-        bool occ_l = false;
-        uint32_t rank_l = 0;
-        {
-          const uint32_t pvx = lane & 1u, pvy = (lane >> 1) & 1u;
-          const uint32_t w_l = pvx ? nxc - nx : nx, h_l = pvy ? nyc - ny : ny;
-          if (lane < 4u && w_l != 0u && h_l != 0u) {
-            const uint32_t cidx = by * pitch + bx + pvx + pvy * pitch;
-            const uint2 ow = __ldg(mv.occ + (cidx >> 5));
-            const uint32_t bit = cidx & 31u;
-            occ_l = ((ow.x >> bit) & 1u) != 0u;
-            rank_l = ow.y + __popc(ow.x & ((1u << bit) - 1u));
-          }
-        }
-        const uint32_t cmask0 = __ballot_sync(0xffffffffu, occ_l);
-        __syncwarp();  // xs / ys visible to every lane
-        uint32_t cmask = cmask0;
-        while (cmask) {
-          const uint32_t v = __ffs(cmask) - 1;
-          cmask &= cmask - 1u;
-          const uint32_t rank = __shfl_sync(0xffffffffu, rank_l, v);
-          const uint32_t vx = v & 1u, vy = v >> 1;
-          const uint32_t cx0 = vx ? nx : 0u, w = vx ? nxc - nx : nx;
-          const uint32_t cy0 = vy ? ny : 0u, h = vy ? nyc - ny : ny;
-          job_useful += w * h;
-          const double2 * f2 = reinterpret_cast<const double2 *>(
-            mv.rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
-          const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
-          if (Ds.y == 0.0) {
-            // orientation with fewer rounds (table lookup)
-            if (kTab.colmode[h][w]) {
-              eval_cell<true>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
-            } else {
-              eval_cell<false>(acc_f, xs, ys, Rw, cx0, w, cy0, h, mean, AB, Ds.x, lane);
-            }
-          } else {
-            // ---- stiff cell (a cluster of near-identical points: |I| ~ 1e17, or
-            // inf / NaN): the reference's own grouping ((q^T I) q,
-            // ndt_model.cpp:113-114) and no FMA, so that it cancels exactly where
-            // the reference cancels.
-            const double2 * r2 = reinterpret_cast<const double2 *>(
-              mv.rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
-            const double2 i0010 = __ldg(r2 + 1), i0111 = __ldg(r2 + 2);
-            const uint32_t cnt = w * h;
-            const uint32_t inv_h = kTab.inv[h];
-            for (uint32_t k = lane; k < cnt; k += 32) {
-              const uint32_t ar = (k * inv_h) >> 16;
-              const uint32_t a = cx0 + ar, b = cy0 + (k - ar * h);
-              const double qx = __dsub_rn(xs[a], mean.x), qy = __dsub_rn(ys[b], mean.y);
-              const double r0 = __dadd_rn(__dmul_rn(qx, i0010.x), __dmul_rn(qy, i0010.y));
-              const double r1 = __dadd_rn(__dmul_rn(qx, i0111.x), __dmul_rn(qy, i0111.y));
-              const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
-              acc_f[a * Rw + b] += exp2f(static_cast<float>(e * kLog2e));
-            }
-          }
-        }
-        __syncwarp();
-      }
-      // float block sums go to the double totals every kFlushSteps steps with hits:
-      // a block sum stays below 32 * kFlushSteps = 128, so its rounding stays ~1e-8 of a score
-      if (dirty_steps == kFlushSteps) {
-        flush_block(acc_d, acc_f, RR, lane);
-        dirty_steps = 0;
-        __syncwarp();
-      }
-    }
-    if (dirty_steps) {
-      flush_block(acc_d, acc_f, RR, lane);
-      __syncwarp();
-    }
+static_assert(sizeof(BatchEntry) <= kBatchSlotBytes && sizeof(BatchEntry) % 4 == 0, "batch slot size");
 
-    n_useful += job_useful;
+// The same job loop over SEVERAL searches in one launch: the job counter enumerates
+// (search, job, chunk) triples, a warp copies the descriptor of the search it is working for
+// into a shared-memory slot.  Tables are read through L1 (they differ per search), there is
+// no coordinate pre-pass.  All searches share the lattice (theta_begin = 0, stride 1).
+__global__ void __launch_bounds__(kWarps * 32, 1)
+search_region_batch_kernel(
+  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
+  uint32_t P, uint32_t chunk_points, uint32_t * __restrict__ job_counter,
+  unsigned long long * __restrict__ stats)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned long long n_useful = 0, n_items = 0;
+  unsigned char * sp = smem_raw + static_cast<size_t>(warp) * (kWarpSmemBytes + kBatchSlotBytes);
+  double * xs = reinterpret_cast<double *>(sp);
+  double * ys = xs + 32;
+  total_t * acc_d = reinterpret_cast<total_t *>(ys + 32);
+  float * acc_f = reinterpret_cast<float *>(acc_d + kAccEntries);
+  BatchEntry * slot = reinterpret_cast<BatchEntry *>(sp + kWarpSmemBytes);
+  uint32_t cur_search = 0xffffffffu;
+  constexpr bool PRE = false, SMEM_TAB = false;
+  const uint32_t theta_begin = 0;
+  double * const scores = nullptr;
+  const uint16_t * const coords = nullptr;
+  const uint32_t n_pts_pad = 0;
+  (void)coords;
+  (void)n_pts_pad;
 
-    // ---- epilogue
-    if (P > 1) {
-      // this chunk's sums; region_chunk_reduce_kernel adds the chunks and finishes the job
-      double * out = chunk_sums + static_cast<size_t>(work) * RR;
-      for (uint32_t k = lane; k < RR; k += 32) {out[k] = total_value(acc_d, acc_f, k);}
-    } else {
-      job_epilogue([acc_d, acc_f](uint32_t k) {return total_value(acc_d, acc_f, k);}, sv, job,
-        itheta, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
-    }
-    __syncwarp();
-  }
-  if (lane == 0 && stats) {
-    atomicAdd(stats, n_useful);      // (candidate, point) evaluations that reached an occupied cell
-    atomicAdd(stats + 1, n_items);   // (point, region) pairs that passed the dilated-bitmap test
-  }
+#define MV (slot->mv)
+#define SV (slot->sv)
+#define NDT2D_BODY_BATCH 1
+#define NDT2D_BODY_TOTAL_WORK (n_batch * n_jobs * P)
+#define NDT2D_BODY_OCCD (slot->mv.occ_dilated)
+#define NDT2D_BODY_THRX (slot->mv.thr_x)
+#define NDT2D_BODY_THRY (slot->mv.thr_y)
+#define NDT2D_BODY_JOBP (slot->job_partials)
+#define NDT2D_BODY_CHUNKS (slot->chunk_sums)
+#include "search_region_body.inc"
+#undef MV
+#undef SV
+#undef NDT2D_BODY_BATCH
+#undef NDT2D_BODY_TOTAL_WORK
+#undef NDT2D_BODY_OCCD
+#undef NDT2D_BODY_THRX
+#undef NDT2D_BODY_THRY
+#undef NDT2D_BODY_JOBP
+#undef NDT2D_BODY_CHUNKS
 }
 
 RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res)
