@@ -266,9 +266,17 @@ def other_workloads(torch, dev_index: int):
             return m.match_scan_raw(w.query_pose, w.query_points)
         t_triple = timed(triple)
         t_match = timed(lambda: m.match_scan_raw(w.query_pose, w.query_points))
+        # latency distribution over 200 calls after warm-up
+        lat = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            m.match_scan_raw(w.query_pose, w.query_points)
+            lat.append((time.perf_counter() - t0) * 1e3)
         na, nl = m.search_shape()
         out[f"config1_local_match_beams{beams}"] = {
             "candidates": na * nl * nl, "matchScan_ms": t_match * 1e3,
+            "matchScan_latency_ms_p50": float(np.percentile(lat, 50)),
+            "matchScan_latency_ms_p99": float(np.percentile(lat, 99)), "latency_calls": len(lat),
             "reset_addScans_scoreScan_matchScan_ms": t_triple * 1e3,
             "candidates_per_s": na * nl * nl / t_match}
         m.close()
@@ -426,7 +434,8 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     c1 = m.counters()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = sum(step_ms)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -506,6 +515,8 @@ def run_ours(args):
                            if world > 1 else "single GPU",
             "l2_flush": "256 MiB memset between steps, outside the per-step CUDA event pairs",
             "matchScan_latency_ms": ms_per_step,
+            "matchScan_latency_ms_p50_p99_rank0": [float(np.percentile(step_ms, 50)),
+                                                   float(np.percentile(step_ms, 99))],
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
