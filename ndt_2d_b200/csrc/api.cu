@@ -201,7 +201,7 @@ struct ndt2d_matcher
   std::vector<ndt2d_matcher *> lanes;   // sub-handles of match_scan_batch (created on first use)
   PinnedBuffer h_arena;
   size_t arena_off = 0;
-  DeviceBuffer d_batch_results;
+  DeviceBuffer d_batch_results, d_batch_arena;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the last search kernel
   bool ev_valid = false;
   cudaEvent_t evb_begin = nullptr, evb_end = nullptr;  // bracket the kernels of the last build
@@ -287,12 +287,10 @@ void subsample_points(const double * pts_xy, size_t npts, size_t n_use, double *
   }
 }
 
-int add_scans_locked(
-  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
-  const double * pts_xy)
+// Bounding box of the scan poses +- range_max (scan_matcher_ndt.cpp:53-64; max_* start at
+// DBL_MIN > 0) and the grid NDT::NDT makes of it (ndt_model.cpp:118-126).
+int grid_from_poses(const ndt2d_matcher * m, size_t n_scans, const double * poses, GridDesc * out)
 {
-  m->has_model = false;  // (a staged scan stays valid across rebuilds)
-  // bounding box (scan_matcher_ndt.cpp:53-64); max_* start at DBL_MIN (> 0)
   double min_x = DBL_MAX, max_x = DBL_MIN, min_y = DBL_MAX, max_y = DBL_MIN;
   for (size_t k = 0; k < n_scans; ++k) {
     const double * pose = poses + 3 * k;
@@ -323,6 +321,21 @@ int add_scans_locked(
   g.n_cells = static_cast<uint32_t>(n_cells64);
   g.n_padded = static_cast<uint32_t>(n_padded64);
   g.n_words = (g.n_padded + 31) / 32;
+  *out = g;
+  return NDT2D_OK;
+}
+
+int add_scans_locked(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy)
+{
+  m->has_model = false;  // (a staged scan stays valid across rebuilds)
+  GridDesc g;
+  {
+    const int grc = grid_from_poses(m, n_scans, poses, &g);
+    if (grc) {return grc;}
+  }
+  const uint64_t n_cells64 = static_cast<uint64_t>(g.size_x) * g.size_y;
 
   const size_t n_points = n_scans ? static_cast<size_t>(pt_offsets[n_scans] - pt_offsets[0]) : 0;
   if (n_points >= (1ull << 32) - 1) {return NDT2D_ERR_SIZE;}
@@ -732,7 +745,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
       &m->d_sx, &m->d_sy, &m->d_heads, &m->d_nheads, &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
-      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results};
+      &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results, &m->d_batch_arena};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
     m->h_result.release();
@@ -846,6 +859,193 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
 
 }  // extern "C"
 
+// match_scan_batch as THREE launches (all models built by one grid of single-CTA builds,
+// all searches by one persistent search kernel, all final reductions by one grid of
+// blocks), one H2D copy of a packed staging area and one D2H copy of the results.
+// Returns kBatchNotEligible when a job does not fit the small-model build or the plan
+// (the caller then pipelines the jobs over the lanes instead).
+constexpr int kBatchNotEligible = -1;
+
+static int match_scan_batch_fused(
+  ndt2d_matcher * m, size_t n_jobs,
+  const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
+  const double * map_pts_xy,
+  const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  if (m->prm.kernel_variant != 0 || n_jobs == 0 || n_jobs > 4096) {return kBatchNotEligible;}
+  const size_t n_ang = m->dth.size(), n_lin = m->dlin.size();
+  if (n_ang == 0 || n_lin == 0) {return kBatchNotEligible;}
+  struct Job
+  {
+    GridDesc g;
+    size_t n_scans, n_points, n_use, npts_q, rec_cap;
+    uint64_t s0, p0, q0;
+    size_t o_tf, o_off, o_pts, o_thr, o_q, o_trig;                       // upload region
+    size_t o_occ, o_occd, o_rec, o_recf, o_nvalid, o_jobp, o_chunk;      // device-only region
+  };
+  std::vector<Job> jobs(n_jobs);
+  uint32_t max_use = 0;
+  for (size_t j = 0; j < n_jobs; ++j) {
+    Job & J = jobs[j];
+    J.s0 = job_scan_offsets[j];
+    J.n_scans = static_cast<size_t>(job_scan_offsets[j + 1] - J.s0);
+    if (J.n_scans == 0) {return kBatchNotEligible;}
+    const int grc = grid_from_poses(m, J.n_scans, map_poses + 3 * J.s0, &J.g);
+    if (grc) {return kBatchNotEligible;}
+    J.p0 = map_pt_offsets[J.s0];
+    J.n_points = static_cast<size_t>(map_pt_offsets[J.s0 + J.n_scans] - J.p0);
+    if (!ndt2d_build_is_small(J.g, J.n_points)) {return kBatchNotEligible;}
+    J.q0 = query_pt_offsets[j];
+    J.npts_q = static_cast<size_t>(query_pt_offsets[j + 1] - J.q0);
+    J.n_use = subsample_count(m, J.npts_q);
+    if (J.n_use == 0 || J.n_use >= (1u << 20)) {return kBatchNotEligible;}
+    max_use = std::max<uint32_t>(max_use, static_cast<uint32_t>(J.n_use));
+    J.rec_cap = std::min<uint64_t>(static_cast<uint64_t>(J.g.size_x) * J.g.size_y, J.n_points / 5) + 1;
+  }
+  RegionBatchPlan pl;
+  ndt2d_region_batch_plan(m->prm.ndt_resolution, static_cast<uint32_t>(n_ang),
+    static_cast<uint32_t>(n_lin), m->prm.search_linear_resolution, max_use, &pl);
+  if (pl.n_jobs == 0 || pl.n_jobs > 4096) {return kBatchNotEligible;}
+  // ---- layout: [upload region][device-only region], everything 256-byte aligned
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+      const size_t o = off;
+      off += (bytes + 255) & ~size_t(255);
+      return o;
+    };
+  const size_t o_counter = take(64);
+  const size_t o_build = take(n_jobs * sizeof(BuildEntry));
+  const size_t o_batch = take(n_jobs * sizeof(BatchEntry));
+  for (Job & J : jobs) {
+    J.o_tf = take(J.n_scans * sizeof(double4));
+    J.o_off = take((J.n_scans + 1) * sizeof(uint64_t));
+    J.o_pts = take(J.n_points * sizeof(double2));
+    J.o_thr = take((static_cast<size_t>(J.g.size_x) + J.g.size_y + 4) * sizeof(double));
+    J.o_q = take(J.n_use * sizeof(double2));
+    J.o_trig = take(n_ang * sizeof(double2));
+  }
+  const size_t upload_bytes = off;
+  for (Job & J : jobs) {
+    J.o_occ = take((static_cast<size_t>(J.g.n_words) + 4) * sizeof(uint2));
+    J.o_occd = take((static_cast<size_t>(J.g.n_words) + 4) * sizeof(uint32_t));
+    J.o_rec = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
+    J.o_recf = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
+    J.o_nvalid = take(sizeof(uint32_t));
+    J.o_jobp = take(static_cast<size_t>(pl.n_jobs) * NDT2D_BLOCK_PARTIAL * sizeof(double));
+    J.o_chunk = take(pl.chunk_doubles ? pl.chunk_doubles * sizeof(double) : 8);
+  }
+  const size_t o_results = take(n_jobs * 32 * sizeof(double));
+  const size_t total_bytes = off;
+  if (total_bytes > (size_t(2) << 30)) {return kBatchNotEligible;}
+  int rc = m->d_batch_arena.ensure(total_bytes);
+  if (!rc) {rc = m->h_arena.ensure(upload_bytes);}
+  if (!rc) {rc = m->h_result.ensure(std::max<size_t>(n_jobs * 32, 64) * sizeof(double));}
+  if (rc) {return rc;}
+  char * hb = m->h_arena.as<char>();
+  char * db = m->d_batch_arena.as<char>();
+  memset(hb + o_counter, 0, 64);
+  BuildEntry * h_build = reinterpret_cast<BuildEntry *>(hb + o_build);
+  BatchEntry * h_batch = reinterpret_cast<BatchEntry *>(hb + o_batch);
+  std::vector<double> thr_x, thr_y;
+  for (size_t j = 0; j < n_jobs; ++j) {
+    const Job & J = jobs[j];
+    // map side (as add_scans_locked)
+    double4 * h_tf = reinterpret_cast<double4 *>(hb + J.o_tf);
+    uint64_t * h_off = reinterpret_cast<uint64_t *>(hb + J.o_off);
+    for (size_t k = 0; k < J.n_scans; ++k) {
+      const double * pose = map_poses + 3 * (J.s0 + k);
+      h_tf[k] = make_double4(pose[0], pose[1], cos(pose[2]), sin(pose[2]));
+      h_off[k] = map_pt_offsets[J.s0 + k] - J.p0;
+    }
+    h_off[J.n_scans] = J.n_points;
+    memcpy(hb + J.o_pts, map_pts_xy + 2 * J.p0, J.n_points * sizeof(double2));
+    axis_thresholds(J.g.origin_x, J.g.cell_size, J.g.size_x, thr_x);
+    axis_thresholds(J.g.origin_y, J.g.cell_size, J.g.size_y, thr_y);
+    double * h_thr = reinterpret_cast<double *>(hb + J.o_thr);
+    memcpy(h_thr, thr_x.data(), thr_x.size() * sizeof(double));
+    memcpy(h_thr + thr_x.size(), thr_y.data(), thr_y.size() * sizeof(double));
+    // query side (as stage_scan_locked)
+    const double * pose3 = query_poses + 3 * j;
+    subsample_points(query_pts_xy + 2 * J.q0, J.npts_q, J.n_use, reinterpret_cast<double *>(hb + J.o_q));
+    double * h_trig = reinterpret_cast<double *>(hb + J.o_trig);
+    for (size_t k = 0; k < n_ang; ++k) {
+      h_trig[2 * k] = cos(pose3[2] + m->dth[k]);
+      h_trig[2 * k + 1] = sin(pose3[2] + m->dth[k]);
+    }
+    BuildEntry & be = h_build[j];
+    memset(&be, 0, sizeof(be));
+    be.g = J.g;
+    be.scan_tf = reinterpret_cast<const double4 *>(db + J.o_tf);
+    be.offsets = reinterpret_cast<const uint64_t *>(db + J.o_off);
+    be.pts = reinterpret_cast<const double2 *>(db + J.o_pts);
+    be.occ = reinterpret_cast<uint2 *>(db + J.o_occ);
+    be.occd = reinterpret_cast<uint32_t *>(db + J.o_occd);
+    be.rec = reinterpret_cast<double *>(db + J.o_rec);
+    be.rec_fast = reinterpret_cast<double *>(db + J.o_recf);
+    be.n_valid = reinterpret_cast<uint32_t *>(db + J.o_nvalid);
+    be.n_scans = static_cast<uint32_t>(J.n_scans);
+    be.n_points = static_cast<uint32_t>(J.n_points);
+    be.rec_cap = static_cast<uint32_t>(J.rec_cap);
+    BatchEntry & se = h_batch[j];
+    memset(&se, 0, sizeof(se));
+    se.mv.g = J.g;
+    se.mv.occ = be.occ;
+    se.mv.occ_dilated = be.occd;
+    se.mv.rec = be.rec;
+    se.mv.rec_fast = be.rec_fast;
+    se.mv.thr_x = reinterpret_cast<const double *>(db + J.o_thr);
+    se.mv.thr_y = se.mv.thr_x + (J.g.size_x + 2);
+    se.mv.n_valid_cap = static_cast<uint32_t>(J.rec_cap);
+    se.sv.pts = reinterpret_cast<const double2 *>(db + J.o_q);
+    se.sv.trig = reinterpret_cast<const double2 *>(db + J.o_trig);
+    se.sv.dth = m->d_dth.as<double>();
+    se.sv.dlin = m->d_dlin.as<double>();
+    se.sv.pose_x = pose3[0];
+    se.sv.pose_y = pose3[1];
+    se.sv.linear_res = m->prm.search_linear_resolution;
+    se.sv.n_pts = static_cast<uint32_t>(J.n_use);
+    se.sv.n_ang = static_cast<uint32_t>(n_ang);
+    se.sv.n_lin = static_cast<uint32_t>(n_lin);
+    se.sv.theta_stride = 1;
+    se.job_partials = reinterpret_cast<double *>(db + J.o_jobp);
+    se.chunk_sums = reinterpret_cast<double *>(db + J.o_chunk);
+  }
+  cudaStream_t st = m->stream;
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
+  m->ctr.h2d_bytes += upload_bytes;
+  rc = ndt2d_launch_build_small_batch(reinterpret_cast<const BuildEntry *>(db + o_build),
+      static_cast<uint32_t>(n_jobs), st, &m->ctr);
+  if (!rc) {
+    rc = ndt2d_launch_search_region_batch(reinterpret_cast<const BatchEntry *>(db + o_batch),
+        static_cast<uint32_t>(n_jobs), pl, reinterpret_cast<uint32_t *>(db + o_counter), st, &m->ctr);
+  }
+  if (!rc) {
+    rc = ndt2d_launch_finish_batch(reinterpret_cast<const BatchEntry *>(db + o_batch),
+        static_cast<uint32_t>(n_jobs), pl.n_jobs, static_cast<double>(n_ang) * n_lin * n_lin,
+        reinterpret_cast<double *>(db + o_results), reinterpret_cast<uint32_t *>(db + o_counter), st,
+        &m->ctr);
+  }
+  m->has_model = false;
+  m->staged = false;
+  m->ev_valid = false;
+  if (rc) {
+    cudaStreamSynchronize(st);
+    return rc;
+  }
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->h_result.p, db + o_results, n_jobs * 32 * sizeof(double),
+    cudaMemcpyDeviceToHost, st));
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
+  m->ctr.d2h_bytes += n_jobs * 32 * sizeof(double);
+  for (size_t j = 0; j < n_jobs; ++j) {
+    if (delta_written) {delta_written[j] = 0;}
+    unpack_result(m->h_result.as<double>() + 32 * j, out_delta3 ? out_delta3 + 3 * j : nullptr,
+      delta_written ? delta_written + j : nullptr, out_cov9 ? out_cov9 + 9 * j : nullptr,
+      out_score ? out_score + j : nullptr);
+  }
+  return NDT2D_OK;
+}
+
 static int match_scan_batch_locked(
   ndt2d_matcher * m, size_t n_jobs,
   const uint64_t * job_scan_offsets, const double * map_poses, const uint64_t * map_pt_offsets,
@@ -857,7 +1057,13 @@ static int match_scan_batch_locked(
     m->has_model = false;
     return NDT2D_OK;
   }
-  // Pipelined over kBatchLanes internal sub-handles (own stream, own model + scratch
+  {
+    const int frc = match_scan_batch_fused(m, n_jobs, job_scan_offsets, map_poses, map_pt_offsets,
+        map_pts_xy, query_poses, query_pt_offsets, query_pts_xy, out_delta3, delta_written, out_cov9,
+        out_score);
+    if (frc != kBatchNotEligible) {return frc;}
+  }
+  // Jobs too large for the single-launch path: pipelined over kBatchLanes internal sub-handles (own stream, own model + scratch
   // buffers): job j's build + search is enqueued on lane j % kBatchLanes without waiting
   // for the device (host staging from that lane's pinned arena), so the dependent chains
   // of small kernels of different jobs overlap; every lane collects its 32-double result

@@ -600,16 +600,23 @@ __device__ __forceinline__ uint32_t small_bits_at(const uint32_t * occw, uint32_
   return __funnelshift_r(lo, hi, sh);
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(
-  GridDesc g, const double4 * __restrict__ scan_tf, const uint64_t * __restrict__ offsets,
-  uint32_t n_scans, const double2 * __restrict__ pts, uint32_t n_points,
-  uint32_t * __restrict__ key_out, uint32_t * __restrict__ val_out, uint32_t * __restrict__ seglen,
-  double * __restrict__ sx, double * __restrict__ sy, uint2 * __restrict__ occ,
-  uint32_t * __restrict__ occ_dilated, double * __restrict__ rec, double * __restrict__ rec_fast,
-  uint32_t rec_cap, uint32_t * __restrict__ n_valid)
+__device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem & sm)
 {
-  extern __shared__ __align__(16) unsigned char small_raw[];
-  SmallSmem & sm = *reinterpret_cast<SmallSmem *>(small_raw);
+  const GridDesc g = e.g;
+  const double4 * __restrict__ scan_tf = e.scan_tf;
+  const uint64_t * __restrict__ offsets = e.offsets;
+  const uint32_t n_scans = e.n_scans, n_points = e.n_points, rec_cap = e.rec_cap;
+  const double2 * __restrict__ pts = e.pts;
+  uint32_t * __restrict__ key_out = e.key_out;    // the five dump outputs may be null
+  uint32_t * __restrict__ val_out = e.val_out;
+  uint32_t * __restrict__ seglen = e.seglen;
+  double * __restrict__ sx = e.sx;
+  double * __restrict__ sy = e.sy;
+  uint2 * __restrict__ occ = e.occ;
+  uint32_t * __restrict__ occ_dilated = e.occd;
+  double * __restrict__ rec = e.rec;
+  double * __restrict__ rec_fast = e.rec_fast;
+  uint32_t * __restrict__ n_valid = e.n_valid;
   const uint32_t tid = threadIdx.x;
   uint32_t n2 = 32;
   while (n2 < n_points) {n2 <<= 1;}
@@ -656,10 +663,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(
   for (uint32_t i = tid; i < n_points; i += kSmallThreads) {
     const unsigned long long it = sm.items[i];
     const uint32_t k = static_cast<uint32_t>(it >> 32), p = static_cast<uint32_t>(it);
-    key_out[i] = k;
-    val_out[i] = p;
-    sx[i] = sm.wx[p];
-    sy[i] = sm.wy[p];
+    if (key_out) {
+      key_out[i] = k;
+      val_out[i] = p;
+      sx[i] = sm.wx[p];
+      sy[i] = sm.wy[p];
+    }
     if (k >= g.n_cells) {continue;}
     if (i > 0 && static_cast<uint32_t>(sm.items[i - 1] >> 32) == k) {continue;}
     uint32_t lo = i, step = 1, hi = n_points;
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(
       if (static_cast<uint32_t>(sm.items[mid] >> 32) == k) {lo = mid;} else {hi = mid;}
     }
     const uint32_t len = hi - i;
-    seglen[i] = len;
+    if (seglen) {seglen[i] = len;}
     if (len >= 5) {
       const uint32_t pi = padded_index(g, k);
       atomicOr(&sm.occw[pi >> 5], 1u << (pi & 31u));
@@ -744,6 +753,43 @@ __global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(
   }
 }
 
+__global__ void __launch_bounds__(kSmallThreads, 1) build_small_kernel(BuildEntry e)
+{
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  build_small_body(e, *reinterpret_cast<SmallSmem *>(small_raw));
+}
+
+// One CTA per model of a batch (the loop-closure windows of match_scan_batch).
+__global__ void __launch_bounds__(kSmallThreads, 1) build_small_batch_kernel(
+  const BuildEntry * __restrict__ entries)
+{
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  __shared__ BuildEntry e;
+  {
+    const uint32_t * src = reinterpret_cast<const uint32_t *>(entries + blockIdx.x);
+    uint32_t * dst = reinterpret_cast<uint32_t *>(&e);
+    for (uint32_t k = threadIdx.x; k < sizeof(BuildEntry) / 4; k += blockDim.x) {dst[k] = src[k];}
+  }
+  __syncthreads();
+  build_small_body(e, *reinterpret_cast<SmallSmem *>(small_raw));
+}
+
+// opt in to the large dynamic shared memory of the single-CTA build, once per device
+int configure_small_kernels()
+{
+  static bool configured[64] = {false};
+  int dev = 0;
+  NDT2D_CUDA_TRY(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    NDT2D_CUDA_TRY(cudaFuncSetAttribute(build_small_kernel,
+      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallSmem))));
+    NDT2D_CUDA_TRY(cudaFuncSetAttribute(build_small_batch_kernel,
+      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallSmem))));
+    configured[dev & 63] = true;
+  }
+  return NDT2D_OK;
+}
+
 int bits_needed(uint32_t max_value)
 {
   int b = 1;
@@ -752,6 +798,22 @@ int bits_needed(uint32_t max_value)
 }
 
 }  // namespace
+
+bool ndt2d_build_is_small(const GridDesc & g, size_t n_points)
+{
+  return n_points > 0 && n_points <= kSmallMaxPoints && g.n_words <= kSmallMaxWords;
+}
+
+int ndt2d_launch_build_small_batch(const BuildEntry * d_entries, uint32_t n, cudaStream_t stream,
+  Counters * ctr)
+{
+  if (n == 0) {return NDT2D_OK;}
+  const int rc0 = configure_small_kernels();
+  if (rc0 != NDT2D_OK) {return rc0;}
+  build_small_batch_kernel<<<n, kSmallThreads, sizeof(SmallSmem), stream>>>(d_entries);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
+}
 
 int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
   cudaStream_t stream, Counters * ctr)
@@ -767,16 +829,27 @@ int ndt2d_launch_build(
 {
   if (n_points > 0 && n_points <= kSmallMaxPoints && g.n_words <= kSmallMaxWords) {
     // small model: the whole build in one CTA / one launch
-    static bool configured = false;
-    if (!configured) {
-      NDT2D_CUDA_TRY(cudaFuncSetAttribute(build_small_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallSmem))));
-      configured = true;
-    }
-    build_small_kernel<<<1, kSmallThreads, sizeof(SmallSmem), stream>>>(
-      g, d_scan_tf, d_offsets, static_cast<uint32_t>(n_scans), d_pts, static_cast<uint32_t>(n_points),
-      s.key[0], s.val[0], s.seglen, s.sx, s.sy, d_occ, d_occ_dilated, d_rec, d_rec_fast, rec_cap,
-      d_n_valid);
+    const int rc0 = configure_small_kernels();
+    if (rc0 != NDT2D_OK) {return rc0;}
+    BuildEntry e{};
+    e.g = g;
+    e.scan_tf = d_scan_tf;
+    e.offsets = d_offsets;
+    e.n_scans = static_cast<uint32_t>(n_scans);
+    e.pts = d_pts;
+    e.n_points = static_cast<uint32_t>(n_points);
+    e.occ = d_occ;
+    e.occd = d_occ_dilated;
+    e.rec = d_rec;
+    e.rec_fast = d_rec_fast;
+    e.rec_cap = rec_cap;
+    e.n_valid = d_n_valid;
+    e.key_out = s.key[0];
+    e.val_out = s.val[0];
+    e.seglen = s.seglen;
+    e.sx = s.sx;
+    e.sy = s.sy;
+    build_small_kernel<<<1, kSmallThreads, sizeof(SmallSmem), stream>>>(e);
     NDT2D_LAUNCH_CHECK(ctr);
     *sorted_buf = 0;
     return NDT2D_OK;

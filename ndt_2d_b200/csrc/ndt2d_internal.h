@@ -100,6 +100,28 @@ struct BuildScratch
   size_t cap_points, cap_hist;
 };
 
+// One small model built by a single CTA (build.cu: build_small_kernel / _batch_kernel).
+struct BuildEntry
+{
+  GridDesc g;
+  const double4 * scan_tf;
+  const uint64_t * offsets;
+  const double2 * pts;
+  uint2 * occ;
+  uint32_t * occd;
+  double * rec;
+  double * rec_fast;
+  uint32_t * n_valid;
+  // parity-dump outputs (sorted keys / values / run lengths / coordinates); null in batches
+  uint32_t * key_out, * val_out, * seglen;
+  double * sx, * sy;
+  uint32_t n_scans, n_points, rec_cap, pad_;
+};
+bool ndt2d_build_is_small(const GridDesc & g, size_t n_points);
+// n models, one CTA each, one launch; d_entries: device array.
+int ndt2d_launch_build_small_batch(const BuildEntry * d_entries, uint32_t n, cudaStream_t stream,
+  Counters * ctr);
+
 // Launches K1..K3 on `stream`: transform + key, stable radix sort by cell key,
 // per-cell sequential moments, occupancy bitmap + rank prefix, packed records.
 // d_scan_tf: per scan {x, y, cos, sin}; d_offsets: n_scans + 1 point offsets;
@@ -190,6 +212,34 @@ int ndt2d_launch_score_poses(
   const ModelView & mv, const double2 * d_pts, uint32_t n_pts, const double4 * d_pose_tf,
   uint32_t n_poses, double sign, int normalise, double * d_out, cudaStream_t stream,
   Counters * ctr);
+
+// ---- batched searches (match_scan_batch): several models / scans, one launch each for
+// build, search and final reduction ------------------------------------------------------
+// One search of a batch: its own model, scan and outputs.
+struct BatchEntry
+{
+  ModelView mv;
+  SearchView sv;
+  double * job_partials;   // n_jobs records of NDT2D_BLOCK_PARTIAL doubles
+  double * chunk_sums;     // n_jobs * P * Rw^2 doubles (P > 1)
+};
+struct RegionBatchPlan
+{
+  uint32_t Rw, Q, n_jobs, P, chunk_points;
+  size_t chunk_doubles;    // per search
+};
+// Plan shared by every search of a batch (same lattice); max_pts = most points of any scan.
+int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, double linear_res,
+  uint32_t max_pts, RegionBatchPlan * out);
+// Search kernel (+ chunk reduction) over all entries; job records land in entry.job_partials.
+int ndt2d_launch_search_region_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, const RegionBatchPlan & pl, uint32_t * d_counter,
+  cudaStream_t stream, Counters * ctr);
+// One block per entry folds its job records (<= 4096) into results32 + 32 * entry and
+// finishes it; clears the job counter block for the next launch.
+int ndt2d_launch_finish_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, uint32_t n_jobs, double n_candidates,
+  double * d_results32, uint32_t * d_counter, cudaStream_t stream, Counters * ctr);
 
 // ---- filter.cu ----------------------------------------------------------
 struct FilterView

@@ -331,6 +331,47 @@ __global__ void __launch_bounds__(256) search_finish_kernel(
   }
 }
 
+// Batched finish: block b folds entry b's job records directly and writes results32 + 32 b.
+__global__ void __launch_bounds__(256) search_finish_batch_kernel(
+  const BatchEntry * __restrict__ batch, uint32_t n_jobs, double n_candidates,
+  double * __restrict__ results32, unsigned long long * __restrict__ counters)
+{
+  const BatchEntry & e = batch[blockIdx.x];
+  Best best{0.0, kNoIndex};
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (blockIdx.x == 0 && threadIdx.x == 0 && counters) {
+    counters[3] = counters[1];
+    counters[4] = counters[2];
+    counters[5] = counters[0];
+    counters[0] = counters[1] = counters[2] = 0ull;
+  }
+  for (uint32_t b = threadIdx.x; b < n_jobs; b += blockDim.x) {
+    const double * p = e.job_partials + static_cast<size_t>(b) * NDT2D_BLOCK_PARTIAL;
+    best_merge(best, p[0], p[1]);
+    const double S = p[2], Sx = p[3], Sy = p[4], Sxx = p[5], Sxy = p[6], Syy = p[7], t = p[8];
+    acc[0] += Sxx;
+    acc[1] += Sxy;
+    acc[2] += t * Sx;
+    acc[3] += Syy;
+    acc[4] += t * Sy;
+    acc[5] += (t * t) * S;
+    acc[6] += Sx;
+    acc[7] += Sy;
+    acc[8] += t * S;
+    acc[9] += S;
+  }
+  __shared__ double folded[12];
+  block_fold_12(best, acc, folded);
+  if (threadIdx.x == 0) {
+    double * out32 = results32 + 32 * static_cast<size_t>(blockIdx.x);
+    for (int k = 0; k < 12; ++k) {out32[k] = folded[k];}
+    out32[12] = n_candidates;
+    out32[13] = static_cast<double>(e.sv.n_pts);
+    out32[14] = out32[15] = 0.0;
+    finish_record(out32, e.sv.dth, e.sv.dlin, e.sv.n_lin);
+  }
+}
+
 // block_partials: n_blocks records of NDT2D_BLOCK_PARTIAL doubles, followed by room for
 // kReduceBlocks stage-1 records (ndt2d_search_scratch_doubles accounts for it).
 constexpr uint32_t kDirectFinishMax = 4096;   // job records one block folds without stage 1
@@ -506,6 +547,17 @@ int ndt2d_launch_search(
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
            n_candidates, d_partial32, stream, ctr, exchange, nullptr);
+}
+
+int ndt2d_launch_finish_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, uint32_t n_jobs, double n_candidates,
+  double * d_results32, uint32_t * d_counter, cudaStream_t stream, Counters * ctr)
+{
+  if (n_batch == 0) {return NDT2D_OK;}
+  search_finish_batch_kernel<<<n_batch, 256, 0, stream>>>(d_batch, n_jobs, n_candidates,
+    d_results32, reinterpret_cast<unsigned long long *>(d_counter));
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
 }
 
 int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d_dth,

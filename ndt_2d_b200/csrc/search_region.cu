@@ -37,6 +37,8 @@
 // warp-uniform loads through L1.  DRAM traffic is a few hundred KB per launch.
 #include <cuda_runtime.h>
 #include <math.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "ndt2d_internal.h"
@@ -422,15 +424,6 @@ search_region_kernel(
 #undef NDT2D_BODY_CHUNKS
 }
 
-// One search of a batch (ndt2d_matcher_match_scan_batch): its own model, scan and outputs.
-struct BatchEntry
-{
-  ModelView mv;
-  SearchView sv;
-  double * job_partials;   // n_jobs records of NDT2D_BLOCK_PARTIAL doubles
-  double * chunk_sums;     // n_jobs * P * Rw^2 doubles (P > 1)
-};
-
 static_assert(sizeof(BatchEntry) <= kBatchSlotBytes && sizeof(BatchEntry) % 4 == 0, "batch slot size");
 
 // The same job loop over SEVERAL searches in one launch: the job counter enumerates
@@ -586,6 +579,88 @@ size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
   return static_cast<size_t>(n_theta) * 2 * pl.Q * n_pts_pad * sizeof(uint16_t);
 }
 
+// region_chunk_reduce_kernel for a batch: one warp per (search, job).
+__global__ void __launch_bounds__(256) region_chunk_reduce_batch_kernel(
+  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
+  uint32_t P)
+{
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (gw >= n_batch * n_jobs) {return;}
+  const uint32_t bj = gw / n_jobs, job = gw - bj * n_jobs;
+  const BatchEntry & e = batch[bj];
+  const uint32_t QQ = Q * Q, RR = Rw * Rw;
+  const uint32_t it = job / QQ, rr = job - it * QQ;
+  const uint32_t rx = rr / Q, ry = rr - rx * Q;
+  const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
+  const uint32_t n_lin = e.sv.n_lin;
+  const uint32_t nxc = min(Rw, n_lin - jx0), nyc = min(Rw, n_lin - jy0);
+  double * first = e.chunk_sums + static_cast<size_t>(job) * P * RR;
+  for (uint32_t k = lane; k < RR; k += 32) {
+    double t = first[k];
+    for (uint32_t c = 1; c < P; ++c) {t += first[static_cast<size_t>(c) * RR + k];}
+    first[k] = t;
+  }
+  __syncwarp();
+  job_epilogue([first](uint32_t k) {return first[k];}, e.sv, job, it, Rw, jx0, jy0, nxc, nyc, lane,
+    e.job_partials, nullptr);
+}
+
+}  // namespace
+
+int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, double linear_res,
+  uint32_t max_pts, RegionBatchPlan * out)
+{
+  GridDesc g{};
+  g.cell_size = cell_size;
+  RegionPlan pl = make_plan(g, n_ang, n_lin, linear_res);
+  // chunk the points as a lone search of this shape would, capped so that a search's chunk
+  // sums stay small
+  plan_chunks(pl, max_pts, size_t(1) << 22);
+  out->Rw = pl.Rw;
+  out->Q = pl.Q;
+  out->n_jobs = pl.n_jobs;
+  out->P = pl.P;
+  out->chunk_points = pl.chunk_points;
+  out->chunk_doubles = pl.P > 1 ? static_cast<size_t>(pl.n_jobs) * pl.P * pl.Rw * pl.Rw : 0;
+  return NDT2D_OK;
+}
+
+int ndt2d_launch_search_region_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, const RegionBatchPlan & pl, uint32_t * d_counter,
+  cudaStream_t stream, Counters * ctr)
+{
+  if (n_batch == 0 || pl.n_jobs == 0) {return NDT2D_OK;}
+  static int configured_sms[64] = {0};
+  int dev = 0;
+  NDT2D_CUDA_TRY(cudaGetDevice(&dev));
+  const int slot = dev & 63;
+  const size_t smem = static_cast<size_t>(kWarps) * (kWarpSmemBytes + kBatchSlotBytes);
+  if (configured_sms[slot] == 0) {
+    int n = 148;
+    NDT2D_CUDA_TRY(cudaFuncSetAttribute(search_region_batch_kernel,
+      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    NDT2D_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    configured_sms[slot] = n;
+  }
+  const uint64_t total = static_cast<uint64_t>(n_batch) * pl.n_jobs * pl.P;
+  if (total >= (1ull << 32)) {return NDT2D_ERR_SIZE;}
+  const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(total, configured_sms[slot]));
+  search_region_batch_kernel<<<grid, kWarps * 32, smem, stream>>>(
+    d_batch, n_batch, pl.Rw, pl.Q, pl.n_jobs, pl.P, pl.chunk_points, d_counter,
+    reinterpret_cast<unsigned long long *>(d_counter) + 1);
+  NDT2D_LAUNCH_CHECK(ctr);
+  if (pl.P > 1) {
+    const uint32_t warps = n_batch * pl.n_jobs;
+    region_chunk_reduce_batch_kernel<<<(warps + 7u) / 8u, 256, 0, stream>>>(
+      d_batch, n_batch, pl.Rw, pl.Q, pl.n_jobs, pl.P);
+    NDT2D_LAUNCH_CHECK(ctr);
+  }
+  return NDT2D_OK;
+}
+
+namespace
+{
+// (closed again below)
 }  // namespace
 
 size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
