@@ -60,7 +60,9 @@ typedef struct ndt2d_params
   double range_max;                  /* initialize(..., range_max) */
   int device;                        /* CUDA device ordinal, -1 = current device */
   void * stream;                     /* cudaStream_t to run on; NULL = handle-owned stream */
-  int kernel_variant;                /* 0 = production search kernel (warp-per-region),
+  int kernel_variant;                /* 0 = auto: warp-per-region kernel, or the dense
+                                        warp-per-candidate kernel for small searches
+                                        (3 forces dense, 4 forces region);
                                         1 = plain per-candidate kernel (reference arithmetic
                                         per evaluation; the on-device cross-check),
                                         2 = previous tiled kernel (A/B runs) */
