@@ -323,6 +323,23 @@ def test_random_small_worlds(o, seed):
     np.testing.assert_allclose(m.scorePoints(q, guess), mo.score_points(q, guess), rtol=RTOL, atol=ATOL_SCORE)
 
 
+@pytest.mark.parametrize("variant", [0, 3, 4])
+def test_long_scan_small_lattice(o, variant):
+    """A 3,240-point scan (more than the dense kernel stages per pass, more than one chunk of
+    the region kernel) on a small lattice."""
+    w = synth.config1()
+    p = dict(w.params, laser_max_beams=5000, search_angular_size=0.02, search_linear_size=0.15)
+    pts = np.concatenate([w.query_points] + [w.query_points + 1e-3 * (k + 1) for k in range(8)])
+    assert pts.shape[0] > 2048
+    m = ScanMatcherNDT.from_params(p, kernel_variant=variant)
+    mo = o.new_matcher(p)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    so, do, wo, co, scores_o = mo.match_scan(w.query_pose, pts, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(w.query_pose, pts)
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(w.query_pose, pts), scores_o)
+
+
 def test_theta_sliced_search_matches_full(o):
     """Partial searches over theta ranges + one combine == the full search (the
     multi-GPU path, exercised on one device)."""
