@@ -658,11 +658,6 @@ int ndt2d_launch_search_region_batch(
   return NDT2D_OK;
 }
 
-namespace
-{
-// (closed again below)
-}  // namespace
-
 size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res)
 {
