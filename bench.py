@@ -472,6 +472,7 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     kernel_ms = float(np.mean(kernel_ms_steps)) if kernel_ms_steps and min(kernel_ms_steps) > 0 else ms_per_step
     algo_bytes = my_candidates * n_pts * ALGO_BYTES_PER_EVAL
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
@@ -537,6 +538,13 @@ def run_ours(args):
             "achieved_all_pairs": achieved, "frac_all_pairs": achieved / gather_gbps,
             "achieved_useful": useful * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9,
             "frac_useful": useful * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9 / gather_gbps},
+        "sfu_roofline": {
+            "what": "Gaussian evaluations that reach an occupied cell (each needs one ex2 on the SFU) against "
+                    "the SFU issue rate: the arithmetic floor of this search; everything above it is bookkeeping",
+            "achieved": useful / (kernel_ms * 1e-3), "unit": "evaluations/s",
+            "peak": sm_count * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+            "frac": (useful / (kernel_ms * 1e-3)) / (sm_count * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+            "peak_source": "SMs x 16 MUFU lanes/clk x sampled SM clock"},
         "useful_evaluations": {"per_launch": useful, "fraction_of_pairs": useful / max(my_candidates * n_pts, 1),
                                "per_second": useful / (kernel_ms * 1e-3),
                                "point_region_items": stats["items"]},
