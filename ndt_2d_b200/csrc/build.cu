@@ -583,6 +583,8 @@ constexpr uint32_t kSmallMaxHeads = kSmallMaxPoints / 5 + 1;
 struct SmallSmem
 {
   unsigned long long items[kSmallMaxPoints];
+  unsigned long long items_alt[kSmallMaxPoints];   // ping-pong buffer of the radix sort
+  uint32_t cnt[32][256];                           // per-warp digit counters / offsets
   double wx[kSmallMaxPoints];
   double wy[kSmallMaxPoints];
   uint32_t occw[kSmallMaxWords];
@@ -618,7 +620,7 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
   double * __restrict__ rec_fast = e.rec_fast;
   uint32_t * __restrict__ n_valid = e.n_valid;
   const uint32_t tid = threadIdx.x;
-  uint32_t n2 = 32;
+  uint32_t n2 = 128;
   while (n2 < n_points) {n2 <<= 1;}
 
   for (uint32_t w = tid; w < g.n_words; w += kSmallThreads) {sm.occw[w] = 0u;}
@@ -643,19 +645,67 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
     }
   }
   __syncthreads();
-  // ---- K2: bitonic sort (ascending); the point index in the low word makes it stable
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = tid; t < (n2 >> 1); t += kSmallThreads) {
-        const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // index with bit j clear
-        const uint32_t l = i | j;
-        const bool up = (i & k) == 0u;
-        const unsigned long long a = sm.items[i], b = sm.items[l];
-        if ((a > b) == up) {
-          sm.items[i] = b;
-          sm.items[l] = a;
+  // ---- K2: stable LSD radix sort on the cell key, 8-bit digits, entirely in shared memory
+  // (the same warp-ordered ranking as radix_scatter_kernel: warp w owns the 128 consecutive
+  // items [128 w, 128 w + 128) and walks them in order, so equal keys keep their order).
+  {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool warp_active = warp * 128u < n2;
+    const int bits = 32 - __clz(g.n_cells | 1u);           // keys are <= n_cells (= "outside")
+    unsigned long long * src = sm.items;
+    unsigned long long * dst = sm.items_alt;
+    for (int shift = 0; shift < bits; shift += 8) {
+      for (uint32_t k = lane; k < 256u; k += 32u) {sm.cnt[warp][k] = 0u;}
+      __syncwarp();
+      unsigned long long item[4];
+      uint32_t local[4], dig[4];
+      if (warp_active) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+          item[st] = src[warp * 128u + st * 32u + lane];
+          // padding items (~0) get digit 255 in every pass and stay at the end
+          const uint32_t d = static_cast<uint32_t>(item[st] >> (32 + shift)) & 255u;
+          const uint32_t peers = __match_any_sync(0xffffffffu, d);
+          const uint32_t r = __popc(peers & lt_mask);
+          const uint32_t base = sm.cnt[warp][d];
+          __syncwarp();
+          if (r == 0u) {sm.cnt[warp][d] = base + __popc(peers);}
+          __syncwarp();
+          local[st] = base + r;
+          dig[st] = d;
         }
       }
+      __syncthreads();
+      {
+        // exclusive scan over (digit, warp) in digit-major order: entry e = d * 32 + w
+        uint32_t v[8], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t e = tid * 8u + q;
+          v[q] = sm.cnt[e & 31u][e >> 5];
+          tsum += v[q];
+        }
+        uint32_t run = block_exclusive_scan_1024(tsum, &sm.total);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t e = tid * 8u + q;
+          sm.cnt[e & 31u][e >> 5] = run;
+          run += v[q];
+        }
+      }
+      __syncthreads();
+      if (warp_active) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {dst[sm.cnt[warp][dig[st]] + local[st]] = item[st];}
+      }
+      __syncthreads();
+      unsigned long long * t = src;
+      src = dst;
+      dst = t;
+    }
+    if (src != sm.items) {
+      for (uint32_t i = tid; i < n2; i += kSmallThreads) {sm.items[i] = src[i];}
       __syncthreads();
     }
   }
