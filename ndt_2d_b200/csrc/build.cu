@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) dilate_kernel(
 // A rolling-window model (config 1: 10 scans, 3,600 points; a loop-closure window:
 // 1-2 scans) is far too small for the multi-launch pipeline above: ~15 dependent
 // launches of a few microseconds each.  build_small_kernel does the whole build in ONE
-// CTA: transform + key, a stable in-shared-memory bitonic sort of (key << 32 | point
+// CTA: transform + key, a stable in-shared-memory radix sort of (key << 32 | point
 // index), run lengths, occupancy bitmap + rank prefix + dilated bitmap, and the same
 // 8-lanes-per-cell moment recurrences -- identical results (the sort is stable because
 // the point index is part of the sort item; the recurrence walks the points in order).
