@@ -325,7 +325,31 @@ int grid_from_poses(const ndt2d_matcher * m, size_t n_scans, const double * pose
   return NDT2D_OK;
 }
 
+int add_scans_impl(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy);
+
+// addScans of a small model (a rolling window) does not wait for the device: its host
+// staging comes from the pinned arena (recycled only after a stream synchronisation), so the
+// caller goes on to scoreScan / matchScan while the build runs -- the way the node calls
+// them back to back (ndt_mapper.cpp:508-515).  Large models keep the synchronous path.
 int add_scans_locked(
+  ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
+  const double * pts_xy)
+{
+  const size_t n_points = n_scans ? static_cast<size_t>(pt_offsets[n_scans] - pt_offsets[0]) : 0;
+  if (m->pipelined || n_points * sizeof(double2) > (size_t(1) << 20)) {
+    return add_scans_impl(m, n_scans, poses, pt_offsets, pts_xy);
+  }
+  int rc = m->h_arena.ensure(size_t(8) << 20);
+  if (rc) {return rc;}
+  m->pipelined = true;
+  rc = add_scans_impl(m, n_scans, poses, pt_offsets, pts_xy);
+  m->pipelined = false;
+  return rc;
+}
+
+int add_scans_impl(
   ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
   const double * pts_xy)
 {
@@ -938,10 +962,13 @@ static int match_scan_batch_fused(
   const size_t o_results = take(n_jobs * 32 * sizeof(double));
   const size_t total_bytes = off;
   if (total_bytes > (size_t(2) << 30)) {return kBatchNotEligible;}
+  // the arena may still feed an earlier asynchronous addScans: drain before reusing / growing it
+  NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
   int rc = m->d_batch_arena.ensure(total_bytes);
   if (!rc) {rc = m->h_arena.ensure(upload_bytes);}
   if (!rc) {rc = m->h_result.ensure(std::max<size_t>(n_jobs * 32, 64) * sizeof(double));}
   if (rc) {return rc;}
+  m->arena_off = 0;
   char * hb = m->h_arena.as<char>();
   char * db = m->d_batch_arena.as<char>();
   memset(hb + o_counter, 0, 64);
@@ -1610,6 +1637,7 @@ NDT2D_API int ndt2d_matcher_counters(ndt2d_matcher * m, uint64_t * out4)
   if (m->has_model) {
     DeviceGuard guard(m->device);
     uint32_t nv = 0;
+    cudaStreamSynchronize(m->stream);   // the build may still be running (asynchronous addScans)
     if (cudaMemcpy(&nv, m->d_nvalid.p, sizeof(nv), cudaMemcpyDeviceToHost) == cudaSuccess) {
       out4[3] = nv;
     }
