@@ -365,28 +365,10 @@ int add_scans_impl(
   if (n_points >= (1ull << 32) - 1) {return NDT2D_ERR_SIZE;}
   const uint64_t off0 = n_scans ? pt_offsets[0] : 0;
 
-  // ---- host staging: per-scan transform, rebased offsets, axis thresholds
-  std::vector<double> thr_x, thr_y;
-  axis_thresholds(g.origin_x, g.cell_size, g.size_x, thr_x);
-  axis_thresholds(g.origin_y, g.cell_size, g.size_y, thr_y);
   const size_t tf_bytes = n_scans * sizeof(double4);
   const size_t off_bytes = (n_scans + 1) * sizeof(uint64_t);
-  const size_t thr_bytes = (thr_x.size() + thr_y.size()) * sizeof(double);
-  char * hs = nullptr;
-  int rc = stage_alloc(m, tf_bytes + off_bytes + thr_bytes, &hs);
-  if (rc) {return rc;}
-  double4 * h_tf = reinterpret_cast<double4 *>(hs);
-  uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + tf_bytes);
-  double * h_thr = reinterpret_cast<double *>(hs + tf_bytes + off_bytes);
-  for (size_t k = 0; k < n_scans; ++k) {
-    const double * pose = poses + 3 * k;
-    // ndt_model.cpp:135-136
-    h_tf[k] = make_double4(pose[0], pose[1], cos(pose[2]), sin(pose[2]));
-    h_off[k] = pt_offsets[k] - off0;
-  }
-  h_off[n_scans] = n_points;
-  memcpy(h_thr, thr_x.data(), thr_x.size() * sizeof(double));
-  memcpy(h_thr + thr_x.size(), thr_y.data(), thr_y.size() * sizeof(double));
+  const size_t thr_bytes = (static_cast<size_t>(g.size_x) + 2 + g.size_y + 2) * sizeof(double);
+  int rc = NDT2D_OK;
 
   // ---- device buffers
   const size_t np1 = n_points ? n_points : 1;
@@ -432,13 +414,8 @@ int add_scans_impl(
   m->bs.hist = m->d_hist.as<uint32_t>();
   m->bs.scan_tmp = m->d_scantmp.as<uint32_t>();
 
-  // ---- uploads
+  // ---- uploads: the points first
   cudaStream_t st = m->stream;
-  if (tf_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_scan_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
-  }
-  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_offsets.p, h_off, off_bytes, cudaMemcpyHostToDevice, st));
-  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_thr.p, h_thr, thr_bytes, cudaMemcpyHostToDevice, st));
   if (n_points) {
     const double * src = pts_xy + 2 * off0;
     if (m->pipelined) {
@@ -451,6 +428,35 @@ int add_scans_impl(
     NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_mappts.p, src, n_points * sizeof(double2),
       cudaMemcpyHostToDevice, st));
   }
+
+  // ---- host staging: per-scan transform, rebased offsets, axis thresholds -- computed while
+  // the points (the bulk of the bytes) are already on their way
+  std::vector<double> thr_x, thr_y;
+  axis_thresholds(g.origin_x, g.cell_size, g.size_x, thr_x);
+  axis_thresholds(g.origin_y, g.cell_size, g.size_y, thr_y);
+  char * hs = nullptr;
+  if ((rc = stage_alloc(m, tf_bytes + off_bytes + thr_bytes, &hs))) {
+    cudaStreamSynchronize(st);  // the points copy reads the caller's buffer
+    return rc;
+  }
+  double4 * h_tf = reinterpret_cast<double4 *>(hs);
+  uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + tf_bytes);
+  double * h_thr = reinterpret_cast<double *>(hs + tf_bytes + off_bytes);
+  for (size_t k = 0; k < n_scans; ++k) {
+    const double * pose = poses + 3 * k;
+    // ndt_model.cpp:135-136
+    h_tf[k] = make_double4(pose[0], pose[1], cos(pose[2]), sin(pose[2]));
+    h_off[k] = pt_offsets[k] - off0;
+  }
+  h_off[n_scans] = n_points;
+  memcpy(h_thr, thr_x.data(), thr_x.size() * sizeof(double));
+  memcpy(h_thr + thr_x.size(), thr_y.data(), thr_y.size() * sizeof(double));
+
+  if (tf_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_scan_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
+  }
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_offsets.p, h_off, off_bytes, cudaMemcpyHostToDevice, st));
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_thr.p, h_thr, thr_bytes, cudaMemcpyHostToDevice, st));
   m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
 
   if (m->evb_begin) {cudaEventRecord(m->evb_begin, st);}
