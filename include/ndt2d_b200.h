@@ -60,9 +60,11 @@ typedef struct ndt2d_params
   double range_max;                  /* initialize(..., range_max) */
   int device;                        /* CUDA device ordinal, -1 = current device */
   void * stream;                     /* cudaStream_t to run on; NULL = handle-owned stream */
-  int kernel_variant;                /* 0 = auto: warp-per-region kernel, or the dense
-                                        warp-per-candidate kernel for small searches
-                                        (3 forces dense, 4 forces region);
+  int kernel_variant;                /* 0 = auto: warp-per-region kernel; for small searches
+                                        the window kernel (thread per candidate, windows a
+                                        few cells wide) or the dense warp-per-candidate
+                                        kernel (3 forces dense, 4 forces region, 5 forces
+                                        window where eligible, else dense);
                                         1 = plain per-candidate kernel (reference arithmetic
                                         per evaluation; the on-device cross-check),
                                         2 = previous tiled kernel (A/B runs) */
@@ -358,6 +360,25 @@ NDT2D_API int ndt2d_laser_to_points(
   int device, const float * ranges, size_t n, float angle_min, float angle_increment,
   double range_max, const double * laser_tf3, const double * translation3, int laser_inverted,
   double * out_pts_xy, size_t * n_out);
+
+/* replaces Graph::findNearest (graph.cpp:167-189), the candidate selection of the loop
+ * closure (ndt_mapper.cpp:612-616): the indices of the scans whose position lies within
+ * the radius of the query position, nearest first.  The reference builds a nanoflann
+ * KD-tree (un-vendored dependency, L2_Simple_Adaptor, 2-D) over the first `limit` scans
+ * on every call and runs radiusSearch, which takes a SQUARED radius (so the node's
+ * global_search_size 0.2 means sqrt(0.2) m), keeps dist < radius (strict) and returns the
+ * matches by ascending distance.  Here: one thread per scan, distance accumulated like
+ * evalMetric (dx*dx then + dy*dy), order (distance, index) -- nanoflann's order among
+ * exactly equal distances is unspecified.
+ *   scan_xy            2 * n_scans doubles: Scan::getPose() (or getBarycenterPose(),
+ *                      graph.cpp:173,178) x, y of every scan of the graph
+ *   limit_scan_index   > 0: only scans [0, limit) are searched; <= 0: all (:171)
+ *   out_indices / out_dist_sq (optional)  room for `capacity` entries
+ *   *n_found           number of matches (may exceed capacity; the nearest are written) */
+NDT2D_API int ndt2d_find_nearest(
+  int device, const double * scan_xy, size_t n_scans, int64_t limit_scan_index,
+  const double * query_xy, double radius_sq, uint64_t * out_indices, double * out_dist_sq,
+  size_t capacity, size_t * n_found);
 
 /* ------------------------------------------------------------------------
  * Occupancy-grid export: ndt_2d::OccupancyGrid

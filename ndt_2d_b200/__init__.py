@@ -15,6 +15,7 @@ _EXPORTS = {
     "MotionModel": ".particle_filter", "ParticleFilter": ".particle_filter",
     "ParameterNode": ".scan_matcher", "Pose2d": ".scan_matcher", "Scan": ".scan_matcher",
     "ScanMatcherNDT": ".scan_matcher", "laser_to_points": ".scan_matcher", "OccupancyGrid": ".scan_matcher",
+    "find_nearest": ".scan_matcher", "graph_find_nearest": ".scan_matcher",
 }
 
 __all__ = sorted(_EXPORTS)

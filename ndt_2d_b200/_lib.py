@@ -103,6 +103,9 @@ SIGNATURES = {
     "ndt2d_laser_to_points": (
         C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_float, C.c_double, _dp, _dp,
                   C.c_int, _dp, C.POINTER(C.c_size_t)]),
+    "ndt2d_find_nearest": (
+        C.c_int, [C.c_int, _dp, C.c_size_t, C.c_int64, _dp, C.c_double, _u64p, _dp, C.c_size_t,
+                  C.POINTER(C.c_size_t)]),
     "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_filter_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, _vp, C.POINTER(_vp)]),

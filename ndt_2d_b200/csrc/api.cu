@@ -935,7 +935,24 @@ static int match_scan_batch_fused(
   }
   RegionBatchPlan pl;
   ndt2d_region_batch_plan(m->prm.ndt_resolution, static_cast<uint32_t>(n_ang),
-    static_cast<uint32_t>(n_lin), m->prm.search_linear_resolution, max_use, &pl);
+    static_cast<uint32_t>(n_lin), m->prm.search_linear_resolution, max_use,
+    static_cast<uint32_t>(std::min<size_t>(n_jobs, 1u << 16)), &pl);
+  // small searches (local-match windows: a region of the region kernel holds too few
+  // candidates to fill a warp) go to the window kernel, else the dense one, by the same rule
+  // as a single search
+  const bool small_search = static_cast<double>(n_ang) * n_lin * n_lin * max_use < 2.0e7 &&
+    n_ang <= 65535 && n_jobs <= 65535;
+  const uint32_t win_k = small_search ? ndt2d_window_cells(m->prm.ndt_resolution,
+      static_cast<uint32_t>(n_lin), m->prm.search_linear_resolution) : 0u;
+  const uint32_t dense_records = win_k ?
+    ndt2d_window_records(static_cast<uint32_t>(n_ang), static_cast<uint32_t>(n_lin)) :
+    ndt2d_dense_batch_records(static_cast<uint32_t>(n_ang), static_cast<uint32_t>(n_lin));
+  const bool dense = small_search && dense_records <= 4096;
+  if (dense) {
+    pl.n_jobs = dense_records;
+    pl.P = 1;
+    pl.chunk_doubles = 0;
+  }
   if (pl.n_jobs == 0 || pl.n_jobs > 4096) {return kBatchNotEligible;}
   // ---- layout: [upload region][device-only region], everything 256-byte aligned
   size_t off = 0;
@@ -1049,7 +1066,15 @@ static int match_scan_batch_fused(
   m->ctr.h2d_bytes += upload_bytes;
   rc = ndt2d_launch_build_small_batch(reinterpret_cast<const BuildEntry *>(db + o_build),
       static_cast<uint32_t>(n_jobs), st, &m->ctr);
-  if (!rc) {
+  if (!rc && dense && win_k) {
+    rc = ndt2d_launch_search_window_batch(reinterpret_cast<const BatchEntry *>(db + o_batch),
+        static_cast<uint32_t>(n_jobs), win_k, static_cast<uint32_t>(n_ang),
+        static_cast<uint32_t>(n_lin), st, &m->ctr);
+  } else if (!rc && dense) {
+    rc = ndt2d_launch_search_dense_batch(reinterpret_cast<const BatchEntry *>(db + o_batch),
+        static_cast<uint32_t>(n_jobs), static_cast<uint32_t>(n_ang), static_cast<uint32_t>(n_lin), st,
+        &m->ctr);
+  } else if (!rc) {
     rc = ndt2d_launch_search_region_batch(reinterpret_cast<const BatchEntry *>(db + o_batch),
         static_cast<uint32_t>(n_jobs), pl, reinterpret_cast<uint32_t *>(db + o_counter), st, &m->ctr);
   }

@@ -8,9 +8,15 @@
 // everything after it is double.  cos / sin are the device's double-precision functions
 // (<= 2 ulp), so points agree with the reference to ~1e-15 relative, not bit for bit;
 // which beams are kept, and their order, is exact.
+//
+// Also here: Graph::findNearest (graph.cpp:167-189), the candidate selection in front of the
+// loop-closure batch -- a brute-force radius search over the scan positions.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "ndt2d_internal.h"
 
@@ -86,6 +92,36 @@ __global__ void __launch_bounds__(1024) laser_to_points_kernel(
   if (threadIdx.x == 0) {*n_out = base_shared;}
 }
 
+// Graph::findNearest (graph.cpp:167-189): every scan position closer than the (squared)
+// radius to the query.  A thread per scan; the squared distance is accumulated as
+// nanoflann's L2_Simple_Adaptor::evalMetric does (0 + dx*dx, then + dy*dy, no FMA), matches
+// are appended through one warp-aggregated atomic.  The host orders them by (distance, index).
+__global__ void __launch_bounds__(256) find_nearest_kernel(
+  const double2 * __restrict__ scan_xy, uint32_t n, double qx, double qy, double radius_sq,
+  double * __restrict__ out_dist, uint32_t * __restrict__ out_index, uint32_t * __restrict__ n_out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool match = false;
+  double d = 0.0;
+  if (i < n) {
+    const double2 p = scan_xy[i];
+    const double dx = __dsub_rn(qx, p.x), dy = __dsub_rn(qy, p.y);
+    d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    match = d < radius_sq;   // RadiusResultSet::addPoint keeps dist < radius (strict)
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, match);
+  if (bal == 0u) {return;}
+  uint32_t base = 0;
+  if (lane == 0) {base = atomicAdd(n_out, static_cast<uint32_t>(__popc(bal)));}
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (match) {
+    const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+    out_dist[slot] = d;
+    out_index[slot] = i;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -158,6 +194,90 @@ NDT2D_API int ndt2d_laser_to_points(
   if (prev >= 0 && device >= 0 && device != prev) {cudaSetDevice(prev);}
   if (rc == NDT2D_OK) {*n_out = h_n;}
   return rc;
+}
+
+NDT2D_API int ndt2d_find_nearest(
+  int device, const double * scan_xy, size_t n_scans, int64_t limit_scan_index,
+  const double * query_xy, double radius_sq, uint64_t * out_indices, double * out_dist_sq,
+  size_t capacity, size_t * n_found)
+{
+  if (!query_xy || !n_found || (n_scans && !scan_xy) || (capacity && !out_indices) ||
+    n_scans >= (1u << 30))
+  {
+    return NDT2D_ERR_INVALID;
+  }
+  *n_found = 0;
+  if (ndt2d_device_count() <= 0) {return NDT2D_ERR_NO_DEVICE;}
+  // graph.cpp:171: limit_scan_index > 0 restricts the search to scans [0, limit)
+  size_t n = n_scans;
+  if (limit_scan_index > 0 && static_cast<uint64_t>(limit_scan_index) < n_scans) {
+    n = static_cast<size_t>(limit_scan_index);
+  }
+  if (n == 0) {return NDT2D_OK;}
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (device >= 0 && device != prev) {NDT2D_CUDA_TRY(cudaSetDevice(device));}
+  double2 * d_xy = nullptr;
+  double * d_dist = nullptr;
+  uint32_t * d_idx = nullptr;
+  uint32_t * d_n = nullptr;
+  int rc = NDT2D_OK;
+  uint32_t h_n = 0;
+  std::vector<double> dist;
+  std::vector<uint32_t> idx;
+  do {
+    if (cudaMalloc(&d_xy, n * sizeof(double2)) != cudaSuccess ||
+      cudaMalloc(&d_dist, n * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&d_idx, n * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc(&d_n, sizeof(uint32_t)) != cudaSuccess)
+    {
+      rc = NDT2D_ERR_CUDA;
+      break;
+    }
+    if (cudaMemcpy(d_xy, scan_xy, n * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemset(d_n, 0, sizeof(uint32_t)) != cudaSuccess)
+    {
+      rc = NDT2D_ERR_CUDA;
+      break;
+    }
+    find_nearest_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(
+      d_xy, static_cast<uint32_t>(n), query_xy[0], query_xy[1], radius_sq, d_dist, d_idx, d_n);
+    if (cudaGetLastError() != cudaSuccess ||
+      cudaMemcpy(&h_n, d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    {
+      rc = NDT2D_ERR_CUDA;
+      break;
+    }
+    dist.resize(h_n);
+    idx.resize(h_n);
+    if (h_n && (cudaMemcpy(dist.data(), d_dist, h_n * sizeof(double), cudaMemcpyDeviceToHost) !=
+      cudaSuccess ||
+      cudaMemcpy(idx.data(), d_idx, h_n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess))
+    {
+      rc = NDT2D_ERR_CUDA;
+      break;
+    }
+  } while (false);
+  if (rc == NDT2D_ERR_CUDA) {ndt2d_set_error("ndt2d_find_nearest", cudaGetLastError(), __FILE__, __LINE__);}
+  cudaFree(d_xy);
+  cudaFree(d_dist);
+  cudaFree(d_idx);
+  cudaFree(d_n);
+  if (prev >= 0 && device >= 0 && device != prev) {cudaSetDevice(prev);}
+  if (rc != NDT2D_OK) {return rc;}
+  // nanoflann returns the matches sorted by ascending distance (SearchParams::sorted); the
+  // append order above is arbitrary, (distance, index) makes the result deterministic
+  std::vector<uint32_t> order(h_n);
+  for (uint32_t k = 0; k < h_n; ++k) {order[k] = k;}
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return dist[a] < dist[b] || (dist[a] == dist[b] && idx[a] < idx[b]);
+    });
+  for (size_t k = 0; k < h_n && k < capacity; ++k) {
+    out_indices[k] = idx[order[k]];
+    if (out_dist_sq) {out_dist_sq[k] = dist[order[k]];}
+  }
+  *n_found = h_n;
+  return NDT2D_OK;
 }
 
 }  // extern "C"

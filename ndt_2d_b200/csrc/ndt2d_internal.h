@@ -230,11 +230,28 @@ struct RegionBatchPlan
 };
 // Plan shared by every search of a batch (same lattice); max_pts = most points of any scan.
 int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, double linear_res,
-  uint32_t max_pts, RegionBatchPlan * out);
+  uint32_t max_pts, uint32_t n_searches, RegionBatchPlan * out);
 // Search kernel (+ chunk reduction) over all entries; job records land in entry.job_partials.
 int ndt2d_launch_search_region_batch(
   const BatchEntry * d_batch, uint32_t n_batch, const RegionBatchPlan & pl, uint32_t * d_counter,
   cudaStream_t stream, Counters * ctr);
+// ---- search_window.cu: small windows (a few cells wide), thread per candidate with the
+// per-point work shared by a CTA.  ndt2d_window_cells() = cells per axis the window can touch
+// (2..4), 0 = not eligible; records as the dense kernel's, ndt2d_window_records() per search.
+uint32_t ndt2d_window_cells(double cell_size, uint32_t n_lin, double linear_res);
+uint32_t ndt2d_window_records(uint32_t n_theta, uint32_t n_lin);
+int ndt2d_launch_search_window(
+  const ModelView & mv, const SearchView & sv, uint32_t K, uint32_t theta_begin, uint32_t n_theta,
+  double * d_block_partials, double * d_scores, cudaStream_t stream, Counters * ctr);
+int ndt2d_launch_search_window_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, uint32_t K, uint32_t n_ang, uint32_t n_lin,
+  cudaStream_t stream, Counters * ctr);
+// Coarse lattices: the dense (warp per candidate) kernel over all entries instead;
+// ndt2d_dense_batch_records() records of NDT2D_BLOCK_PARTIAL doubles land in entry.job_partials.
+uint32_t ndt2d_dense_batch_records(uint32_t n_ang, uint32_t n_lin);
+int ndt2d_launch_search_dense_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, uint32_t n_ang, uint32_t n_lin, cudaStream_t stream,
+  Counters * ctr);
 // One block per entry folds its job records (<= 4096) into results32 + 32 * entry and
 // finishes it; clears the job counter block for the next launch.
 int ndt2d_launch_finish_batch(

@@ -109,18 +109,6 @@ constexpr uint32_t kDenseWarps = 8;
 constexpr uint32_t kDenseCandPerBlock = 32;
 constexpr uint32_t kDenseMaxPts = 2048;         // outer points staged per CTA (32 KB)
 
-__device__ __forceinline__ uint32_t padded_coord_thr_g(
-  double v, const double * __restrict__ thr, uint32_t size, double origin, double inv_cell)
-{
-  if (!(v >= __ldg(thr))) {return 0u;}
-  const double q = (v - origin) * inv_cell;
-  uint32_t pc = (q >= static_cast<double>(size)) ? size : static_cast<uint32_t>(q);
-  pc += 1u;
-  while (pc <= size && v >= __ldg(thr + pc)) {++pc;}
-  while (pc > 1u && v < __ldg(thr + pc - 1u)) {--pc;}
-  return pc;
-}
-
 // Likelihood of one map-frame point, thresholds + packed records (see ModelView).
 __device__ __forceinline__ double point_likelihood_fast(
   const ModelView & mv, double inv_cell, double x, double y)
@@ -145,9 +133,9 @@ __device__ __forceinline__ double point_likelihood_fast(
   return cell_likelihood(mv.occ, mv.rec, pidx, x, y);   // stiff cell: reference grouping
 }
 
-__global__ void __launch_bounds__(kDenseWarps * 32) search_dense_kernel(
-  ModelView mv, SearchView sv, uint32_t theta_begin, double * __restrict__ block_partials,
-  double * __restrict__ scores)
+__device__ __forceinline__ void dense_block(
+  const ModelView & mv, const SearchView & sv, uint32_t theta_begin,
+  double * __restrict__ block_partials, double * __restrict__ scores)
 {
   __shared__ double2 outer[kDenseMaxPts];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -206,6 +194,27 @@ __global__ void __launch_bounds__(kDenseWarps * 32) search_dense_kernel(
     (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * NDT2D_BLOCK_PARTIAL;
   block_reduce_partial<kDenseWarps * 32>(best, sum, out);
   if (threadIdx.x == 0) {out[8] = sv.dth[itheta];}
+}
+
+__global__ void __launch_bounds__(kDenseWarps * 32) search_dense_kernel(
+  ModelView mv, SearchView sv, uint32_t theta_begin, double * __restrict__ block_partials,
+  double * __restrict__ scores)
+{
+  dense_block(mv, sv, theta_begin, block_partials, scores);
+}
+
+// The same CTA body over SEVERAL searches in one launch (match_scan_batch with coarse
+// lattices, where a region of the region kernel holds too few candidates to fill a warp):
+// blockIdx.z picks the search, its descriptor is copied to shared memory first.
+__global__ void __launch_bounds__(kDenseWarps * 32) search_dense_batch_kernel(
+  const BatchEntry * __restrict__ batch)
+{
+  __shared__ __align__(16) uint32_t entry_words[(sizeof(BatchEntry) + 3) / 4];
+  const uint32_t * src = reinterpret_cast<const uint32_t *>(batch + blockIdx.z);
+  for (uint32_t k = threadIdx.x; k < sizeof(BatchEntry) / 4; k += blockDim.x) {entry_words[k] = src[k];}
+  __syncthreads();
+  const BatchEntry & e = *reinterpret_cast<const BatchEntry *>(entry_words);
+  dense_block(e.mv, e.sv, 0u, e.job_partials, nullptr);
 }
 
 uint32_t dense_blocks_x(uint32_t n_lin)
@@ -635,9 +644,23 @@ int ndt2d_launch_search(
   // (< 2e7 (candidate, point) pairs: local matches, plugin-default windows -- measured 10-20 %
   // faster there, both kernels being latency-bound), else the region kernel (7x faster
   // already at 1/100 of config 4)
-  bool dense = variant == 3;
+  bool dense = variant == 3 || variant == 5;
   if (variant == 0) {
     dense = n_candidates * static_cast<double>(sv.n_pts) < 2.0e7;
+  }
+  // small windows (a few cells wide -- the usual local match): thread per candidate, the
+  // per-point work shared by the CTA (search_window.cu); variant 5 forces it where eligible
+  const uint32_t win_k = (variant == 0 || variant == 5) ?
+    ndt2d_window_cells(mv.g.cell_size, sv.n_lin, sv.linear_res) : 0u;
+  if (dense && win_k != 0u) {
+    if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
+    const int rc = ndt2d_launch_search_window(mv, sv, win_k, theta_begin, n_theta, d_block_partials,
+        d_scores, stream, ctr);
+    if (rc != NDT2D_OK) {return rc;}
+    if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
+    return launch_final(d_block_partials, ndt2d_window_records(n_theta, sv.n_lin),
+             d_block_partials + stage1_offset, sv, n_candidates, d_partial32, stream, ctr, exchange,
+             nullptr);
   }
   if (dense) {
     const uint32_t bx = dense_blocks_x(sv.n_lin);
@@ -693,6 +716,24 @@ int ndt2d_launch_search(
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
            n_candidates, d_partial32, stream, ctr, exchange, nullptr);
+}
+
+uint32_t ndt2d_dense_batch_records(uint32_t n_ang, uint32_t n_lin)
+{
+  const uint64_t r = static_cast<uint64_t>(n_ang) * dense_blocks_x(n_lin);
+  return r > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(r);
+}
+
+int ndt2d_launch_search_dense_batch(
+  const BatchEntry * d_batch, uint32_t n_batch, uint32_t n_ang, uint32_t n_lin, cudaStream_t stream,
+  Counters * ctr)
+{
+  if (n_batch == 0 || n_ang == 0 || n_lin == 0) {return NDT2D_OK;}
+  if (n_ang > 65535u || n_batch > 65535u) {return NDT2D_ERR_SIZE;}
+  dim3 grid(dense_blocks_x(n_lin), n_ang, n_batch);
+  search_dense_batch_kernel<<<grid, kDenseWarps * 32, 0, stream>>>(d_batch);
+  NDT2D_LAUNCH_CHECK(ctr);
+  return NDT2D_OK;
 }
 
 int ndt2d_launch_finish_batch(

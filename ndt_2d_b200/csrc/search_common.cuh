@@ -27,6 +27,22 @@ __device__ __forceinline__ uint32_t padded_coord_exact(
   return (gi >= size ? size : gi) + 1u;
 }
 
+// The same padded coordinate from the host-tabulated exact thresholds (api.cu:
+// axis_thresholds; thr[k] = smallest double whose reference coordinate is >= k,
+// thr[size + 1] = +inf): pc(v) = #{k in [0, size] : thr[k] <= v}.  The product with 1 / cell
+// is only a starting guess, the thresholds fix the answer -- no division.
+__device__ __forceinline__ uint32_t padded_coord_thr_g(
+  double v, const double * __restrict__ thr, uint32_t size, double origin, double inv_cell)
+{
+  if (!(v >= __ldg(thr))) {return 0u;}
+  const double q = (v - origin) * inv_cell;
+  uint32_t pc = (q >= static_cast<double>(size)) ? size : static_cast<uint32_t>(q);
+  pc += 1u;
+  while (pc <= size && v >= __ldg(thr + pc)) {++pc;}
+  while (pc > 1u && v < __ldg(thr + pc - 1u)) {--pc;}
+  return pc;
+}
+
 // Likelihood of one map-frame point given its padded cell index: 0 for an
 // unoccupied cell, else exp(-0.5 q^T I q) (Cell::score, ndt_model.cpp:105-116).
 __device__ __forceinline__ double cell_likelihood(

@@ -475,7 +475,10 @@ search_region_batch_kernel(
 #undef NDT2D_BODY_CHUNKS
 }
 
-RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res)
+// n_searches > 1: a batch of searches of this shape shares the launch, so regions shrink (and
+// points get chunked) only as far as the whole batch needs to fill the machine.
+RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res,
+  uint32_t n_searches = 1)
 {
   RegionPlan pl{};
   // (Rw - 1) * step < cell keeps a region inside a 2 x 2 cell neighbourhood
@@ -489,7 +492,7 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
   // small searches: more, smaller regions so that every SM gets work
   for (;;) {
     const uint32_t q = (n_lin + Rw - 1) / Rw;
-    if (static_cast<uint64_t>(n_theta) * q * q >= kTargetJobs || Rw <= 6) {break;}
+    if (static_cast<uint64_t>(n_theta) * q * q * n_searches >= kTargetJobs || Rw <= 6) {break;}
     Rw = (Rw + 1) / 2;
   }
   pl.Rw = Rw;
@@ -508,13 +511,14 @@ RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, doubl
 
 // Small searches: split the scan points of every job into chunks until there are
 // about kChunkTargetWork (job, chunk) pairs, bounded by the chunk-sum scratch.
-void plan_chunks(RegionPlan & pl, uint32_t n_pts, size_t chunk_cap_doubles)
+void plan_chunks(RegionPlan & pl, uint32_t n_pts, size_t chunk_cap_doubles, uint32_t n_searches = 1)
 {
   pl.P = 1;
   pl.chunk_points = (n_pts + 31u) & ~31u;
   const uint32_t steps = (n_pts + 31u) / 32u;
-  if (pl.n_jobs == 0 || steps < 2 || pl.n_jobs >= kChunkTargetWork) {return;}
-  uint32_t P = (kChunkTargetWork + pl.n_jobs - 1) / pl.n_jobs;
+  const uint64_t jobs_in_flight = static_cast<uint64_t>(pl.n_jobs) * n_searches;
+  if (pl.n_jobs == 0 || steps < 2 || jobs_in_flight >= kChunkTargetWork) {return;}
+  uint32_t P = static_cast<uint32_t>((kChunkTargetWork + jobs_in_flight - 1) / jobs_in_flight);
   if (P > steps) {P = steps;}
   const size_t per_chunk = static_cast<size_t>(pl.n_jobs) * pl.Rw * pl.Rw;
   if (per_chunk * P > chunk_cap_doubles) {P = static_cast<uint32_t>(chunk_cap_doubles / per_chunk);}
@@ -608,14 +612,14 @@ __global__ void __launch_bounds__(256) region_chunk_reduce_batch_kernel(
 }  // namespace
 
 int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, double linear_res,
-  uint32_t max_pts, RegionBatchPlan * out)
+  uint32_t max_pts, uint32_t n_searches, RegionBatchPlan * out)
 {
   GridDesc g{};
   g.cell_size = cell_size;
-  RegionPlan pl = make_plan(g, n_ang, n_lin, linear_res);
-  // chunk the points as a lone search of this shape would, capped so that a search's chunk
-  // sums stay small
-  plan_chunks(pl, max_pts, size_t(1) << 22);
+  RegionPlan pl = make_plan(g, n_ang, n_lin, linear_res, n_searches ? n_searches : 1u);
+  // chunk the points only while the batch as a whole is short of work, capped so that a
+  // search's chunk sums stay small
+  plan_chunks(pl, max_pts, size_t(1) << 22, n_searches ? n_searches : 1u);
   out->Rw = pl.Rw;
   out->Q = pl.Q;
   out->n_jobs = pl.n_jobs;

@@ -99,6 +99,13 @@ public:
     const std::vector<size_t> & candidates, size_t rolling, size_t search_limit,
     double typical_response, size_t * n_batches = nullptr);
 
+  // Graph::findNearest(scan, dist, limit_scan_index) (graph.cpp:167-189) over
+  // graph_->scans: the candidate list closeLoop takes, nearest first.  `dist` is a squared
+  // radius, as nanoflann's radiusSearch takes it; use_barycenter = Graph::use_barycenter_.
+  std::vector<size_t> findNearest(
+    const std::vector<ndt_2d::ScanPtr> & graph_scans, const ndt_2d::ScanPtr & scan, double dist,
+    int limit_scan_index = -1, bool use_barycenter = false) const;
+
   // CUDA device / stream selection, before initialize() (defaults: current device,
   // a stream owned by the handle).
   void setDevice(int device, void * cuda_stream = nullptr);

@@ -255,6 +255,29 @@ std::vector<ScanMatcherNDT::LoopClosure> ScanMatcherNDT::closeLoop(
   return out;
 }
 
+std::vector<size_t> ScanMatcherNDT::findNearest(
+  const std::vector<ndt_2d::ScanPtr> & graph_scans, const ndt_2d::ScanPtr & scan, double dist,
+  int limit_scan_index, bool use_barycenter) const
+{
+  std::vector<double> xy(2 * graph_scans.size());
+  for (size_t i = 0; i < graph_scans.size(); ++i) {
+    // GraphAdapter::kdtree_get_pt (graph.hpp:97-108)
+    const ndt_2d::Pose2d p =
+      use_barycenter ? graph_scans[i]->getBarycenterPose() : graph_scans[i]->getPose();
+    xy[2 * i] = p.x;
+    xy[2 * i + 1] = p.y;
+  }
+  const ndt_2d::Pose2d q = use_barycenter ? scan->getBarycenterPose() : scan->getPose();
+  const double query[2] = {q.x, q.y};
+  std::vector<uint64_t> idx(std::max<size_t>(1, graph_scans.size()));
+  size_t n = 0;
+  const int rc = ndt2d_find_nearest(
+    device_, xy.data(), graph_scans.size(), limit_scan_index, query, dist, idx.data(), nullptr,
+    idx.size(), &n);
+  if (rc != NDT2D_OK) {fail("findNearest", rc);}
+  return std::vector<size_t>(idx.begin(), idx.begin() + std::min(n, idx.size()));
+}
+
 }  // namespace ndt_2d_b200
 
 #include <pluginlib/class_list_macros.hpp>

@@ -3,12 +3,13 @@
 Same names, argument meaning and error behaviour as ndt_2d::ScanMatcher /
 ndt_2d::ScanMatcherNDT (include/ndt_2d/scan_matcher.hpp:42-91,
 src/scan_matcher_ndt.cpp:35-183) so that parity tests read like calls into the
-reference.  The C++ drop-in class lives in ndt_2d_b200/cpp/; this module exists
+reference.  The C++ drop-in class lives in ndt_2d_b200/plugin/; this module exists
 for tests and bench.py.  All computation happens in libndt2d_b200.so.
 """
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass, field
 from typing import Iterable, Optional, Sequence
 
@@ -46,6 +47,19 @@ class Scan:
 
     def setPoints(self, points) -> None:
         self.points = L.f64(points).reshape(-1, 2)
+
+    def getBarycenterPose(self) -> Pose2d:
+        """scan.cpp:55-59, 72-91: pose moved to the mean of the points (sums in point order)."""
+        p = self.pose
+        x, y = p.x, p.y
+        pts = L.f64(self.points).reshape(-1, 2)
+        if pts.shape[0]:
+            c, s = math.cos(p.theta), math.sin(p.theta)
+            cx = np.add.accumulate(c * pts[:, 0] - s * pts[:, 1])[-1]     # sequential, like the loop
+            cy = np.add.accumulate(s * pts[:, 0] + c * pts[:, 1])[-1]
+            x += cx / pts.shape[0]
+            y += cy / pts.shape[0]
+        return Pose2d(float(x), float(y), p.theta)
 
 
 class ParameterNode:
@@ -116,6 +130,33 @@ def laser_to_points(ranges, angle_min: float, angle_increment: float, range_max:
                                         angle_min, angle_increment, range_max, L.dptr(lt), L.dptr(tr),
                                         int(bool(inverted)), L.dptr(out), C.byref(n)), "ndt2d_laser_to_points")
     return out[:n.value].copy()
+
+
+def find_nearest(scan_xy, query_xy, dist: float, limit_scan_index: int = -1, device: int = -1,
+                 return_distances: bool = False):
+    """Graph::findNearest (graph.cpp:167-189) on the device: indices of the scans whose position
+    (pose or barycenter x, y) is closer than `dist` -- a SQUARED radius, as nanoflann's
+    radiusSearch takes it -- to the query, nearest first; only scans [0, limit) when limit > 0."""
+    xy = np.ascontiguousarray(scan_xy, dtype=np.float64).reshape(-1, 2)
+    q = np.ascontiguousarray(query_xy, dtype=np.float64).reshape(2)
+    cap = max(xy.shape[0], 1)
+    idx = np.zeros(cap, dtype=np.uint64)
+    d2 = np.zeros(cap)
+    n = C.c_size_t(0)
+    L.check(L.lib.ndt2d_find_nearest(device, L.dptr(xy), xy.shape[0], int(limit_scan_index), L.dptr(q),
+                                     float(dist), idx.ctypes.data_as(C.POINTER(C.c_uint64)), L.dptr(d2),
+                                     cap, C.byref(n)), "ndt2d_find_nearest")
+    k = min(n.value, cap)
+    return (idx[:k].copy(), d2[:k].copy()) if return_distances else idx[:k].copy()
+
+
+def graph_find_nearest(scans, scan: Scan, dist: float, limit_scan_index: int = -1,
+                       use_barycenter: bool = False, device: int = -1) -> np.ndarray:
+    """Graph::findNearest(scan, dist, limit_scan_index) over a list of Scan (graph.cpp:167-189)."""
+    pick = (lambda s: s.getBarycenterPose()) if use_barycenter else (lambda s: s.getPose())
+    xy = np.array([[pick(s).x, pick(s).y] for s in scans], dtype=np.float64).reshape(-1, 2)
+    q = pick(scan)
+    return find_nearest(xy, [q.x, q.y], dist, limit_scan_index, device)
 
 
 class ScanMatcherNDT:

@@ -68,6 +68,7 @@ class OracleLib:
             "normalize_angle": (C.c_double, [C.c_double]),
             "shortest_angular_distance": (C.c_double, [C.c_double, C.c_double]),
             "kd_leaf_counts": (None, [_dp, C.c_size_t, _dp, _u64p]),
+            "scan_barycenter": (None, [_dp, _dp, C.c_size_t, _dp]),
             "occ_create": (_vp, [C.c_double, C.c_double]), "occ_destroy": (None, [_vp]),
             "occ_render": (C.c_size_t, [_vp, C.c_size_t, _dp, _u64p, _dp, _dp, C.POINTER(C.c_int8),
                                         C.c_size_t]),
@@ -78,6 +79,7 @@ class OracleLib:
                 "matcher_match_scan_window": (
                     C.c_double, [_vp, _dp, _dp, C.c_size_t, _dp, C.POINTER(C.c_int), _dp, _dp,
                                  C.c_size_t, C.c_size_t, _u64p]),
+                "find_nearest": (C.c_size_t, [_dp, C.c_size_t, C.c_longlong, _dp, C.c_double, _u64p, _dp]),
                 "laser_to_points": (C.c_size_t, [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_float,
                                                  C.c_double, _dp, _dp, C.c_int, _dp]),
                 "matcher_partial": (None, [_vp, _dp, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _dp]),
@@ -273,6 +275,24 @@ def laser_to_points(o: OracleLib, ranges, angle_min, angle_increment, range_max,
     n = o.laser_to_points(r.ctypes.data_as(C.POINTER(C.c_float)), r.shape[0], angle_min, angle_increment,
                           range_max, _d(lt), _d(tr), int(bool(inverted)), _d(out))
     return out[:n].copy()
+
+
+def scan_barycenter(o: OracleLib, pose3, points) -> np.ndarray:
+    """Scan::getBarycenterPose (scan.cpp:55-59, 72-91)."""
+    pose3, pts = _f64(pose3).reshape(3), _f64(points).reshape(-1, 2)
+    out = np.zeros(3)
+    o.scan_barycenter(_d(pose3), _d(pts), pts.shape[0], _d(out))
+    return out
+
+
+def find_nearest(o: OracleLib, scan_xy, query_xy, dist: float, limit_scan_index: int = -1):
+    """Graph::findNearest (graph.cpp:167-189), oracle restatement only -> (indices, squared distances)."""
+    xy, q = _f64(scan_xy).reshape(-1, 2), _f64(query_xy).reshape(2)
+    idx = np.zeros(max(xy.shape[0], 1), dtype=np.uint64)
+    d2 = np.zeros(max(xy.shape[0], 1))
+    n = o.find_nearest(_d(xy), xy.shape[0], int(limit_scan_index), _d(q), float(dist),
+                       idx.ctypes.data_as(_u64p), _d(d2))
+    return idx[:n].copy(), d2[:n].copy()
 
 
 # ---- oracle-only particle-filter helpers ---------------------------------

@@ -796,6 +796,66 @@ ORC_API size_t orc_pf_resample(
 }
 
 /* ------------------------------------------------------------------ */
+/* Candidate selection of the loop closure:        */
+/* Scan::update's barycenter (src/scan.cpp:72-91) and Graph::findNearest            */
+/* (src/graph.cpp:167-189).  findNearest runs nanoflann (un-vendored dependency,    */
+/* package.xml, version unpinned): KDTreeSingleIndexAdaptor<L2_Simple_Adaptor<double,*/
+/* GraphAdapter>, GraphAdapter, 2>::radiusSearch with default SearchParams.  Its     */
+/* published behaviour, restated: evalMetric = sum over the dimensions of            */
+/* (query[d] - point[d])^2 accumulated from 0 in dimension order; RadiusResultSet    */
+/* keeps a point when dist < radius (strict; radius is a SQUARED distance); the      */
+/* result is sorted by ascending distance (order among equal distances unspecified;  */
+/* here: ascending index).  graph.cpp cannot be compiled here (nanoflann, rosbag2)   */
+/* and no reference test calls it: findNearest is PARITY UNPINNED.                   */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_scan_barycenter(const double * pose3, const double * pts_xy, size_t n, double * out3)
+{
+  const double cos_theta = cos(pose3[2]), sin_theta = sin(pose3[2]); /* scan.cpp:74-75 */
+  out3[0] = pose3[0]; /* :78 */
+  out3[1] = pose3[1];
+  out3[2] = pose3[2];
+  if (n) {
+    double cx = 0.0, cy = 0.0;
+    for (size_t i = 0; i < n; ++i) { /* :82-86 */
+      cx += cos_theta * pts_xy[2 * i] - sin_theta * pts_xy[2 * i + 1];
+      cy += sin_theta * pts_xy[2 * i] + cos_theta * pts_xy[2 * i + 1];
+    }
+    out3[0] += cx / n; /* :87-88 */
+    out3[1] += cy / n;
+  }
+}
+
+ORC_API size_t orc_find_nearest(
+  const double * scan_xy, size_t n_scans, long long limit_scan_index, const double * query_xy,
+  double radius_sq, unsigned long long * out_indices, double * out_dist_sq)
+{
+  /* graph.cpp:171 */
+  size_t limit = (limit_scan_index > 0) ? (size_t)limit_scan_index : n_scans;
+  if (limit > n_scans) {limit = n_scans;}
+  size_t m = 0;
+  for (size_t i = 0; i < limit; ++i) {
+    double result = 0.0;
+    for (size_t d = 0; d < 2; ++d) {
+      const double diff = query_xy[d] - scan_xy[2 * i + d];
+      result += diff * diff;
+    }
+    if (result < radius_sq) {
+      /* insertion keeps (distance, index) ascending */
+      size_t k = m;
+      while (k > 0 && out_dist_sq[k - 1] > result) {
+        out_dist_sq[k] = out_dist_sq[k - 1];
+        out_indices[k] = out_indices[k - 1];
+        --k;
+      }
+      out_dist_sq[k] = result;
+      out_indices[k] = i;
+      ++m;
+    }
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------ */
 /* LaserScan -> Scan points (Mapper::laserCallback, src/ndt_mapper.cpp:385-453)   */
 /* SURVEY.md section 8(f) rank 3.  The reference code sits inside the ROS node and */
 /* cannot be compiled here, and no reference test covers it: this restatement is   */

@@ -86,6 +86,15 @@ static ndt_2d::ScanPtr make_scan(const double * pose, const double * pts_xy, siz
   return scan;
 }
 
+// Scan::getBarycenterPose (scan.cpp:55-59, 72-91) of the reference's own Scan class
+REF_API void ref_scan_barycenter(const double * pose3, const double * pts_xy, size_t n, double * out3)
+{
+  const ndt_2d::Pose2d b = make_scan(pose3, pts_xy, n)->getBarycenterPose();
+  out3[0] = b.x;
+  out3[1] = b.y;
+  out3[2] = b.theta;
+}
+
 REF_API void * ref_ndt_create(double cell, double sx, double sy, double ox, double oy)
 {
   return new ndt_2d::NDT(cell, sx, sy, ox, oy);

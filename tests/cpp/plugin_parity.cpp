@@ -9,12 +9,14 @@
 //
 //   plugin_parity            full comparison (needs a CUDA device), exit 0 = parity
 //   plugin_parity --no-gpu   checks that the B200 plugin fails loudly without a device
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #define private public
@@ -255,6 +257,36 @@ int main(int argc, char ** argv)
     for (auto & m : {ref, dev}) {
       m->reset();
       m->addScans(scans.begin(), scans.end());
+    }
+  }
+
+  // ---- candidate selection: Graph::findNearest (graph.cpp:167-189) -- nanoflann is not
+  // installed here, so the expectation is its radius search written out (squared L2 over the
+  // reference's own Scan poses / barycenters, dist < radius, nearest first)
+  {
+    auto * ours = dynamic_cast<ndt_2d_b200::ScanMatcherNDT *>(dev.get());
+    for (const bool bary : {false, true}) {
+      for (const int limit : {-1, 7}) {
+        const double radius_sq = 0.7;
+        const ndt_2d::Pose2d q = bary ? query->getBarycenterPose() : query->getPose();
+        std::vector<std::pair<double, size_t>> want;
+        const size_t lim = limit > 0 ? static_cast<size_t>(limit) : scans.size();
+        for (size_t i = 0; i < lim; ++i) {
+          const ndt_2d::Pose2d p = bary ? scans[i]->getBarycenterPose() : scans[i]->getPose();
+          double result = 0.0;
+          const double a[2] = {q.x, q.y}, b[2] = {p.x, p.y};
+          for (int d = 0; d < 2; ++d) {
+            const double diff = a[d] - b[d];
+            result += diff * diff;
+          }
+          if (result < radius_sq) {want.emplace_back(result, i);}
+        }
+        std::sort(want.begin(), want.end());
+        const std::vector<size_t> got = ours->findNearest(scans, query, radius_sq, limit, bary);
+        bool same = got.size() == want.size();
+        for (size_t k = 0; same && k < got.size(); ++k) {same = got[k] == want[k].second;}
+        expect(same && !want.empty() && want.size() < lim, "findNearest: same scans, same order");
+      }
     }
   }
 

@@ -84,7 +84,7 @@ def test_oracle_kd_tree_golden(oracle):
 
 # ----------------------------------------------------------------------------- GPU: CUDA path
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
 @pytest.mark.parametrize("name", MATCHER_CASES)
 def test_device_matches_reference_golden(gpu, name, variant):
     from ndt_2d_b200 import ScanMatcherNDT

@@ -167,7 +167,7 @@ def test_build_degenerate_cell_is_nan_like_reference(o):
 
 # ------------------------------------------------------------------ search
 @pytest.mark.parametrize("beams", [360, 100])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_match_scan_config1(o, beams, variant):
     w = synth.config1(laser_max_beams=beams)
     m = ScanMatcherNDT.from_params(w.params, kernel_variant=variant)
@@ -323,7 +323,7 @@ def test_random_small_worlds(o, seed):
     np.testing.assert_allclose(m.scorePoints(q, guess), mo.score_points(q, guess), rtol=RTOL, atol=ATOL_SCORE)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4])
+@pytest.mark.parametrize("variant", [0, 3, 4, 5])
 def test_long_scan_small_lattice(o, variant):
     """A 3,240-point scan (more than the dense kernel stages per pass, more than one chunk of
     the region kernel) on a small lattice."""
@@ -338,6 +338,41 @@ def test_long_scan_small_lattice(o, variant):
     so, do, wo, co, scores_o = mo.match_scan(w.query_pose, pts, want_scores=True)
     sg, dg, wg, cg, _ = m.match_scan_raw(w.query_pose, pts)
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(w.query_pose, pts), scores_o)
+
+
+WINDOW_CASES = [
+    # lin_res, lin_size, ndt_res, beams, guess offset      -- window kernel shape (variant 5)
+    (0.005, 0.05, 0.25, 100, (0.02, -0.03, 0.01)),      # K = 2: plugin defaults, 441 candidates = 4 CTAs per slice
+    (0.05, 0.25, 0.25, 360, (0.12, -0.07, 0.02)),       # K = 3: config 1's window
+    (0.04, 0.34, 0.25, 360, (0.0, 0.0, 0.0)),           # K = 4: 0.64 m window over 0.25 m cells
+    (0.03, 0.2, 0.1, 360, (0.05, 0.05, 0.0)),           # K = 4 again with small cells: 0.39 m / 0.1 m
+    (0.02, 0.1, 0.5, 1000, (0.3, -0.2, 0.05)),          # K = 2, every beam
+    (0.05, 0.25, 0.25, 360, (9.0, -8.5, 0.3)),          # window over the edge of the grid (most points outside)
+    (0.05, 0.25, 0.25, 360, (40.0, 40.0, 0.0)),         # scan entirely outside: every score 0, pose untouched
+    (0.1, 0.45, 0.1, 360, (0.0, 0.0, 0.0)),             # too wide (9 cells): falls back to the dense kernel
+]
+
+
+@pytest.mark.parametrize("case", range(len(WINDOW_CASES)))
+def test_window_kernel_shapes(o, case):
+    """search_window.cu (thread per candidate, per-point tables shared by the CTA) forced with
+    kernel_variant 5 over its K = 2 / 3 / 4 instantiations, several CTAs per slice, grid edges."""
+    lres, lsize, res, beams, off = WINDOW_CASES[case]
+    w = synth.config1()
+    p = dict(ndt_resolution=res, search_angular_resolution=0.005, search_angular_size=0.03,
+             search_linear_resolution=lres, search_linear_size=lsize, laser_max_beams=beams, range_max=10.0)
+    m = ScanMatcherNDT.from_params(p, kernel_variant=5)
+    mo = o.new_matcher(p)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    guess = w.true_pose - np.array(off)
+    so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+    sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+    if not wo:
+        assert not wg and sg == so
+        assert np.all(m.dump_scores(guess, w.query_points) == 0.0)
+        return
+    check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
 def test_theta_sliced_search_matches_full(o):
