@@ -11,15 +11,13 @@
 // ONCE per (theta slice, point) and shared by all candidates:
 //   phase A (thread per point): rotate + translate with the reference's operation order,
 //            exact padded cell of the window's first column / row (threshold tables);
-//            because the loop values are non-decreasing, "which cell does candidate
-//            column ix put this point in" is a step function of ix: its K - 1 steps
-//            (SPLIT INDICES: the number of columns whose exact coordinate
-//            outer.x + dlin[ix] stays below the next threshold) are found here with the
-//            reference's own additions, likewise for rows; plus occupancy + record rank
-//            of the K x K cells -> shared memory;
-//   phase B (thread per candidate): cell = integer comparisons of (ix, iy) with the
-//            point's split indices -- exact, no floating point --, record rank from the
-//            point's table, Gaussian exactly as the dense kernel evaluates it (double
+//            then, for every candidate column ix, which of the K columns of cells the
+//            exact coordinate outer.x + dlin[ix] (the reference's own addition) falls in
+//            -- one byte per ix, likewise per row iy --, plus occupancy + record rank of
+//            the K x K cells -> shared memory;
+//   phase B (thread per candidate): cell = the point's byte for its ix + the byte for its
+//            iy (exact, no floating point), record rank from the point's table, Gaussian
+//            exactly as the dense kernel evaluates it (double
 //            differences and quadratic form, 2^t on the SFU), summed in scan-point order
 //            like the reference's own loop (float blocks of 8 points into a double).
 // A CTA = a tile of <= 128 candidates of one theta slice x G groups of threads that split
@@ -41,19 +39,21 @@ using namespace ndt2d_dev;
 
 constexpr uint32_t kWinTile = 128;               // candidates per CTA (at most)
 constexpr uint32_t kWinMaxThreads = 512;         // tile x point groups, rounded up to a warp
+constexpr uint32_t kWinBatchThreads = 256;       // the same for the CTAs of a batch launch
 constexpr uint32_t kWinMaxK = 4;
-constexpr uint32_t kWinMaxLin = 512;             // loop values staged in shared memory
+constexpr uint32_t kWinMaxLin = 64;              // steps per axis (byte tables per point)
 constexpr uint32_t kWinSmemBytes = 32 * 1024;    // point tables of one pass (+ 11.5 KB static < 48 KB)
 constexpr uint32_t kWinBlockPts = 8;             // points per float accumulation block
 
-__host__ __device__ constexpr uint32_t win_point_bytes(uint32_t K)
+// Shared-memory bytes per scan point: outer (double2), K * K ranks, padded index of the
+// first cell, and the two byte tables (n_lin rounded up to a multiple of 4 each).
+__host__ __device__ inline uint32_t win_point_bytes(uint32_t K, uint32_t n_lin)
 {
-  // outer (double2) + split indices (2 x 4 u16) + K * K ranks + padded index of the first cell
-  return 16u + 16u + 4u * K * K + 4u;
+  return 16u + 4u * K * K + 4u + 2u * ((n_lin + 3u) & ~3u);
 }
-__host__ __device__ constexpr uint32_t win_pass_points(uint32_t K)
+__host__ __device__ inline uint32_t win_pass_points(uint32_t K, uint32_t n_lin)
 {
-  return (kWinSmemBytes / win_point_bytes(K)) & ~31u;
+  return (kWinSmemBytes / win_point_bytes(K, n_lin)) & ~31u;
 }
 
 template<uint32_t K>
@@ -61,18 +61,21 @@ __device__ __forceinline__ void window_block(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t tile,
   uint32_t n_groups, double * __restrict__ block_partials, double * __restrict__ scores)
 {
-  constexpr uint32_t PP = win_pass_points(K), KK = K * K;
+  constexpr uint32_t KK = K * K;
+  const uint32_t n_lin = sv.n_lin, n_cand = n_lin * n_lin;
+  const uint32_t LT = (n_lin + 3u) & ~3u;                     // bytes per axis table
+  const uint32_t PP = win_pass_points(K, n_lin);
   extern __shared__ __align__(16) unsigned char win_smem[];
   double2 * outer = reinterpret_cast<double2 *>(win_smem);
-  uint4 * split = reinterpret_cast<uint4 *>(outer + PP);       // .x .y: x splits, .z .w: y splits (u16 each)
-  int32_t * rank = reinterpret_cast<int32_t *>(split + PP);
+  int32_t * rank = reinterpret_cast<int32_t *>(outer + PP);
   uint32_t * base = reinterpret_cast<uint32_t *>(rank + static_cast<size_t>(PP) * KK);
+  uint8_t * kx = reinterpret_cast<uint8_t *>(base + PP);      // [point][ix] = column of cells (0 .. K-1)
+  uint8_t * ky = kx + static_cast<size_t>(PP) * LT;           // [point][iy] = row of cells * K
   __shared__ double group_sums[kWinMaxThreads];
   __shared__ double dlin_s[kWinMaxLin];
 
   const uint32_t itheta = theta_begin + blockIdx.y * sv.theta_stride;
   const double2 cs = sv.trig[itheta];
-  const uint32_t n_lin = sv.n_lin, n_cand = n_lin * n_lin;
   const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y, pitch = mv.g.pitch;
   const double inv_cell = 1.0 / mv.g.cell_size;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -104,26 +107,25 @@ __device__ __forceinline__ void window_block(
       const uint32_t by = padded_coord_thr_g(__dadd_rn(o.y, dlin_s[0]), mv.thr_y, size_y, mv.g.origin_y, inv_cell);
       // upper bounds of the cells bx .. bx + K - 2 (thr[size + 1] = +inf: nothing lies beyond)
       double tx[K - 1u], ty[K - 1u];
-      uint32_t sx[3] = {0xffffu, 0xffffu, 0xffffu}, sy[3] = {0xffffu, 0xffffu, 0xffffu};
 #pragma unroll
       for (uint32_t j = 0; j < K - 1u; ++j) {
         tx[j] = (bx + j <= size_x + 1u) ? __ldg(mv.thr_x + bx + j) : inf;
         ty[j] = (by + j <= size_y + 1u) ? __ldg(mv.thr_y + by + j) : inf;
-        sx[j] = 0u;
-        sy[j] = 0u;
       }
-      // split indices: candidates [0, s_j) stay below threshold j (scan_matcher_ndt.cpp:123-124:
-      // the candidate's coordinate is outer + d, one rounding)
+      // cell column / row of every candidate column / row: the candidate's coordinate is
+      // outer + d, one rounding (scan_matcher_ndt.cpp:123-124), counted against the thresholds
       for (uint32_t k = 0; k < n_lin; ++k) {
         const double d = dlin_s[k];
         const double xa = __dadd_rn(o.x, d), ya = __dadd_rn(o.y, d);
+        uint32_t ccx = 0, ccy = 0;
 #pragma unroll
         for (uint32_t j = 0; j < K - 1u; ++j) {
-          sx[j] += (xa < tx[j]) ? 1u : 0u;
-          sy[j] += (ya < ty[j]) ? 1u : 0u;
+          ccx += (xa >= tx[j]) ? 1u : 0u;
+          ccy += (ya >= ty[j]) ? 1u : 0u;
         }
+        kx[i * LT + k] = static_cast<uint8_t>(ccx);
+        ky[i * LT + k] = static_cast<uint8_t>(ccy * K);
       }
-      split[i] = make_uint4(sx[0] | (sx[1] << 16), sx[2], sy[0] | (sy[1] << 16), sy[2]);
       base[i] = by * pitch + bx;
 #pragma unroll
       for (uint32_t cy = 0; cy < K; ++cy) {
@@ -147,39 +149,32 @@ __device__ __forceinline__ void window_block(
     if (active) {
       const uint32_t per_group = (np + n_groups - 1u) / n_groups;
       const uint32_t i_end = min(np, (group + 1u) * per_group);
+      // one (candidate, point) evaluation -> its likelihood as a float (0 for an unoccupied cell)
+      auto eval = [&](uint32_t i) -> float {
+          const uint32_t k = static_cast<uint32_t>(kx[i * LT + ix]) + static_cast<uint32_t>(ky[i * LT + iy]);
+          const int32_t r = rank[i * KK + k];
+          // unoccupied cell: evaluate record 0 and drop the result -- cheaper than diverging
+          const double2 * f2 = reinterpret_cast<const double2 *>(
+            mv.rec_fast + static_cast<size_t>(max(r, 0)) * NDT2D_REC_DOUBLES);
+          const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
+          const double2 o = outer[i];
+          const double x = __dadd_rn(o.x, dx), y = __dadd_rn(o.y, dy);   // scan_matcher_ndt.cpp:123-124
+          const double qx = x - mean.x, qy = y - mean.y;
+          const double e = qx * (AB.x * qx + AB.y * qy) + (Ds.x * qy) * qy;   // log2 of the likelihood
+          float f;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(static_cast<float>(e)));
+          const bool stiff = ((__double2hiint(Ds.y) & 0x7fffffff) | __double2loint(Ds.y)) != 0;
+          if (r >= 0 && stiff) {
+            // stiff cell: the reference's own grouping (see search_common.cuh)
+            f = 0.0f;
+            acc += cell_likelihood(mv.occ, mv.rec, base[i] + (k / K) * pitch + (k % K), x, y);
+          }
+          return (r >= 0) ? f : 0.0f;
+        };
       for (uint32_t i0 = group * per_group; i0 < i_end; i0 += kWinBlockPts) {
         const uint32_t i1 = min(i_end, i0 + kWinBlockPts);
         float blk = 0.0f;
-        for (uint32_t i = i0; i < i1; ++i) {
-          const uint4 sp = split[i];
-          uint32_t cx = (ix >= (sp.x & 0xffffu)) ? 1u : 0u, cy = (iy >= (sp.z & 0xffffu)) ? 1u : 0u;
-          if (K > 2u) {
-            cx += (ix >= (sp.x >> 16)) ? 1u : 0u;
-            cy += (iy >= (sp.z >> 16)) ? 1u : 0u;
-          }
-          if (K > 3u) {
-            cx += (ix >= sp.y) ? 1u : 0u;
-            cy += (iy >= sp.w) ? 1u : 0u;
-          }
-          const int32_t r = rank[i * KK + cy * K + cx];
-          if (r >= 0) {
-            const double2 * f2 = reinterpret_cast<const double2 *>(
-              mv.rec_fast + static_cast<size_t>(r) * NDT2D_REC_DOUBLES);
-            const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
-            const double2 o = outer[i];
-            const double x = __dadd_rn(o.x, dx), y = __dadd_rn(o.y, dy);   // scan_matcher_ndt.cpp:123-124
-            if ((__double2hiint(Ds.y) & 0x7fffffff) == 0 && __double2loint(Ds.y) == 0) {
-              const double qx = x - mean.x, qy = y - mean.y;
-              const double e = qx * (AB.x * qx + AB.y * qy) + (Ds.x * qy) * qy;   // log2 of the likelihood
-              float f;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(static_cast<float>(e)));
-              blk += f;
-            } else {
-              // stiff cell: the reference's own grouping (see search_common.cuh)
-              acc += cell_likelihood(mv.occ, mv.rec, base[i] + cy * pitch + cx, x, y);
-            }
-          }
-        }
+        for (uint32_t i = i0; i < i1; ++i) {blk += eval(i);}
         acc += static_cast<double>(blk);
       }
     }
@@ -236,22 +231,20 @@ struct WinShape
 {
   uint32_t tile, tiles, groups, threads;
 };
-WinShape window_shape(uint32_t n_lin)
+WinShape window_shape(uint32_t n_lin, uint32_t max_threads)
 {
   const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
   WinShape w;
   w.tile = n_cand < kWinTile ? static_cast<uint32_t>(n_cand ? n_cand : 1u) : kWinTile;
   w.tiles = static_cast<uint32_t>((n_cand + w.tile - 1) / w.tile);
-  w.groups = kWinMaxThreads / w.tile;
+  w.groups = max_threads / w.tile;
   w.threads = (w.tile * w.groups + 31u) & ~31u;
   return w;
 }
 
-size_t window_smem(uint32_t K)
+size_t window_smem(uint32_t K, uint32_t n_lin)
 {
-  return static_cast<size_t>(K == 2 ? win_pass_points(2) * win_point_bytes(2) :
-         K == 3 ? win_pass_points(3) * win_point_bytes(3) :
-         win_pass_points(4) * win_point_bytes(4));
+  return static_cast<size_t>(win_pass_points(K, n_lin)) * win_point_bytes(K, n_lin);
 }
 
 }  // namespace
@@ -270,7 +263,7 @@ uint32_t ndt2d_window_cells(double cell_size, uint32_t n_lin, double linear_res)
 
 uint32_t ndt2d_window_records(uint32_t n_theta, uint32_t n_lin)
 {
-  const uint64_t r = static_cast<uint64_t>(n_theta) * window_shape(n_lin).tiles;
+  const uint64_t r = static_cast<uint64_t>(n_theta) * window_shape(n_lin, kWinMaxThreads).tiles;
   return r > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(r);
 }
 
@@ -279,7 +272,7 @@ int ndt2d_launch_search_window(
   double * d_block_partials, double * d_scores, cudaStream_t stream, Counters * ctr)
 {
   if (K < 2 || K > kWinMaxK) {return NDT2D_ERR_INVALID;}
-  const WinShape ws = window_shape(sv.n_lin);
+  const WinShape ws = window_shape(sv.n_lin, kWinMaxThreads);   // one search: shortest serial loop
   const uint32_t bx = ws.tiles;
   const uint32_t stride = sv.theta_stride ? sv.theta_stride : 1u;
   uint32_t done = 0;
@@ -289,13 +282,13 @@ int ndt2d_launch_search_window(
     double * out = d_block_partials + static_cast<size_t>(done) * bx * NDT2D_BLOCK_PARTIAL;
     const uint32_t tb = theta_begin + done * stride;
     if (K == 2) {
-      search_window_kernel<2><<<grid, ws.threads, window_smem(2), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
+      search_window_kernel<2><<<grid, ws.threads, window_smem(2, sv.n_lin), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
         d_scores);
     } else if (K == 3) {
-      search_window_kernel<3><<<grid, ws.threads, window_smem(3), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
+      search_window_kernel<3><<<grid, ws.threads, window_smem(3, sv.n_lin), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
         d_scores);
     } else {
-      search_window_kernel<4><<<grid, ws.threads, window_smem(4), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
+      search_window_kernel<4><<<grid, ws.threads, window_smem(4, sv.n_lin), stream>>>(mv, sv, tb, ws.tile, ws.groups, out,
         d_scores);
     }
     NDT2D_LAUNCH_CHECK(ctr);
@@ -311,14 +304,18 @@ int ndt2d_launch_search_window_batch(
   if (n_batch == 0 || n_ang == 0 || n_lin == 0) {return NDT2D_OK;}
   if (K < 2 || K > kWinMaxK) {return NDT2D_ERR_INVALID;}
   if (n_ang > 65535u || n_batch > 65535u) {return NDT2D_ERR_SIZE;}
-  const WinShape ws = window_shape(n_lin);
+  // a batch has CTAs to spare: smaller ones overlap the two phases of different CTAs better
+  const WinShape ws = window_shape(n_lin, kWinBatchThreads);
   dim3 grid(ws.tiles, n_ang, n_batch);
   if (K == 2) {
-    search_window_batch_kernel<2><<<grid, ws.threads, window_smem(2), stream>>>(d_batch, ws.tile, ws.groups);
+    search_window_batch_kernel<2><<<grid, ws.threads, window_smem(2, n_lin), stream>>>(d_batch, ws.tile,
+      ws.groups);
   } else if (K == 3) {
-    search_window_batch_kernel<3><<<grid, ws.threads, window_smem(3), stream>>>(d_batch, ws.tile, ws.groups);
+    search_window_batch_kernel<3><<<grid, ws.threads, window_smem(3, n_lin), stream>>>(d_batch, ws.tile,
+      ws.groups);
   } else {
-    search_window_batch_kernel<4><<<grid, ws.threads, window_smem(4), stream>>>(d_batch, ws.tile, ws.groups);
+    search_window_batch_kernel<4><<<grid, ws.threads, window_smem(4, n_lin), stream>>>(d_batch, ws.tile,
+      ws.groups);
   }
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
