@@ -45,11 +45,16 @@ constexpr uint32_t kWinMaxLin = 64;              // steps per axis (byte tables 
 constexpr uint32_t kWinSmemBytes = 32 * 1024;    // point tables of one pass (+ 11.5 KB static < 48 KB)
 constexpr uint32_t kWinBlockPts = 8;             // points per float accumulation block
 
-// Shared-memory bytes per scan point: outer (double2), K * K ranks, padded index of the
-// first cell, and the two byte tables (n_lin rounded up to a multiple of 4 each).
+// One shared-memory record per scan point (16-byte aligned, all tables of a point side by
+// side so that the candidate loop advances ONE pointer per point):
+//   +0            outer (double2)
+//   +16           K * K record ranks (int32, -1 = unoccupied)
+//   +16 + 4 K K   padded index of the first cell (uint32)
+//   +20 + 4 K K   byte per candidate column: cell column 0 .. K-1   (LT bytes, LT = n_lin up to a multiple of 4)
+//   ... + LT      byte per candidate row: cell row * K              (LT bytes)
 __host__ __device__ inline uint32_t win_point_bytes(uint32_t K, uint32_t n_lin)
 {
-  return 16u + 4u * K * K + 4u + 2u * ((n_lin + 3u) & ~3u);
+  return (20u + 4u * K * K + 2u * ((n_lin + 3u) & ~3u) + 15u) & ~15u;
 }
 __host__ __device__ inline uint32_t win_pass_points(uint32_t K, uint32_t n_lin)
 {
@@ -66,11 +71,9 @@ __device__ __forceinline__ void window_block(
   const uint32_t LT = (n_lin + 3u) & ~3u;                     // bytes per axis table
   const uint32_t PP = win_pass_points(K, n_lin);
   extern __shared__ __align__(16) unsigned char win_smem[];
-  double2 * outer = reinterpret_cast<double2 *>(win_smem);
-  int32_t * rank = reinterpret_cast<int32_t *>(outer + PP);
-  uint32_t * base = reinterpret_cast<uint32_t *>(rank + static_cast<size_t>(PP) * KK);
-  uint8_t * kx = reinterpret_cast<uint8_t *>(base + PP);      // [point][ix] = column of cells (0 .. K-1)
-  uint8_t * ky = kx + static_cast<size_t>(PP) * LT;           // [point][iy] = row of cells * K
+  const uint32_t S = win_point_bytes(K, n_lin);                // bytes per point record
+  constexpr uint32_t kOffRank = 16u, kOffBase = 16u + 4u * KK, kOffKx = 20u + 4u * KK;
+  const uint32_t off_ky = kOffKx + LT;
   __shared__ double group_sums[kWinMaxThreads];
   __shared__ double dlin_s[kWinMaxLin];
 
@@ -79,6 +82,9 @@ __device__ __forceinline__ void window_block(
   const uint32_t size_x = mv.g.size_x, size_y = mv.g.size_y, pitch = mv.g.pitch;
   const double inv_cell = 1.0 / mv.g.cell_size;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  // (in registers: for a batch launch mv / sv live in shared memory)
+  const double * const rec_fast = mv.rec_fast;
+  const uint2 * const occ = mv.occ;
 
   for (uint32_t k = threadIdx.x; k < n_lin; k += blockDim.x) {dlin_s[k] = sv.dlin[k];}
 
@@ -101,7 +107,8 @@ __device__ __forceinline__ void window_block(
       // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y  (scan_matcher_ndt.cpp:111-114)
       o.x = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
       o.y = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-      outer[i] = o;
+      unsigned char * const rec_i = win_smem + static_cast<size_t>(i) * S;
+      *reinterpret_cast<double2 *>(rec_i) = o;
       // padded cell of the window's first column / row
       const uint32_t bx = padded_coord_thr_g(__dadd_rn(o.x, dlin_s[0]), mv.thr_x, size_x, mv.g.origin_x, inv_cell);
       const uint32_t by = padded_coord_thr_g(__dadd_rn(o.y, dlin_s[0]), mv.thr_y, size_y, mv.g.origin_y, inv_cell);
@@ -123,10 +130,10 @@ __device__ __forceinline__ void window_block(
           ccx += (xa >= tx[j]) ? 1u : 0u;
           ccy += (ya >= ty[j]) ? 1u : 0u;
         }
-        kx[i * LT + k] = static_cast<uint8_t>(ccx);
-        ky[i * LT + k] = static_cast<uint8_t>(ccy * K);
+        rec_i[kOffKx + k] = static_cast<uint8_t>(ccx);
+        rec_i[off_ky + k] = static_cast<uint8_t>(ccy * K);
       }
-      base[i] = by * pitch + bx;
+      *reinterpret_cast<uint32_t *>(rec_i + kOffBase) = by * pitch + bx;
 #pragma unroll
       for (uint32_t cy = 0; cy < K; ++cy) {
 #pragma unroll
@@ -134,13 +141,13 @@ __device__ __forceinline__ void window_block(
           int32_t r = -1;
           if (bx + cx <= size_x + 1u && by + cy <= size_y + 1u) {
             const uint32_t pidx = (by + cy) * pitch + bx + cx;
-            const uint2 w = __ldg(mv.occ + (pidx >> 5));
+            const uint2 w = __ldg(occ + (pidx >> 5));
             const uint32_t bit = pidx & 31u;
             if ((w.x >> bit) & 1u) {
               r = static_cast<int32_t>(w.y + __popc(w.x & ((1u << bit) - 1u)));
             }
           }
-          rank[i * KK + cy * K + cx] = r;
+          reinterpret_cast<int32_t *>(rec_i + kOffRank)[cy * K + cx] = r;
         }
       }
     }
@@ -149,32 +156,46 @@ __device__ __forceinline__ void window_block(
     if (active) {
       const uint32_t per_group = (np + n_groups - 1u) / n_groups;
       const uint32_t i_end = min(np, (group + 1u) * per_group);
-      // one (candidate, point) evaluation -> its likelihood as a float (0 for an unoccupied cell)
-      auto eval = [&](uint32_t i) -> float {
-          const uint32_t k = static_cast<uint32_t>(kx[i * LT + ix]) + static_cast<uint32_t>(ky[i * LT + iy]);
-          const int32_t r = rank[i * KK + k];
-          // unoccupied cell: evaluate record 0 and drop the result -- cheaper than diverging
-          const double2 * f2 = reinterpret_cast<const double2 *>(
-            mv.rec_fast + static_cast<size_t>(max(r, 0)) * NDT2D_REC_DOUBLES);
-          const double2 mean = __ldg(f2), AB = __ldg(f2 + 1), Ds = __ldg(f2 + 2);
-          const double2 o = outer[i];
+      int32_t r_cached = -1;
+      bool stiff_cached = false;
+      double2 mean = make_double2(0.0, 0.0), AB = mean, Ds = mean;
+      const uint32_t i_begin = min(np, group * per_group);
+      // one pointer walks the point records; this candidate's two bytes sit at fixed offsets
+      const unsigned char * prec = win_smem + static_cast<size_t>(i_begin) * S;
+      const uint32_t my_kx = kOffKx + ix, my_ky = off_ky + iy;
+      for (uint32_t i0 = i_begin; i0 < i_end; i0 += kWinBlockPts) {
+        const uint32_t n_blk = min(i_end - i0, kWinBlockPts);
+        float blk = 0.0f;
+        for (uint32_t j = 0; j < n_blk; ++j, prec += S) {
+          // one (candidate, point) evaluation
+          const uint32_t k = static_cast<uint32_t>(prec[my_kx]) + static_cast<uint32_t>(prec[my_ky]);
+          const int32_t r = reinterpret_cast<const int32_t *>(prec + kOffRank)[k];
+          // consecutive beams mostly stay in one cell: the record is fetched only when this
+          // candidate's cell changes; an unoccupied cell evaluates the record at hand and drops
+          // the result -- cheaper than diverging around the arithmetic
+          if (r >= 0 && r != r_cached) {
+            const double2 * f2 = reinterpret_cast<const double2 *>(
+              rec_fast + static_cast<size_t>(r) * NDT2D_REC_DOUBLES);
+            mean = __ldg(f2);
+            AB = __ldg(f2 + 1);
+            Ds = __ldg(f2 + 2);
+            r_cached = r;
+            stiff_cached = ((__double2hiint(Ds.y) & 0x7fffffff) | __double2loint(Ds.y)) != 0;
+          }
+          const double2 o = *reinterpret_cast<const double2 *>(prec);
           const double x = __dadd_rn(o.x, dx), y = __dadd_rn(o.y, dy);   // scan_matcher_ndt.cpp:123-124
           const double qx = x - mean.x, qy = y - mean.y;
           const double e = qx * (AB.x * qx + AB.y * qy) + (Ds.x * qy) * qy;   // log2 of the likelihood
           float f;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(static_cast<float>(e)));
-          const bool stiff = ((__double2hiint(Ds.y) & 0x7fffffff) | __double2loint(Ds.y)) != 0;
-          if (r >= 0 && stiff) {
+          if (r >= 0 && stiff_cached) {
             // stiff cell: the reference's own grouping (see search_common.cuh)
             f = 0.0f;
-            acc += cell_likelihood(mv.occ, mv.rec, base[i] + (k / K) * pitch + (k % K), x, y);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(prec + kOffBase);
+            acc += cell_likelihood(occ, mv.rec, b0 + (k / K) * pitch + (k % K), x, y);
           }
-          return (r >= 0) ? f : 0.0f;
-        };
-      for (uint32_t i0 = group * per_group; i0 < i_end; i0 += kWinBlockPts) {
-        const uint32_t i1 = min(i_end, i0 + kWinBlockPts);
-        float blk = 0.0f;
-        for (uint32_t i = i0; i < i1; ++i) {blk += eval(i);}
+          blk += (r >= 0) ? f : 0.0f;
+        }
         acc += static_cast<double>(blk);
       }
     }
