@@ -187,6 +187,12 @@ struct ndt2d_matcher
   double pose_x = 0, pose_y = 0;
   uint32_t n_pts = 0;
   size_t trig_offset_bytes = 0;     // (cos, sin) table inside d_pts, after the points
+  // staged API: the (cos, sin) of a theta slice is computed and uploaded when a search first
+  // asks for it (a rank of a sharded search only ever needs its own slices)
+  bool trig_lazy = false;
+  double pose_th = 0.0;
+  std::vector<double> h_trig_all;   // host mirror, 2 * n_ang
+  std::vector<uint8_t> trig_done;
 
   PinnedBuffer h_stage, h_result;
   // Pipelined mode (match_scan_batch): host staging comes from a pinned arena that is
@@ -478,7 +484,8 @@ int add_scans_impl(
   return NDT2D_OK;
 }
 
-int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts)
+int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  bool lazy_trig = false)
 {
   const size_t n_use = subsample_count(m, npts);
   if (n_use >= (1u << 30)) {return NDT2D_ERR_SIZE;}
@@ -486,25 +493,32 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   const size_t pts_bytes = n_use * sizeof(double2);
   const size_t trig_bytes = n_ang * sizeof(double2);
   char * hs = nullptr;
-  int rc = stage_alloc(m, pts_bytes + trig_bytes + 64, &hs);
+  const size_t up_bytes = pts_bytes + (lazy_trig ? 0 : trig_bytes);
+  int rc = stage_alloc(m, up_bytes + 64, &hs);
   if (rc) {return rc;}
   // points and per-theta (cos, sin) share one device buffer: one H2D copy per scan
   if ((rc = m->d_pts.ensure(pts_bytes + trig_bytes + 16))) {return rc;}
   double * h_pts = reinterpret_cast<double *>(hs);
   double * h_trig = h_pts + 2 * n_use;
   if (n_use) {subsample_points(pts_xy, npts, n_use, h_pts);}
-  for (size_t k = 0; k < n_ang; ++k) {
-    // scan_matcher_ndt.cpp:106-107
-    h_trig[2 * k] = cos(pose3[2] + m->dth[k]);
-    h_trig[2 * k + 1] = sin(pose3[2] + m->dth[k]);
+  m->trig_lazy = lazy_trig;
+  m->pose_th = pose3[2];
+  if (lazy_trig) {
+    m->h_trig_all.assign(2 * n_ang, 0.0);
+    m->trig_done.assign(n_ang, 0);
+  } else {
+    for (size_t k = 0; k < n_ang; ++k) {
+      // scan_matcher_ndt.cpp:106-107
+      h_trig[2 * k] = cos(pose3[2] + m->dth[k]);
+      h_trig[2 * k + 1] = sin(pose3[2] + m->dth[k]);
+    }
   }
   cudaStream_t st = m->stream;
-  if (pts_bytes + trig_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes + trig_bytes, cudaMemcpyHostToDevice,
-      st));
+  if (up_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, up_bytes, cudaMemcpyHostToDevice, st));
   }
   m->trig_offset_bytes = pts_bytes;
-  m->ctr.h2d_bytes += pts_bytes + trig_bytes;
+  m->ctr.h2d_bytes += up_bytes;
   m->pose_x = pose3[0];
   m->pose_y = pose3[1];
   m->n_pts = static_cast<uint32_t>(n_use);
@@ -564,6 +578,41 @@ int fetch_result_locked(ndt2d_matcher * m, double * r32)
   NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
   m->ctr.d2h_bytes += 32 * sizeof(double);
   memcpy(r32, h, 32 * sizeof(double));
+  return NDT2D_OK;
+}
+
+// (cos, sin) of the theta slices begin, begin + stride, ... < end of a lazily staged scan:
+// the missing ones are computed on the host (libm, scan_matcher_ndt.cpp:106-107) into the
+// mirror, then the covering range of the mirror is uploaded -- entries of other slices in
+// that range are either already valid or never read before they are computed.
+int ensure_trig_locked(ndt2d_matcher * m, size_t begin, size_t end, size_t stride)
+{
+  if (!m->trig_lazy || begin >= end) {return NDT2D_OK;}
+  size_t lo = end, hi = begin;
+  for (size_t k = begin; k < end; k += stride) {
+    if (m->trig_done[k]) {continue;}
+    m->h_trig_all[2 * k] = cos(m->pose_th + m->dth[k]);
+    m->h_trig_all[2 * k + 1] = sin(m->pose_th + m->dth[k]);
+    m->trig_done[k] = 1;
+    lo = std::min(lo, k);
+    hi = std::max(hi, k);
+  }
+  if (lo > hi) {return NDT2D_OK;}
+  const size_t bytes = (hi - lo + 1) * sizeof(double2);
+  // staged from the pinned arena (recycled only after a stream synchronisation): the search
+  // that follows is enqueued without waiting for this copy
+  char * hs = nullptr;
+  int rc = m->h_arena.ensure(size_t(8) << 20);
+  if (rc) {return rc;}
+  const bool was_pipelined = m->pipelined;
+  m->pipelined = true;
+  rc = stage_alloc(m, bytes, &hs);
+  m->pipelined = was_pipelined;
+  if (rc) {return rc;}
+  memcpy(hs, m->h_trig_all.data() + 2 * lo, bytes);
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.as<char>() + m->trig_offset_bytes + lo * sizeof(double2), hs,
+    bytes, cudaMemcpyHostToDevice, m->stream));
+  m->ctr.h2d_bytes += bytes;
   return NDT2D_OK;
 }
 
@@ -1326,7 +1375,7 @@ NDT2D_API int ndt2d_matcher_stage_scan(
   if (!m || !pose3 || (npts && !pts_xy)) {return NDT2D_ERR_INVALID;}
   std::lock_guard<std::mutex> lock(m->mu);
   DeviceGuard guard(m->device);
-  return stage_scan_locked(m, pose3, pts_xy, npts);
+  return stage_scan_locked(m, pose3, pts_xy, npts, true);
 }
 
 NDT2D_API int ndt2d_matcher_search_staged_strided(
@@ -1340,9 +1389,11 @@ NDT2D_API int ndt2d_matcher_search_staged_strided(
   const uint64_t n_ang = m->dth.size();
   if (theta_begin > theta_end || theta_end > n_ang) {return NDT2D_ERR_INVALID;}
   DeviceGuard guard(m->device);
+  int rc = ensure_trig_locked(m, theta_begin, theta_end, theta_stride);
+  if (rc) {return rc;}
   SearchView sv = search_view(m);
   sv.theta_stride = static_cast<uint32_t>(theta_stride);
-  int rc = ndt2d_launch_search(model_view(m), sv, static_cast<uint32_t>(theta_begin),
+  rc = ndt2d_launch_search(model_view(m), sv, static_cast<uint32_t>(theta_begin),
       static_cast<uint32_t>(theta_end), m->prm.kernel_variant, m->d_blockpart.as<double>(),
       m->d_partial.as<double>(), nullptr, m->d_counter.as<uint32_t>(), m->stream, &m->ctr,
       m->ev_begin, m->ev_end);
@@ -1426,6 +1477,10 @@ NDT2D_API int ndt2d_matcher_search_exchange(
   const uint64_t n_ang = m->dth.size();
   if (theta_begin > theta_end || theta_end > n_ang) {return NDT2D_ERR_INVALID;}
   DeviceGuard guard(m->device);
+  {
+    const int trc = ensure_trig_locked(m, theta_begin, theta_end, theta_stride);
+    if (trc) {return trc;}
+  }
   SearchView sv = search_view(m);
   sv.theta_stride = static_cast<uint32_t>(theta_stride);
   ExchangeView xv;
