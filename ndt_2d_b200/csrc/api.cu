@@ -494,7 +494,18 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
   const size_t trig_bytes = n_ang * sizeof(double2);
   char * hs = nullptr;
   const size_t up_bytes = pts_bytes + (lazy_trig ? 0 : trig_bytes);
-  int rc = stage_alloc(m, up_bytes + 64, &hs);
+  // small uploads are staged from the pinned arena (recycled only after a stream
+  // synchronisation), so the search is enqueued right behind the copy without waiting for it
+  const bool from_arena = m->pipelined || up_bytes + 64 <= (size_t(1) << 20);
+  int rc = NDT2D_OK;
+  if (from_arena && !m->pipelined) {
+    if ((rc = m->h_arena.ensure(size_t(8) << 20))) {return rc;}
+    m->pipelined = true;
+    rc = stage_alloc(m, up_bytes + 64, &hs);
+    m->pipelined = false;
+  } else {
+    rc = stage_alloc(m, up_bytes + 64, &hs);
+  }
   if (rc) {return rc;}
   // points and per-theta (cos, sin) share one device buffer: one H2D copy per scan
   if ((rc = m->d_pts.ensure(pts_bytes + trig_bytes + 16))) {return rc;}
@@ -548,8 +559,8 @@ int stage_scan_locked(ndt2d_matcher * m, const double * pose3, const double * pt
     if (cd && (rc = m->d_chunk.ensure(cd * sizeof(double)))) {return rc;}
   }
   if ((rc = m->h_result.ensure(64 * sizeof(double)))) {return rc;}
-  // the pinned staging area is reused by the next call: wait for the copies
-  if (!m->pipelined) {
+  // the single pinned staging buffer is reused by the next call: wait for the copies
+  if (!from_arena) {
     NDT2D_CUDA_TRY(cudaStreamSynchronize(st));
   }
   m->staged = true;
