@@ -138,3 +138,84 @@ class ShardedSearch:
         self.m.stage_scan(pose, points)
         self.search_staged()
         return self.result()
+
+
+# ----------------------------------------------------------------------------------------------
+# Loop-closure batch over several ranks ("for config 3 alternatively split the
+# candidates"): the jobs of ndt2d_matcher_match_scan_batch are independent, so rank r takes jobs
+# r, r + world, ... and ONE all-gather of the 14-double result rows puts every job's result on
+# every rank.  No exchange inside a job.
+RESULT_DOUBLES = 14     # score, delta_written, delta[3], covariance[9]
+
+
+def job_slice(n_jobs: int, rank: int, world: int) -> np.ndarray:
+    """Indices of the jobs `rank` runs (interleaved: jobs are sorted by distance, so neighbours cost alike)."""
+    return np.arange(min(rank, n_jobs), n_jobs, world, dtype=np.int64)
+
+
+def select_jobs(jobs, job_scan_offsets, map_poses, map_offsets, map_points, query_poses, query_offsets,
+                query_points):
+    """The match_scan_batch arguments restricted to `jobs` (offsets rebased, order kept)."""
+    so = np.asarray(job_scan_offsets, dtype=np.int64)
+    mo = np.asarray(map_offsets, dtype=np.int64)
+    qo = np.asarray(query_offsets, dtype=np.int64)
+    mp_, qp = L.f64(map_poses).reshape(-1, 3), L.f64(query_poses).reshape(-1, 3)
+    mpts, qpts = L.f64(map_points).reshape(-1, 2), L.f64(query_points).reshape(-1, 2)
+    out_so, out_mo, out_qo = [0], [0], [0]
+    poses, pts, qposes, qs = [], [], [], []
+    for j in jobs:
+        s0, s1 = int(so[j]), int(so[j + 1])
+        for s in range(s0, s1):
+            poses.append(mp_[s])
+            pts.append(mpts[int(mo[s]):int(mo[s + 1])])
+            out_mo.append(out_mo[-1] + int(mo[s + 1] - mo[s]))
+        out_so.append(out_so[-1] + (s1 - s0))
+        qposes.append(qp[j])
+        qs.append(qpts[int(qo[j]):int(qo[j + 1])])
+        out_qo.append(out_qo[-1] + int(qo[j + 1] - qo[j]))
+    cat = lambda parts, width: np.concatenate(parts) if parts else np.zeros((0, width))   # noqa: E731
+    return (np.array(out_so, dtype=np.uint64), cat([p[None] for p in poses], 3).reshape(-1, 3),
+            np.array(out_mo, dtype=np.uint64), cat(pts, 2), cat([p[None] for p in qposes], 3).reshape(-1, 3),
+            np.array(out_qo, dtype=np.uint64), cat(qs, 2))
+
+
+def gather_job_rows(rows: np.ndarray, n_jobs: int, rank: int, world: int, device, group=None) -> np.ndarray:
+    """All-gather of the ranks' result rows -> [n_jobs, RESULT_DOUBLES] in job order (every rank)."""
+    import torch
+    import torch.distributed as dist
+    per_rank = (n_jobs + world - 1) // world
+    mine = torch.zeros(per_rank * RESULT_DOUBLES, dtype=torch.float64, device=device)
+    flat = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64).ravel())
+    mine[:flat.numel()] = flat.to(device)
+    gathered = torch.zeros(world * per_rank * RESULT_DOUBLES, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered.copy_(mine)
+    g = gathered.cpu().numpy().reshape(world, per_rank, RESULT_DOUBLES)
+    out = np.zeros((n_jobs, RESULT_DOUBLES))
+    for r in range(world):
+        jobs = job_slice(n_jobs, r, world)
+        out[jobs] = g[r, :jobs.shape[0]]
+    return out
+
+
+class ShardedBatch:
+    """match_scan_batch with the jobs interleaved over the ranks of a process group."""
+
+    def __init__(self, matcher, rank: int, world: int, device, group=None):
+        self.m, self.rank, self.world, self.device, self.group = matcher, rank, world, device, group
+
+    def match_scan_batch(self, job_scan_offsets, map_poses, map_offsets, map_points, query_poses,
+                         query_offsets, query_points):
+        """-> (score[n], delta[n,3], written[n], cov[n,3,3]) of ALL jobs, on every rank."""
+        n_jobs = np.asarray(query_poses).reshape(-1, 3).shape[0]
+        jobs = job_slice(n_jobs, self.rank, self.world)
+        rows = np.zeros((jobs.shape[0], RESULT_DOUBLES))
+        if jobs.shape[0]:
+            score, delta, written, cov = self.m.match_scan_batch(*select_jobs(
+                jobs, job_scan_offsets, map_poses, map_offsets, map_points, query_poses, query_offsets,
+                query_points))
+            rows[:, 0], rows[:, 1], rows[:, 2:5], rows[:, 5:14] = score, written, delta, cov.reshape(-1, 9)
+        allr = gather_job_rows(rows, n_jobs, self.rank, self.world, self.device, self.group)
+        return allr[:, 0].copy(), allr[:, 2:5].copy(), allr[:, 1] != 0.0, allr[:, 5:14].reshape(-1, 3, 3).copy()

@@ -41,6 +41,19 @@ def main():
         m.close()
         if rank == 0:
             print(f"{name}: nccl and p2p exchanges match the single-GPU search on {world} ranks")
+    # loop-closure batch: jobs interleaved over the ranks, one all-gather of the result rows
+    w = synth.config3(n_jobs=13)
+    m = ScanMatcherNDT.from_params(w.params, device=local, stream=stream.cuda_stream)
+    args = (w.job_scan_offsets, w.map_poses, w.map_offsets, w.map_points, w.query_poses, w.query_offsets,
+            w.query_points)
+    full = m.match_scan_batch(*args)
+    got = sharded.ShardedBatch(m, rank, world, dev).match_scan_batch(*args)
+    assert np.array_equal(got[2], full[2]) and np.array_equal(got[1], full[1])
+    np.testing.assert_allclose(got[0], full[0], rtol=1e-6)
+    np.testing.assert_allclose(got[3], full[3], rtol=1e-6, atol=1e-9 * np.nanmax(np.abs(full[3])))
+    m.close()
+    if rank == 0:
+        print(f"config3/13 jobs: the batch split over {world} ranks matches the single-GPU batch")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

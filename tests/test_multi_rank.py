@@ -81,3 +81,57 @@ def test_lattice_replays_accumulated_bounds():
     assert len(sharded.lattice(0.1, 0.0025)) == 80
     assert len(sharded.lattice(np.pi, 0.002)) == 3142
     assert sharded.lattice(0.05, 0.005)[-1] == 0.04999999999999999
+
+
+# ------------------------------------------------------------------ loop-closure batch, jobs over ranks
+def _batch_worker(rank, world, port, out_dir):
+    from oracle import binding as B
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = synth.config3(n_jobs=7)
+        o = B.load_oracle()
+        mo = o.new_matcher(w.params)
+
+        class OracleBatchMatcher:
+            """match_scan_batch of the product's mirror, computed by the oracle (no GPU here)."""
+            def match_scan_batch(self, so, mposes, moffs, mpts, qposes, qoffs, qpts):
+                n = qposes.shape[0]
+                score, delta, written, cov = np.zeros(n), np.zeros((n, 3)), np.zeros(n, bool), np.zeros((n, 3, 3))
+                for j in range(n):
+                    s0, s1 = int(so[j]), int(so[j + 1])
+                    offs = moffs[s0:s1 + 1].astype(np.int64)
+                    mo.reset()
+                    mo.add_scans(mposes[s0:s1], (offs - offs[0]).astype(np.uint64), mpts[int(offs[0]):int(offs[-1])])
+                    q0, q1 = int(qoffs[j]), int(qoffs[j + 1])
+                    score[j], d, written[j], cov[j], _ = mo.match_scan(qposes[j], qpts[q0:q1])
+                    if written[j]:
+                        delta[j] = d
+                return score, delta, written, cov
+
+        args = (w.job_scan_offsets, w.map_poses, w.map_offsets, w.map_points, w.query_poses, w.query_offsets,
+                w.query_points)
+        sb = sharded.ShardedBatch(OracleBatchMatcher(), rank, world, torch.device("cpu"))
+        got = sb.match_scan_batch(*args)
+        jobs = np.arange(w.query_poses.shape[0])
+        want = OracleBatchMatcher().match_scan_batch(*sharded.select_jobs(jobs, *args))
+        for g, x in zip(got, want):
+            assert np.array_equal(np.nan_to_num(g, nan=-7.0), np.nan_to_num(x, nan=-7.0))   # every job, job order
+        np.save(os.path.join(out_dir, f"batch{rank}.npy"), np.nan_to_num(got[0], nan=-7.0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_loop_closure_batch_jobs_over_ranks_gloo(tmp_path, world):
+    mp.spawn(_batch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"batch{r}.npy") for r in range(world)]
+    for r in res[1:]:
+        assert np.array_equal(r, res[0])
+
+
+def test_job_slice_covers_every_job_once():
+    for n_jobs in (0, 1, 5, 50):
+        for world in (1, 2, 3, 8, 64):
+            seen = np.concatenate([sharded.job_slice(n_jobs, r, world) for r in range(world)])
+            assert sorted(seen.tolist()) == list(range(n_jobs))
