@@ -466,6 +466,57 @@ def test_match_scan_batch(o):
     assert m.match_scan_raw(w.query_poses[0], w.query_points[:10])[4] == L.ERR_NO_MAP
 
 
+def _batch_against_oracle(o, params, jobs, variant=0):
+    """jobs: list of (map_poses, map_offsets, map_points, query_pose, query_points)."""
+    so_, mo_, qo_ = [0], [0], [0]
+    mposes, mpts, qposes, qpts = [], [], [], []
+    for poses, offs, pts, qpose, qp in jobs:
+        offs = np.asarray(offs, dtype=np.int64)
+        for k in range(poses.shape[0]):
+            mposes.append(poses[k])
+            mpts.append(pts[offs[k]:offs[k + 1]])
+            mo_.append(mo_[-1] + int(offs[k + 1] - offs[k]))
+        so_.append(so_[-1] + poses.shape[0])
+        qposes.append(qpose)
+        qpts.append(qp)
+        qo_.append(qo_[-1] + qp.shape[0])
+    m = ScanMatcherNDT.from_params(params, kernel_variant=variant)
+    score, delta, written, cov = m.match_scan_batch(
+        np.array(so_, dtype=np.uint64), np.array(mposes), np.array(mo_, dtype=np.uint64), np.concatenate(mpts),
+        np.array(qposes), np.array(qo_, dtype=np.uint64), np.concatenate(qpts))
+    mo = o.new_matcher(params)
+    for j, (poses, offs, pts, qpose, qp) in enumerate(jobs):
+        mo.reset()
+        mo.add_scans(poses, np.asarray(offs, dtype=np.uint64), pts)
+        s, d, wr, c, sc = mo.match_scan(qpose, qp, want_scores=True)
+        check_match((score[j], delta[j], written[j], cov[j]), (s, d, wr, c), None, sc)
+
+
+def test_match_scan_batch_other_kernel_paths(o):
+    """match_scan_batch beyond the local-window shape: a window too wide for the window kernel
+    (dense batch kernel), searches above 2e7 (candidate, point) pairs (region batch kernel, planned
+    for the whole batch) and maps too large for the one-CTA build (pipelined lanes)."""
+    w = synth.config1(laser_max_beams=100)
+    two = slice(0, 2)
+    offs2 = w.map_offsets[:3]
+    small_map = (w.map_poses[two], offs2, w.map_points[:int(offs2[-1])])
+    guesses = [w.true_pose - np.array([0.03 * k, -0.02 * k, 0.01 * k]) for k in range(1, 4)]
+    # (a) 10 x 10 lattice 0.9 m wide over 0.1 m cells: 11 cells per axis -> dense batch
+    p = dict(w.params, ndt_resolution=0.1, search_linear_resolution=0.1, search_linear_size=0.45,
+             search_angular_size=0.05)
+    _batch_against_oracle(o, p, [small_map + (g, w.query_points) for g in guesses])
+    # (b) 40 x 100 x 100 candidates x 100 beams = 4e7 pairs per job -> region batch
+    p = dict(w.params, search_linear_resolution=0.01, search_linear_size=0.5, search_angular_size=0.05)
+    _batch_against_oracle(o, p, [small_map + (g, w.query_points) for g in guesses[:2]])
+    # (c) 17-scan maps (more points than one CTA's 4,096) -> lanes
+    poses17 = np.concatenate([w.map_poses, w.map_poses[:7] + np.array([0.05, 0.05, 0.01])])
+    sizes = np.diff(w.map_offsets.astype(np.int64))
+    offs17 = np.concatenate([[0], np.cumsum(np.concatenate([sizes, sizes[:7]]))])
+    pts17 = np.concatenate([w.map_points, w.map_points[:int(w.map_offsets[7])]])
+    assert pts17.shape[0] > 4096
+    _batch_against_oracle(o, w.params, [(poses17, offs17, pts17, g, w.query_points) for g in guesses[:2]])
+
+
 def _sequential_loop_closure(mo, poses, offs, pts, candidates, rolling, limit, typical, qpose, qpts):
     """The reference's inner loop (ndt_mapper.cpp:619-671) with the oracle matcher, one
     candidate at a time."""
