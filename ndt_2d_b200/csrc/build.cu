@@ -435,9 +435,14 @@ __device__ __forceinline__ void write_records(
 // K3b: the cells of the head list replay Cell::addPoint's recurrence and emit their
 // records.  The five running quantities (mean x, mean y, second moments xx, xy, yy) are
 // independent recurrences of the same form v <- (v * n + term) / (n + 1), so a cell is
-// given to a group of 8 lanes, lanes 0..4 each carrying one of them through the cell's
-// points in order (bit-identical to the sequential CPU build, one divide per point on
-// the critical path instead of five); 4 cells per warp.
+// given to a group of 5 lanes, each carrying one of them through the cell's points in order
+// (bit-identical to the sequential CPU build, one divide per point on the critical path
+// instead of five); 6 cells per warp (lanes 30, 31 idle), warps stride over the head list
+// (its length is only known on the device: the grid is sized for the machine, not for the
+// worst case).  The kernel is issue-bound -- config 5: 51,725 cells of 5..469 points --, so
+// what counts is lanes busy per instruction (profiles/r01_build_kernels_config5.md).
+constexpr uint32_t kMomentCellsPerWarp = 6;
+
 __global__ void __launch_bounds__(256) segment_moments_kernel(
   GridDesc g, const uint32_t * __restrict__ key, const uint2 * __restrict__ heads,
   const uint32_t * __restrict__ n_heads, const double * __restrict__ sx,
@@ -450,59 +455,69 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
     const uint2 last = occ[g.n_words - 1];
     *n_valid = last.y + __popc(last.x);
   }
-  const uint32_t cell = t >> 3, r = t & 7u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = t >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t sub = lane / 5u, r = lane - sub * 5u;      // lanes 30, 31: sub == 6, no cell
+  const uint32_t src = (sub < kMomentCellsPerWarp ? sub : kMomentCellsPerWarp - 1u) * 5u;
   const uint32_t total = *n_heads;
-  const bool have = cell < total;
-  const uint2 h = have ? heads[cell] : make_uint2(0u, 0u);
-  const size_t i = h.x;
-  const uint32_t len = h.y;
-  double v = 0.0, n = 0.0;
-  if (have && r < 5u) {
-    // the loads of four points are issued before the (dependent) recurrence steps
-    // that consume them: the chain is then bound by the divide, not by memory latency
-    uint32_t j = 0;
-    for (; j + 4 <= len; j += 4) {
-      double x[4], y[4];
+  for (uint32_t first = warp * kMomentCellsPerWarp; first < total;
+    first += n_warps * kMomentCellsPerWarp)
+  {
+    const uint32_t cell = first + sub;
+    const bool have = sub < kMomentCellsPerWarp && cell < total;
+    const uint2 h = have ? heads[cell] : make_uint2(0u, 0u);
+    const size_t i = h.x;
+    const uint32_t len = h.y;
+    double v = 0.0, n = 0.0;
+    if (have) {
+      // the loads of four points are issued before the (dependent) recurrence steps
+      // that consume them: the chain is then bound by the divide, not by memory latency
+      uint32_t j = 0;
+      for (; j + 4 <= len; j += 4) {
+        double x[4], y[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        x[u] = sx[i + j + u];
-        y[u] = sy[i + j + u];
+        for (int u = 0; u < 4; ++u) {
+          x[u] = sx[i + j + u];
+          y[u] = sy[i + j + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double term = r == 0u ? x[u] : r == 1u ? y[u] : r == 2u ? __dmul_rn(x[u], x[u]) :
+            r == 3u ? __dmul_rn(x[u], y[u]) : __dmul_rn(y[u], y[u]);
+          const double n1 = __dadd_rn(n, 1.0);
+          v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+          n = n1;
+        }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double term = r == 0u ? x[u] : r == 1u ? y[u] : r == 2u ? __dmul_rn(x[u], x[u]) :
-          r == 3u ? __dmul_rn(x[u], y[u]) : __dmul_rn(y[u], y[u]);
+      for (; j < len; ++j) {
+        const double x = sx[i + j], y = sy[i + j];
+        const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
+          r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
         const double n1 = __dadd_rn(n, 1.0);
         v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
         n = n1;
       }
     }
-    for (; j < len; ++j) {
-      const double x = sx[i + j], y = sy[i + j];
-      const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
-        r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
-      const double n1 = __dadd_rn(n, 1.0);
-      v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
-      n = n1;
+    // collect the five quantities in the first lane of the group (all 32 lanes shuffle)
+    CellStats c;
+    c.n = static_cast<double>(len);
+    c.mean[0] = __shfl_sync(0xffffffffu, v, src + 0u);
+    c.mean[1] = __shfl_sync(0xffffffffu, v, src + 1u);
+    c.corr[0] = __shfl_sync(0xffffffffu, v, src + 2u);
+    c.corr[1] = __shfl_sync(0xffffffffu, v, src + 3u);
+    c.corr[2] = __shfl_sync(0xffffffffu, v, src + 4u);
+    if (have && r == 0u) {
+      stats_finalize(c);
+      const uint32_t k = key[i];
+      const uint32_t p = padded_index(g, k);
+      const uint2 w = occ[p >> 5];
+      const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
+      if (rank < rec_cap) {
+        write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+      }
     }
   }
-  // collect the five quantities in lane 0 of the group (all 32 lanes shuffle)
-  CellStats c;
-  c.n = static_cast<double>(len);
-  c.mean[0] = __shfl_sync(0xffffffffu, v, 0, 8);
-  c.mean[1] = __shfl_sync(0xffffffffu, v, 1, 8);
-  c.corr[0] = __shfl_sync(0xffffffffu, v, 2, 8);
-  c.corr[1] = __shfl_sync(0xffffffffu, v, 3, 8);
-  c.corr[2] = __shfl_sync(0xffffffffu, v, 4, 8);
-  if (!have || r != 0u) {return;}
-  stats_finalize(c);
-  const uint32_t k = key[i];
-  const uint32_t p = padded_index(g, k);
-  const uint2 w = occ[p >> 5];
-  const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
-  if (rank >= rec_cap) {return;}
-  write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-    rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
 }
 
 // Parity dump: every occupied cell, dense, in the layout of ndt_2d::Cell.
@@ -943,8 +958,9 @@ int ndt2d_launch_build(
     NDT2D_LAUNCH_CHECK(ctr);
   }
   if (n_points > 0) {
-    // one 8-lane group per listed cell; the list cannot be longer than rec_cap
-    const uint32_t nb = (rec_cap * 8u + 255u) / 256u;
+    // one 5-lane group per listed cell, warps stride over the list (at most rec_cap long)
+    const uint32_t want = (rec_cap + 8u * kMomentCellsPerWarp - 1u) / (8u * kMomentCellsPerWarp);
+    const uint32_t nb = want < 148u * 8u ? (want ? want : 1u) : 148u * 8u;
     segment_moments_kernel<<<nb, 256, 0, stream>>>(
       g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, d_occ, d_rec, d_rec_fast, rec_cap, d_n_valid);
     NDT2D_LAUNCH_CHECK(ctr);
