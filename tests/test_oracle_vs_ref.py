@@ -72,6 +72,48 @@ def test_matcher_far_scan_leaves_pose_untouched(both):
         assert np.all(np.isnan(cov))          # s == 0 -> (1/s) k is NaN (:146)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_small_worlds_oracle_vs_reference(both, seed):
+    """Randomised worlds, poses (negative coordinates included), scan counts and matcher
+    parameters: the restatement must reproduce the compiled reference bit for bit -- grid,
+    every cell, best pose, score, covariance, scorePoints."""
+    o, r = both
+    rng = np.random.default_rng(4000 + seed)
+    arena = float(rng.choice([12.0, 25.0, 60.0]))
+    rects = synth.world(seed=300 + seed, arena=arena, n_obstacles=int(rng.integers(3, 25)),
+                        side_min=0.3, side_max=3.0)
+    n_scans = int(rng.integers(1, 9))
+    beams = int(rng.choice([45, 180, 360]))
+    rmax = float(rng.choice([3.5, 8.0, 20.0]))
+    centre = rng.uniform(0.2 * arena, 0.8 * arena, size=2)
+    poses = np.column_stack([centre[0] + rng.normal(0, 0.4, n_scans + 1), centre[1] + rng.normal(0, 0.4, n_scans + 1),
+                             rng.uniform(-np.pi, np.pi, n_scans + 1)])
+    offs, pts = synth.scans(rects, poses, beams, rmax, seed=500 + seed,
+                            noise_sigma=float(rng.choice([0.0, 0.01, 0.05])), arena=arena)
+    poses[:, :2] += rng.choice([0.0, -arena, -3.0 * arena])      # all-negative / mixed-sign coordinates
+    lres = float(rng.choice([0.02, 0.05, 0.1]))
+    p = dict(ndt_resolution=float(rng.choice([0.1, 0.25, 0.5, 1.0])),
+             search_angular_resolution=float(rng.choice([0.005, 0.02])),
+             search_angular_size=float(rng.choice([0.01, 0.05])),
+             search_linear_resolution=lres, search_linear_size=lres * float(rng.choice([1.5, 4.0])),
+             laser_max_beams=int(rng.choice([30, 100, 1000])), range_max=rmax)
+    mo, mr = o.new_matcher(p), r.new_matcher(p)
+    map_offs, map_pts = offs[: n_scans + 1], pts[: int(offs[n_scans])]
+    for m in (mo, mr):
+        m.add_scans(poses[:n_scans], map_offs, map_pts)
+    assert mo.grid() == mr.grid()
+    assert np.array_equal(mo.dump_cells(), mr.dump_cells(), equal_nan=True)
+    q = pts[int(offs[n_scans]):int(offs[n_scans + 1])]
+    guess = poses[n_scans] + np.array([0.5 * lres, -1.2 * lres, 0.004])
+    so, do, wo, co, _ = mo.match_scan(guess, q)
+    sr, dr, wr, cr, _ = mr.match_scan(guess, q)
+    assert wo == wr and (not wo or np.array_equal(do, dr))
+    assert so == sr or (np.isnan(so) and np.isnan(sr))
+    np.testing.assert_allclose(co, cr, rtol=1e-12, equal_nan=True)
+    if q.shape[0]:
+        assert mo.score_points(q, guess) == mr.score_points(q, guess)
+
+
 def test_particle_filter_measure_and_stats(both):
     o, r = both
     w = synth.config2(n_side=10, n_particles=300)
