@@ -66,8 +66,7 @@ typedef struct ndt2d_params
                                         kernel (3 forces dense, 4 forces region, 5 forces
                                         window where eligible, else dense);
                                         1 = plain per-candidate kernel (reference arithmetic
-                                        per evaluation; the on-device cross-check),
-                                        2 = previous tiled kernel (A/B runs) */
+                                        per evaluation; the on-device cross-check) */
 } ndt2d_params;
 
 typedef struct ndt2d_matcher ndt2d_matcher;

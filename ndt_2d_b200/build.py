@@ -21,7 +21,7 @@ LIBDIR = PKG / "lib"
 OBJDIR = LIBDIR / "obj"
 LIB = LIBDIR / "libndt2d_b200.so"
 
-CU_SOURCES = ["api.cu", "build.cu", "search.cu", "search_tiled.cu", "search_region.cu", "search_window.cu", "filter.cu", "probe.cu", "frontend.cu", "occupancy.cu"]
+CU_SOURCES = ["api.cu", "build.cu", "search.cu", "search_region.cu", "search_window.cu", "filter.cu", "probe.cu", "frontend.cu", "occupancy.cu"]
 CXX_SOURCES = ["synth.cpp"]
 HEADERS = [CSRC / "ndt2d_internal.h", CSRC / "search_common.cuh", CSRC / "search_region_body.inc",
            ROOT / "include" / "ndt2d_b200.h"]

@@ -172,7 +172,7 @@ struct ndt2d_matcher
 
   bool has_model = false;
   GridDesc g{};
-  DeviceBuffer d_occ, d_occd, d_rec, d_rec_fast, d_thr, d_nvalid;
+  DeviceBuffer d_occ, d_occd, d_rec, d_rec_fast, d_rec_vtx, d_thr, d_nvalid;
   uint32_t rec_cap = 0;
   uint32_t n_valid = 0;
 
@@ -225,6 +225,7 @@ ModelView model_view(const ndt2d_matcher * m)
   mv.occ_dilated = m->d_occd.as<uint32_t>();
   mv.rec = m->d_rec.as<double>();
   mv.rec_fast = m->d_rec_fast.as<double>();
+  mv.rec_vtx = m->d_rec_vtx.as<double>();
   mv.thr_x = m->d_thr.as<double>();
   mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 2);
   mv.n_valid_cap = m->rec_cap;
@@ -327,6 +328,8 @@ int grid_from_poses(const ndt2d_matcher * m, size_t n_scans, const double * pose
   g.n_cells = static_cast<uint32_t>(n_cells64);
   g.n_padded = static_cast<uint32_t>(n_padded64);
   g.n_words = (g.n_padded + 31) / 32;
+  g.lin_res = m->prm.search_linear_resolution;
+  g.dil_x = ndt2d_region_dilate_x(cell, g.lin_res, static_cast<uint32_t>(m->dlin.size()));
   *out = g;
   return NDT2D_OK;
 }
@@ -404,6 +407,7 @@ int add_scans_impl(
   m->rec_cap = static_cast<uint32_t>(cap64);
   if ((rc = m->d_rec.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
   if ((rc = m->d_rec_fast.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
+  if ((rc = m->d_rec_vtx.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
   if ((rc = m->d_heads.ensure(cap64 * sizeof(uint2)))) {return rc;}
 
   m->bs.wx = m->d_wx.as<double>();
@@ -468,7 +472,8 @@ int add_scans_impl(
   if (m->evb_begin) {cudaEventRecord(m->evb_begin, st);}
   rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
       m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
-      m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->rec_cap, m->d_nvalid.as<uint32_t>(), st,
+      m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->d_rec_vtx.as<double>(), m->rec_cap,
+      m->d_nvalid.as<uint32_t>(), st,
       &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
   if (m->evb_end) {
@@ -832,7 +837,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
-    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_thr, &m->d_nvalid,
+    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_rec_vtx, &m->d_thr, &m->d_nvalid,
       &m->d_sx, &m->d_sy, &m->d_heads, &m->d_nheads, &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
       &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results, &m->d_batch_arena};
@@ -972,7 +977,7 @@ static int match_scan_batch_fused(
     size_t n_scans, n_points, n_use, npts_q, rec_cap;
     uint64_t s0, p0, q0;
     size_t o_tf, o_off, o_pts, o_thr, o_q, o_trig;                       // upload region
-    size_t o_occ, o_occd, o_rec, o_recf, o_nvalid, o_jobp, o_chunk;      // device-only region
+    size_t o_occ, o_occd, o_rec, o_recf, o_recv, o_nvalid, o_jobp, o_chunk;      // device-only region
   };
   std::vector<Job> jobs(n_jobs);
   uint32_t max_use = 0;
@@ -1038,6 +1043,7 @@ static int match_scan_batch_fused(
     J.o_occd = take((static_cast<size_t>(J.g.n_words) + 4) * sizeof(uint32_t));
     J.o_rec = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
     J.o_recf = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
+    J.o_recv = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
     J.o_nvalid = take(sizeof(uint32_t));
     J.o_jobp = take(static_cast<size_t>(pl.n_jobs) * NDT2D_BLOCK_PARTIAL * sizeof(double));
     J.o_chunk = take(pl.chunk_doubles ? pl.chunk_doubles * sizeof(double) : 8);
@@ -1093,6 +1099,7 @@ static int match_scan_batch_fused(
     be.occd = reinterpret_cast<uint32_t *>(db + J.o_occd);
     be.rec = reinterpret_cast<double *>(db + J.o_rec);
     be.rec_fast = reinterpret_cast<double *>(db + J.o_recf);
+    be.rec_vtx = reinterpret_cast<double *>(db + J.o_recv);
     be.n_valid = reinterpret_cast<uint32_t *>(db + J.o_nvalid);
     be.n_scans = static_cast<uint32_t>(J.n_scans);
     be.n_points = static_cast<uint32_t>(J.n_points);
@@ -1104,6 +1111,7 @@ static int match_scan_batch_fused(
     se.mv.occ_dilated = be.occd;
     se.mv.rec = be.rec;
     se.mv.rec_fast = be.rec_fast;
+    se.mv.rec_vtx = be.rec_vtx;
     se.mv.thr_x = reinterpret_cast<const double *>(db + J.o_thr);
     se.mv.thr_y = se.mv.thr_x + (J.g.size_x + 2);
     se.mv.n_valid_cap = static_cast<uint32_t>(J.rec_cap);

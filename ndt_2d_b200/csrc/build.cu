@@ -409,9 +409,10 @@ __device__ __forceinline__ void stats_walk(
   }
 }
 
-// The two packed records of one finished cell (layout: ndt2d_internal.h, ModelView).
+// The packed records of one finished cell (layout: ndt2d_internal.h, ModelView).
 __device__ __forceinline__ void write_records(
-  const CellStats & c, double cell_size, double * __restrict__ rr, double * __restrict__ f)
+  const CellStats & c, const GridDesc & g, double * __restrict__ rr, double * __restrict__ f,
+  double * __restrict__ vt)
 {
   // -0.5 * information: scaling by a power of two is exact, so the device
   // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
@@ -421,15 +422,27 @@ __device__ __forceinline__ void write_records(
   rr[3] = -0.5 * c.info[2];  // (1,0)
   rr[4] = -0.5 * c.info[1];  // (0,1)
   rr[5] = -0.5 * c.info[3];  // (1,1)
-  // short form of the search kernel
+  // short form of the window / dense search kernels
   constexpr double kLog2e = 1.44269504088896340736;
   const double mag = fmax(fmax(fabs(c.info[0]), fabs(c.info[3])), fmax(fabs(c.info[1]), fabs(c.info[2])));
+  const double A = rr[2] * kLog2e, B = (rr[3] + rr[4]) * kLog2e, D = rr[5] * kLog2e;
+  const bool stiff = !(mag * (g.cell_size * g.cell_size) <= 1.0e7);  // NaN -> stiff
   f[0] = c.mean[0];
   f[1] = c.mean[1];
-  f[2] = rr[2] * kLog2e;
-  f[3] = (rr[3] + rr[4]) * kLog2e;
-  f[4] = rr[5] * kLog2e;
-  f[5] = (mag * (cell_size * cell_size) <= 1.0e7) ? 0.0 : 1.0;  // NaN -> stiff
+  f[2] = A;
+  f[3] = B;
+  f[4] = D;
+  f[5] = stiff ? 1.0 : 0.0;
+  // vertex form of the region kernel: log2 L = D (qy + Bh qx)^2 + S qx^2 ; needs D < 0
+  const bool vstiff = stiff || !(D < 0.0);
+  const double Bh = B / (2.0 * D), S = A - (B * B) / (4.0 * D);
+  vt[0] = c.mean[0];
+  vt[1] = c.mean[1];
+  vt[2] = D;
+  vt[3] = Bh;
+  vt[4] = S;
+  const float2 tail = make_float2(static_cast<float>(D * (g.lin_res * g.lin_res)), vstiff ? 1.0f : 0.0f);
+  *reinterpret_cast<float2 *>(vt + 5) = tail;
 }
 
 // K3b: the cells of the head list replay Cell::addPoint's recurrence and emit their
@@ -447,7 +460,8 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
   GridDesc g, const uint32_t * __restrict__ key, const uint2 * __restrict__ heads,
   const uint32_t * __restrict__ n_heads, const double * __restrict__ sx,
   const double * __restrict__ sy, const uint2 * __restrict__ occ, double * __restrict__ rec,
-  double * __restrict__ rec_fast, uint32_t rec_cap, uint32_t * __restrict__ n_valid)
+  double * __restrict__ rec_fast, double * __restrict__ rec_vtx, uint32_t rec_cap,
+  uint32_t * __restrict__ n_valid)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) {
@@ -513,8 +527,9 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
       const uint2 w = occ[p >> 5];
       const uint32_t rank = w.y + __popc(w.x & ((1u << (p & 31u)) - 1u));
       if (rank < rec_cap) {
-        write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+        write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
       }
     }
   }
@@ -567,18 +582,23 @@ __device__ __forceinline__ uint32_t occ_bits_at(
   return __funnelshift_r(lo, hi, sh);
 }
 
-// K3c: dilated occupancy D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1].
-// A patch of search candidates whose first candidate puts a point in padded
-// cell c can only touch those four cells (search.cu), so one D bit rejects the
-// whole patch.
+// K3c: dilated occupancy D[c] = OR of E over columns c .. c + dil_x and rows c, c + pitch.
+// A region of search candidates whose first candidate puts a point in padded cell c can
+// only touch those (dil_x + 1) x 2 cells (search_region.cu: a region is up to 32 columns
+// wide -- at most 3 cell columns -- and at most one cell high), so one D bit rejects the
+// whole region.  Past the last column the window wraps into the next row's border cell and
+// first real cells: a conservative superset, the search probes the real cells afterwards.
 __global__ void __launch_bounds__(256) dilate_kernel(
   GridDesc g, const uint2 * __restrict__ occ, uint32_t * __restrict__ occ_dilated)
 {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= g.n_words) {return;}
   const uint64_t pos = static_cast<uint64_t>(w) << 5;
-  occ_dilated[w] = occ_bits_at(occ, g.n_words, pos) | occ_bits_at(occ, g.n_words, pos + 1) |
-    occ_bits_at(occ, g.n_words, pos + g.pitch) | occ_bits_at(occ, g.n_words, pos + g.pitch + 1);
+  uint32_t d = 0;
+  for (uint32_t i = 0; i <= g.dil_x; ++i) {
+    d |= occ_bits_at(occ, g.n_words, pos + i) | occ_bits_at(occ, g.n_words, pos + g.pitch + i);
+  }
+  occ_dilated[w] = d;
 }
 
 
@@ -633,6 +653,7 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
   uint32_t * __restrict__ occ_dilated = e.occd;
   double * __restrict__ rec = e.rec;
   double * __restrict__ rec_fast = e.rec_fast;
+  double * __restrict__ rec_vtx = e.rec_vtx;
   uint32_t * __restrict__ n_valid = e.n_valid;
   const uint32_t tid = threadIdx.x;
   uint32_t n2 = 128;
@@ -774,9 +795,11 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
   for (uint32_t w = tid; w < g.n_words; w += kSmallThreads) {
     occ[w] = make_uint2(sm.occw[w], sm.pref[w]);
     const uint32_t pos = w << 5;
-    occ_dilated[w] = small_bits_at(sm.occw, g.n_words, pos) | small_bits_at(sm.occw, g.n_words, pos + 1) |
-      small_bits_at(sm.occw, g.n_words, pos + g.pitch) |
-      small_bits_at(sm.occw, g.n_words, pos + g.pitch + 1);
+    uint32_t d = 0;
+    for (uint32_t i = 0; i <= g.dil_x; ++i) {
+      d |= small_bits_at(sm.occw, g.n_words, pos + i) | small_bits_at(sm.occw, g.n_words, pos + g.pitch + i);
+    }
+    occ_dilated[w] = d;
   }
   // ---- K3b: moment recurrences, 8 lanes per listed cell (see segment_moments_kernel)
   const uint32_t group = tid >> 3, r = tid & 7u;
@@ -811,8 +834,9 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
       const uint32_t bits = sm.occw[pi >> 5];
       const uint32_t rank = sm.pref[pi >> 5] + __popc(bits & ((1u << (pi & 31u)) - 1u));
       if (rank < rec_cap) {
-        write_records(c, g.cell_size, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+        write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+          rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
       }
     }
   }
@@ -889,8 +913,8 @@ int ndt2d_launch_exclusive_scan(uint32_t * d_data, size_t n, uint32_t * d_tmp,
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
   const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
-  double * d_rec, double * d_rec_fast, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream,
-  Counters * ctr, int * sorted_buf)
+  double * d_rec, double * d_rec_fast, double * d_rec_vtx, uint32_t rec_cap, uint32_t * d_n_valid,
+  cudaStream_t stream, Counters * ctr, int * sorted_buf)
 {
   if (n_points > 0 && n_points <= kSmallMaxPoints && g.n_words <= kSmallMaxWords) {
     // small model: the whole build in one CTA / one launch
@@ -907,6 +931,7 @@ int ndt2d_launch_build(
     e.occd = d_occ_dilated;
     e.rec = d_rec;
     e.rec_fast = d_rec_fast;
+    e.rec_vtx = d_rec_vtx;
     e.rec_cap = rec_cap;
     e.n_valid = d_n_valid;
     e.key_out = s.key[0];
@@ -962,7 +987,7 @@ int ndt2d_launch_build(
     const uint32_t want = (rec_cap + 8u * kMomentCellsPerWarp - 1u) / (8u * kMomentCellsPerWarp);
     const uint32_t nb = want < 148u * 8u ? (want ? want : 1u) : 148u * 8u;
     segment_moments_kernel<<<nb, 256, 0, stream>>>(
-      g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, d_occ, d_rec, d_rec_fast, rec_cap, d_n_valid);
+      g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, d_occ, d_rec, d_rec_fast, d_rec_vtx, rec_cap, d_n_valid);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   *sorted_buf = cur;

@@ -23,6 +23,9 @@ struct GridDesc
   uint32_t n_cells;         // size_x * size_y
   uint32_t n_padded;        // (size_x + 2) * (size_y + 2)
   uint32_t n_words;         // ceil(n_padded / 32)
+  // search parameters the build needs (they are fixed per matcher handle):
+  uint32_t dil_x;           // the dilated bitmap ORs cell columns c .. c + dil_x (1 or 2), rows c, c + 1
+  double lin_res;           // search_linear_resolution (row step of the vertex-form records)
 };
 
 // Device-resident model of one matcher.
@@ -41,14 +44,21 @@ struct GridDesc
 //              within 1e-7 of the reference's grouping (max|I| cell^2 > 1e7, inf
 //              or NaN); the search then evaluates them from rec[] with the
 //              reference's own operation order.
+//   rec_vtx[r*6] = mean_x, mean_y, D, Bh = B / (2 D), S = A - B^2 / (4 D), {float c2 = D h^2,
+//              float stiff}: the same quadratic in "vertex form" along a column of candidates
+//              (x fixed, y = y0 + b h):  log2 L = D (qy + Bh qx)^2 + S qx^2, which the region
+//              kernel evaluates per row b as c2 b'^2 + d1 b' + e0 in float with b' = b - b*
+//              counted from the row nearest the vertex (no cancellation between the terms).
+//              stiff additionally covers D >= 0 (the form needs D < 0).
 //   thr_x[k] = smallest double x whose reference grid_x is >= k  (k=0: origin)
 struct ModelView
 {
   GridDesc g;
   const uint2 * occ;
-  const uint32_t * occ_dilated;  // D[c] = E[c] | E[c+1] | E[c+pitch] | E[c+pitch+1]
+  const uint32_t * occ_dilated;  // D[c] = OR of E over columns c .. c + g.dil_x, rows c, c + pitch
   const double * rec;
-  const double * rec_fast;  // 6 doubles per occupied cell, see below
+  const double * rec_fast;  // 6 doubles per occupied cell, see above
+  const double * rec_vtx;   // 6 doubles per occupied cell, see above
   const double * thr_x;  // size_x + 2 entries (the last is +inf)
   const double * thr_y;  // size_y + 2 entries
   uint32_t n_valid_cap;
@@ -64,7 +74,7 @@ struct SearchView
   const double * dth;    // n_ang
   const double * dlin;   // n_lin
   double pose_x, pose_y;
-  double linear_res;     // search_linear_resolution (patch sizing of the tiled kernel)
+  double linear_res;     // search_linear_resolution (region sizing, row step of the region kernel)
   uint32_t n_pts, n_ang, n_lin;
   uint16_t * coords;        // scratch of the coordinate pre-pass (may be null)
   size_t coords_cap_bytes;
@@ -111,6 +121,7 @@ struct BuildEntry
   uint32_t * occd;
   double * rec;
   double * rec_fast;
+  double * rec_vtx;
   uint32_t * n_valid;
   // parity-dump outputs (sorted keys / values / run lengths / coordinates); null in batches
   uint32_t * key_out, * val_out, * seglen;
@@ -129,8 +140,8 @@ int ndt2d_launch_build_small_batch(const BuildEntry * d_entries, uint32_t n, cud
 int ndt2d_launch_build(
   const GridDesc & g, const double4 * d_scan_tf, const uint64_t * d_offsets, size_t n_scans,
   const double2 * d_pts, size_t n_points, BuildScratch & s, uint2 * d_occ, uint32_t * d_occ_dilated,
-  double * d_rec, double * d_rec_fast, uint32_t rec_cap, uint32_t * d_n_valid, cudaStream_t stream,
-  Counters * ctr, int * sorted_buf);
+  double * d_rec, double * d_rec_fast, double * d_rec_vtx, uint32_t rec_cap, uint32_t * d_n_valid,
+  cudaStream_t stream, Counters * ctr, int * sorted_buf);
 
 // Debug/parity: dense dump (16 doubles per reference cell) from the sorted
 // buffers of the last build.
@@ -171,17 +182,13 @@ struct ExchangeView
 size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_size,
   double linear_res);
 
-// search_tiled.cu: the previous production kernel (variant 2, kept for A/B runs).
-size_t ndt2d_tiled_scratch_doubles(const GridDesc & g, uint32_t n_ang, uint32_t n_lin,
-  double linear_res);
-int ndt2d_launch_search_tiled(
-  const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
-  uint32_t n_theta, double * d_block_partials, double * d_scores, cudaStream_t stream,
-  Counters * ctr, uint32_t * n_blocks);
 // search_region.cu: the production kernel (variant 0): one warp per
 // (theta, region of candidates) job, jobs handed out through *d_counter.
 size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res);
+// Extra cell columns the dilated bitmap has to cover for this lattice (1 or 2): a region is
+// up to 32 candidate columns wide.
+uint32_t ndt2d_region_dilate_x(double cell_size, double linear_res, uint32_t n_lin);
 // Bytes of the coordinate pre-pass table for a search of this shape (0 if above cap).
 size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res, uint32_t n_pts, size_t cap_bytes);
@@ -225,7 +232,7 @@ struct BatchEntry
 };
 struct RegionBatchPlan
 {
-  uint32_t Rw, Q, n_jobs, P, chunk_points;
+  uint32_t RX, RY, Qx, Qy, n_jobs, P, chunk_points;
   size_t chunk_doubles;    // per search
 };
 // Plan shared by every search of a batch (same lattice); max_pts = most points of any scan.

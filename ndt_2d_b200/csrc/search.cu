@@ -35,7 +35,7 @@ using namespace ndt2d_dev;
 // ------------------------------------------------------------------ K4, plain
 // One thread per candidate, one theta slice per blockIdx.y, reference
 // arithmetic for every cell lookup (two double divides per evaluation).  Kept
-// as the simple on-device cross-check of the tiled kernel.
+// as the simple on-device cross-check of the production kernels.
 __global__ void __launch_bounds__(kPlainThreads) search_plain_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, double * __restrict__ block_partials,
   double * __restrict__ scores)
@@ -602,13 +602,10 @@ size_t ndt2d_search_scratch_doubles(uint32_t n_ang, uint32_t n_lin, double cell_
 {
   const size_t plain =
     static_cast<size_t>(n_ang ? n_ang : 1) * plain_blocks_x(n_lin) * NDT2D_BLOCK_PARTIAL;
-  GridDesc g{};
-  g.cell_size = cell_size;
-  const size_t tiled = ndt2d_tiled_scratch_doubles(g, n_ang, n_lin, linear_res);
   const size_t region = ndt2d_region_scratch_doubles(cell_size, n_ang, n_lin, linear_res);
   const size_t dense =
     static_cast<size_t>(n_ang ? n_ang : 1) * dense_blocks_x(n_lin) * NDT2D_BLOCK_PARTIAL;
-  size_t a = plain > tiled ? plain : tiled;
+  size_t a = plain;
   a = a > region ? a : region;
   a = a > dense ? a : dense;
   return a + static_cast<size_t>(kReduceBlocks) * kStage1Doubles;
@@ -679,7 +676,7 @@ int ndt2d_launch_search(
     return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
              n_candidates, d_partial32, stream, ctr, exchange, nullptr);
   }
-  if (variant != 1 && variant != 2) {
+  if (variant != 1) {
     uint32_t n_jobs = 0;
     if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
     const int rc = ndt2d_launch_search_region(mv, sv, sv.linear_res, theta_begin, n_theta,
@@ -688,16 +685,6 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_jobs, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr, exchange, d_counter);
-  }
-  if (variant == 2) {
-    uint32_t n_blocks = 0;
-    if (ev_begin) {NDT2D_CUDA_TRY(cudaEventRecord(ev_begin, stream));}
-    const int rc = ndt2d_launch_search_tiled(mv, sv, sv.linear_res, theta_begin, n_theta,
-        d_block_partials, d_scores, stream, ctr, &n_blocks);
-    if (rc != NDT2D_OK) {return rc;}
-    if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
-    return launch_final(d_block_partials, n_blocks, d_block_partials + stage1_offset, sv,
              n_candidates, d_partial32, stream, ctr, exchange, d_counter);
   }
   const uint32_t bx = plain_blocks_x(sv.n_lin);

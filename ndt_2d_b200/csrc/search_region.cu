@@ -5,11 +5,11 @@
 // NDT::getIndex / Cell::score (ndt_model.cpp:105-116, 162-187, 203-218).
 //
 // Work decomposition
-//   job    = (theta slice, REGION of Rw x Rw adjacent (dx, dy) candidates),
-//            Rw chosen so that (Rw - 1) * search_linear_resolution < cell size:
-//            for a fixed scan point the candidates of a region can only put it
-//            into the 2 x 2 cells starting at the cell of the region's first
-//            candidate.
+//   job    = (theta slice, REGION of RX x RY adjacent (dx, dy) candidates): RX <= 32 columns
+//            (one per lane) with (RX - 1) * search_linear_resolution < 2 cells, RY <= 25 rows
+//            with (RY - 1) * search_linear_resolution < 1 cell: for a fixed scan point the
+//            candidates of a region can only put it into the (<= 3) x 2 cells starting at
+//            the cell of the region's first candidate.
 //   warp   = one job at a time, taken from a global atomic job counter
 //            (persistent CTAs, dynamic balance: job cost varies with how much
 //            of the scan overlaps the map).  Warps never synchronise with each
@@ -18,23 +18,28 @@
 //            reference's own operation order (scan_matcher_ndt.cpp:111-114),
 //            padded cell coordinate of the region's first candidate from the
 //            host-tabulated thresholds (bit-exact, no division), one bit test
-//            in the DILATED occupancy bitmap D[c] = E[c]|E[c+1]|E[c+pitch]|
-//            E[c+pitch+1].  A clear bit rejects the point for all Rw*Rw
-//            candidates at once -- most of a large search is empty space.
+//            in the DILATED occupancy bitmap (OR of E over that (<= 3) x 2 window).  A
+//            clear bit rejects the point for all RX * RY candidates at once -- most of a
+//            large search is empty space.
 //   item   = a (point, region) pair whose D bit is set, processed by the whole
-//            warp: lanes compute the exact candidate coordinates of the
-//            region's columns / rows (one __dadd_rn each), a ballot against the
-//            next threshold gives the exact split of the region between the
-//            2 x 2 cells, and for every OCCUPIED cell the candidates of its
-//            sub-rectangle are flattened over the 32 lanes -- every lane
-//            evaluates a Gaussian that the reference evaluates too.
-//   sums   = per-candidate score sums live in shared memory, private to the
-//            warp (Rw*Rw doubles), accumulated in scan-point order.
+//            warp, LANE = CANDIDATE COLUMN: the lane forms its exact column coordinate (one
+//            __dadd_rn) and compares it with the next two thresholds -> its cell column; a
+//            ballot over the exact row coordinates gives the row where the region crosses
+//            into the next cell row.  Each lane therefore has (at most) two cells, one per
+//            row range, and sets up, in double, the cell's quadratic along its column in
+//            VERTEX FORM (rows counted from the row nearest the ridge of the Gaussian):
+//            log2 L(b) = c2 b'^2 + d1 b' + e0 with all three terms <= 0 -- no cancellation,
+//            so the row loop runs in float: FADD, 2 FFMA, MUFU.EX2, FADD per row, the
+//            accumulators being REGISTERS (rows are unrolled, entered by a jump table).
+//   sums   = per-candidate float block sums in registers (25 per lane), flushed every 4
+//            steps with hits into double totals in shared memory (lane-private columns: no
+//            synchronisation anywhere in the job loop).
 //
 // Staging: D and the threshold tables are bulk-copied into shared memory once
 // per CTA with cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier when
 // they fit; E (+ rank prefix) and the 48-byte cell records are read with
-// warp-uniform loads through L1.  DRAM traffic is a few hundred KB per launch.
+// loads through L1 (at most three distinct addresses per warp).  DRAM traffic is the
+// coordinate pre-pass table, written and read once.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -49,29 +54,20 @@ namespace
 
 using namespace ndt2d_dev;
 
-constexpr uint32_t kMaxRw = 25;                 // region side (candidates)
-// Per-candidate totals: float + the running rounding residual kept in the block-sum slot
-// (compensated: the pair carries ~48 bits) -- 5.5 KB of shared memory per warp, so 28 warps
-// fit one SM (measured 28.8 ms at config 4 against 31.3 ms for 24 warps with double totals).
-// -DNDT2D_REGION_DOUBLE_TOTALS -DNDT2D_REGION_WARPS=24 restores plain double totals.
+constexpr uint32_t kMaxRX = 32;                 // region columns (candidates along dx) = lanes
+constexpr uint32_t kMaxRY = 25;                 // region rows (candidates along dy) = registers
 #ifndef NDT2D_REGION_WARPS
-#define NDT2D_REGION_WARPS 28
-#endif
-#ifdef NDT2D_REGION_DOUBLE_TOTALS
-using total_t = double;
-#else
-using total_t = float;
+#define NDT2D_REGION_WARPS 24
 #endif
 constexpr uint32_t kWarps = NDT2D_REGION_WARPS;  // warps per CTA; one persistent CTA per SM
-constexpr uint32_t kAccEntries = kMaxRw * kMaxRw;
-// per warp: double totals, xs[32], ys[32], float block sums (16-byte rounded)
-constexpr uint32_t kWarpSmemBytes =
-  ((kAccEntries * static_cast<uint32_t>(sizeof(total_t)) + 64 * 8 + kAccEntries * 4) + 15u) & ~15u;
+// per warp: double totals, [row][lane]
+constexpr uint32_t kWarpSmemBytes = kMaxRY * 32u * static_cast<uint32_t>(sizeof(double));
 constexpr size_t kSmemTabBudget = 64 * 1024;    // D + thresholds in shared memory up to this
 constexpr uint32_t kBatchSlotBytes = 320;        // per-warp BatchEntry slot of the batch kernel (>= sizeof)
 constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight
+constexpr double kRoundMagic = 6755399441055744.0;      // 1.5 * 2^52: (x + M) - M == rint(x)
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
@@ -117,42 +113,11 @@ __device__ __forceinline__ float ex2_ftz(float x)
   return y;
 }
 
-// Small integer tables (constant memory, warp-uniform reads).
-struct Tables
-{
-  uint8_t rounds[kMaxRw + 1][kMaxRw + 1];  // [n][m] = ceil(m / (32 / n)): rounds to cover m lines
-                                           // when the lane-fixed axis has n entries
-  uint8_t colmode[kMaxRw + 1][kMaxRw + 1];  // [h][w] = 1: lay the rows (y) over the lanes
-  uint8_t div32[33];                       // 32 / n
-  uint32_t inv[33];                        // 65536 / n + 1: (k * inv[n]) >> 16 == k / n, k < 1100
-};
-constexpr Tables make_tables()
-{
-  Tables t{};
-  for (uint32_t n = 1; n <= 32; ++n) {
-    t.div32[n] = static_cast<uint8_t>(32u / n);
-    t.inv[n] = 65536u / n + 1u;
-  }
-  for (uint32_t n = 1; n <= kMaxRw; ++n) {
-    for (uint32_t m = 0; m <= kMaxRw; ++m) {
-      const uint32_t lines = 32u / n;
-      t.rounds[n][m] = static_cast<uint8_t>((m + lines - 1) / lines);
-    }
-  }
-  for (uint32_t h = 1; h <= kMaxRw; ++h) {
-    for (uint32_t w = 1; w <= kMaxRw; ++w) {
-      t.colmode[h][w] = t.rounds[h][w] <= t.rounds[w][h] ? 1 : 0;
-    }
-  }
-  return t;
-}
-__constant__ Tables kTab = make_tables();
-
 struct RegionPlan
 {
-  uint32_t Rw;        // region side
-  uint32_t Q;         // regions per axis
-  uint32_t n_jobs;    // n_theta * Q * Q
+  uint32_t RX, RY;    // region columns / rows
+  uint32_t Qx, Qy;    // regions per axis
+  uint32_t n_jobs;    // n_theta * Qx * Qy
   uint32_t thr_doubles;  // size_x + 1 + size_y + 1
   uint32_t tab_bytes; // D + thresholds, 16-byte rounded (0 = keep in global memory)
   bool smem_tab;
@@ -179,93 +144,96 @@ __device__ __forceinline__ uint32_t padded_coord(
   return pc;
 }
 
-// Evaluates one occupied cell for the candidates of its sub-rectangle
-// [cx0, cx0 + w) x [cy0, cy0 + h) of the region.  Well-conditioned cells only:
-//   log2 L = qx (A qx + B qy) + (D qy) qy.
-// One axis of the sub-rectangle (U: rows if COL, else columns) is laid over the
-// lanes and stays fixed per lane, 32 / nU lines of it side by side; the other
-// (V) is iterated.  Per evaluation: 1 subtract + 2 FMA in double, ex2 and the
-// shared-memory add in float.
-template<bool COL>
-__device__ __forceinline__ void eval_cell(
-  float * __restrict__ acc_f, const double * __restrict__ xs, const double * __restrict__ ys,
-  uint32_t Rw, uint32_t cx0, uint32_t w, uint32_t cy0, uint32_t h, double2 mean, double2 AB,
-  double Dv, uint32_t lane)
+// One row of the region for this lane's column: b' = B - bs, log2 L = c2 b'^2 + d1 b' + e0.
+// NDT2D_ROW_DOWN(B) sits under `case B + 1` of a switch on the number of rows (enter there,
+// fall through down to row 0); NDT2D_ROW_UP(B) under `case B` of a switch on the first row.
+#define NDT2D_ROW_EVAL(B) \
+  { \
+    const float bp = static_cast<float>(B) + nbs; \
+    acc[B] += ex2_ftz(fmaf(fmaf(c2, bp, d1), bp, e0)); \
+  }
+#define NDT2D_ROW_DOWN(B) case (B) + 1: NDT2D_ROW_EVAL(B)
+#define NDT2D_ROW_UP(B) case (B): NDT2D_ROW_EVAL(B)
+
+// A lane's cell along its candidate column, vertex form, float coefficients.
+struct VtxLine
 {
-  const uint32_t nU = COL ? h : w, nV = COL ? w : h;
-  const uint32_t u0 = COL ? cy0 : cx0, v0 = COL ? cx0 : cy0;
-  const double * us = COL ? ys : xs;
-  const double * vs = COL ? xs : ys;
-  const double mean_u = COL ? mean.y : mean.x, mean_v = COL ? mean.x : mean.y;
-  const double Cu = COL ? Dv : AB.x, Cv = COL ? AB.x : Dv;
-  const uint32_t lines = kTab.div32[nU];
-  const uint32_t lv = (lane * kTab.inv[nU]) >> 16, lu = lane - lv * nU;
-  if (lv < lines) {
-    const double qu = us[u0 + lu] - mean_u;
-    const double Bqu = AB.y * qu, Cqu2 = (Cu * qu) * qu;
-    float * ap = acc_f + (COL ? (u0 + lu) + (v0 + lv) * Rw : (u0 + lu) * Rw + (v0 + lv));
-    const double * vp = vs + v0 + lv;
-    const uint32_t ap_step = COL ? lines * Rw : lines;
-    const double * const vend = vs + v0 + nV;   // one past the last entry of the iterated axis
-    // two independent evaluations per trip: halves the loop overhead and gives the
-    // scheduler a second dependency chain (LDS -> DADD -> DFMA -> DFMA -> F2F -> MUFU)
-    for (; vp + lines < vend; vp += 2u * lines) {
-      const double qv0 = vp[0] - mean_v, qv1 = vp[lines] - mean_v;
-      const double e0 = fma(qv0, fma(Cv, qv0, Bqu), Cqu2);
-      const double e1 = fma(qv1, fma(Cv, qv1, Bqu), Cqu2);
-      const float f0 = ex2_ftz(static_cast<float>(e0)), f1 = ex2_ftz(static_cast<float>(e1));
-      ap[0] += f0;
-      ap[ap_step] += f1;
-      ap += 2u * ap_step;
-    }
-    if (vp < vend) {
-      const double qv = *vp - mean_v;
-      const double e = fma(qv, fma(Cv, qv, Bqu), Cqu2);
-      *ap += ex2_ftz(static_cast<float>(e));
+  float c2, d1, e0, nbs;
+  bool stiff;
+};
+
+// Per-lane setup in double.  Record (ndt2d_internal.h): mean, D, Bh, S, {float c2, float stiff}.
+//   w0 = (y0 - mean.y) + Bh (x - mean.x)         the quadratic's argument at row 0
+//   bs = rint(-w0 / h), dl = w0 + bs h           the row nearest the ridge, |dl| <= h / 2
+//   log2 L(b) = c2 b'^2 + (2 h D dl) b' + (D dl^2 + S qx^2),  b' = b - bs
+// A lane without an occupied cell gets e0 = -inf (2^-inf == +0).
+__device__ __forceinline__ VtxLine vtx_setup(
+  bool occ, const double * __restrict__ rec_vtx, uint32_t rank, double xa, double y0, double h,
+  double neg_inv_h, double two_h)
+{
+  VtxLine ln{0.0f, 0.0f, -INFINITY, 0.0f, false};
+  if (occ) {
+    const double2 * r = reinterpret_cast<const double2 *>(
+      rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+    const double2 mean = __ldg(r), DB = __ldg(r + 1), SF = __ldg(r + 2);
+    ln.stiff = __double2hiint(SF.y) != 0;
+    const double qu = xa - mean.x;
+    const double w0 = fma(DB.y, qu, y0 - mean.y);
+    const double rb = w0 * neg_inv_h;
+    if (fabs(rb) < 2097152.0) {   // else the ridge is > 2e6 rows away: L == 0 on this column
+      const double rm = __dadd_rn(rb, kRoundMagic);
+      const double bs = __dadd_rn(rm, -kRoundMagic);      // rint(rb)
+      const double dl = fma(bs, h, w0);
+      const double Dd = DB.x * dl;
+      ln.e0 = static_cast<float>(fma(Dd, dl, (SF.x * qu) * qu));
+      ln.d1 = static_cast<float>(two_h * Dd);
+      ln.c2 = __int_as_float(__double2loint(SF.y));
+      ln.nbs = __int_as_float(0x4B400000 - __double2loint(rm)) - 12582912.0f;   // float(-bs)
     }
   }
+  return ln;
 }
 
-// total += block sum, per warp, lanes stride over the region.  With float totals the
-// rounding residual of the addition (Knuth's TwoSum, exact) stays in the block-sum slot
-// and is carried into the next block, so nothing is lost to the float total.
-__device__ __forceinline__ void flush_block(
-  total_t * __restrict__ acc_d, float * __restrict__ acc_f, uint32_t RR, uint32_t lane)
+// Rows [lo, hi) of a phase in which some lane's cell is stiff (a cluster of near-identical
+// points: |I| ~ 1e17, inf / NaN, or D >= 0): every lane takes the reference's own grouping
+// ((q^T I) q, ndt_model.cpp:113-114) without FMA, so that it cancels exactly where the
+// reference cancels.
+__device__ __forceinline__ void stiff_rows(
+  float (&acc)[kMaxRY], bool occ, const double * __restrict__ rec, uint32_t rank, double xa,
+  double poy, const double * __restrict__ dlin_rows, uint32_t lo, uint32_t hi)
 {
-  for (uint32_t k = lane; k < RR; k += 32) {
-#ifdef NDT2D_REGION_DOUBLE_TOTALS
-    acc_d[k] += static_cast<double>(acc_f[k]);
-    acc_f[k] = 0.0f;
-#else
-    const float tot = acc_d[k], blk = acc_f[k];
-    const float t = __fadd_rn(tot, blk);
-    const float bb = __fsub_rn(t, tot);
-    const float err = __fadd_rn(__fsub_rn(tot, __fsub_rn(t, bb)), __fsub_rn(blk, bb));
-    acc_d[k] = t;
-    acc_f[k] = err;
-#endif
+  double2 mean = make_double2(0.0, 0.0), i0010 = mean, i0111 = mean;
+  if (occ) {
+    const double2 * r2 = reinterpret_cast<const double2 *>(
+      rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+    mean = __ldg(r2);
+    i0010 = __ldg(r2 + 1);
+    i0111 = __ldg(r2 + 2);
   }
-}
-
-// Value of candidate k after the last flush (total + the residual still in the slot).
-__device__ __forceinline__ double total_value(
-  const total_t * __restrict__ acc_d, const float * __restrict__ acc_f, uint32_t k)
-{
-#ifdef NDT2D_REGION_DOUBLE_TOTALS
-  return acc_d[k];
-#else
-  return static_cast<double>(acc_d[k]) + static_cast<double>(acc_f[k]);
-#endif
+  const double qx = __dsub_rn(xa, mean.x);
+#pragma unroll
+  for (uint32_t b = 0; b < kMaxRY; ++b) {
+    if (b >= lo && b < hi) {
+      const double yb = __dadd_rn(poy, dlin_rows[b]);
+      const double qy = __dsub_rn(yb, mean.y);
+      const double r0 = __dadd_rn(__dmul_rn(qx, i0010.x), __dmul_rn(qy, i0010.y));
+      const double r1 = __dadd_rn(__dmul_rn(qx, i0111.x), __dmul_rn(qy, i0111.y));
+      const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
+      const float f = exp2f(static_cast<float>(e * kLog2e));
+      acc[b] += occ ? f : 0.0f;
+    }
+  }
 }
 
 // Pre-pass of the search: for every (theta slice, scan point) the padded cell
-// coordinate of the FIRST column of each of the Q region columns (x) and of the
-// first row of each of the Q region rows (y).  The Q*Q regions of a slice share
-// them, so computing them here instead of inside every job removes a factor Q
-// of threshold lookups.  Layout: coords[((it * 2 + axis) * Q + q) * n_pts_pad + i], u16.
+// coordinate of the FIRST column of each of the Qx region columns (x) and of the
+// first row of each of the Qy region rows (y).  The Qx*Qy regions of a slice share
+// them, so computing them here instead of inside every job removes a factor ~Q
+// of threshold lookups.  Layout: coords[(it * (Qx + Qy) + q) * n_pts_pad + i], u16,
+// q < Qx: x of region column q, q >= Qx: y of region row q - Qx.
 __global__ void __launch_bounds__(128) region_coords_kernel(
-  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t Rw, uint32_t Q,
-  uint32_t n_pts_pad, uint16_t * __restrict__ coords)
+  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t RX, uint32_t RY,
+  uint32_t Qx, uint32_t Qy, uint32_t n_pts_pad, uint16_t * __restrict__ coords)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sv.n_pts) {return;}
@@ -275,38 +243,39 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
     const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
     const double ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
     const double oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-    uint16_t * cx = coords + (static_cast<size_t>(it) * 2 * Q) * n_pts_pad + i;
-    uint16_t * cy = cx + static_cast<size_t>(Q) * n_pts_pad;
-    for (uint32_t q = 0; q < Q; ++q) {
-      const double dl = sv.dlin[q * Rw];
+    uint16_t * cx = coords + (static_cast<size_t>(it) * (Qx + Qy)) * n_pts_pad + i;
+    uint16_t * cy = cx + static_cast<size_t>(Qx) * n_pts_pad;
+    for (uint32_t q = 0; q < Qx; ++q) {
       cx[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
-          __dadd_rn(ox, dl), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell));
+          __dadd_rn(ox, sv.dlin[q * RX]), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell));
+    }
+    for (uint32_t q = 0; q < Qy; ++q) {
       cy[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
-          __dadd_rn(oy, dl), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell));
+          __dadd_rn(oy, sv.dlin[q * RY]), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell));
     }
   }
 }
 
 // Per-candidate score of one job from its sums, warp argmin + the six covariance
-// sums -> the job's 9-double record.  sums[k], k = a * Rw + b.
+// sums -> the job's 9-double record.  sums(b) = this lane's column (dx index jx0 + lane), row b.
 template<typename SUMS>
 __device__ __forceinline__ void job_epilogue(
   SUMS sums, const SearchView & sv, uint32_t job, uint32_t itheta,
-  uint32_t Rw, uint32_t jx0, uint32_t jy0, uint32_t nxc, uint32_t nyc, uint32_t lane,
+  uint32_t jx0, uint32_t jy0, uint32_t nxc, uint32_t nyc, uint32_t lane,
   double * __restrict__ job_partials, double * __restrict__ scores)
 {
   const uint32_t n_lin = sv.n_lin;
   const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
-  const uint32_t RR = Rw * Rw, inv_rw = 65536u / Rw + 1u;
   Best best{0.0, kNoIndex};
   double sum[6] = {0, 0, 0, 0, 0, 0};
-  for (uint32_t k = lane; k < RR; k += 32) {
-    const uint32_t a = (k * inv_rw) >> 16, b = k - a * Rw;
-    if (a < nxc && b < nyc) {
-      const double score = -sums(k);
-      const double dx = sv.dlin[jx0 + a], dy = sv.dlin[jy0 + b];
-      const uint64_t gi = static_cast<uint64_t>(itheta) * n_cand +
-        static_cast<uint64_t>(jx0 + a) * n_lin + (jy0 + b);
+  if (lane < nxc) {
+    const double dx = sv.dlin[jx0 + lane];
+    const uint64_t g0 = static_cast<uint64_t>(itheta) * n_cand +
+      static_cast<uint64_t>(jx0 + lane) * n_lin + jy0;
+    for (uint32_t b = 0; b < nyc; ++b) {
+      const double score = -sums(b);
+      const double dy = sv.dlin[jy0 + b];
+      const uint64_t gi = g0 + b;
       if (scores) {scores[gi] = score;}
       best_merge(best, score, static_cast<double>(gi));
       sum[0] += score;
@@ -332,19 +301,19 @@ __device__ __forceinline__ void job_epilogue(
 
 // Small searches split every job's scan points into P chunks (more warps in flight,
 // shorter critical path); this kernel adds the chunk sums of a job in chunk order
-// (deterministic) and finishes it.  One warp per job.
+// (deterministic) and finishes it.  One warp per job; chunk sums are [row][lane].
 __global__ void __launch_bounds__(256) region_chunk_reduce_kernel(
-  SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs, uint32_t P,
-  double * __restrict__ chunk_sums, double * __restrict__ job_partials,
-  double * __restrict__ scores)
+  SearchView sv, uint32_t theta_begin, uint32_t RX, uint32_t RY, uint32_t Qx, uint32_t Qy,
+  uint32_t n_jobs, uint32_t P, double * __restrict__ chunk_sums,
+  double * __restrict__ job_partials, double * __restrict__ scores)
 {
   const uint32_t job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (job >= n_jobs) {return;}
-  const uint32_t QQ = Q * Q, RR = Rw * Rw;
+  const uint32_t QQ = Qx * Qy, RR = 32u * RY;
   const uint32_t it = job / QQ, rr = job - it * QQ;
-  const uint32_t rx = rr / Q, ry = rr - rx * Q;
-  const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
-  const uint32_t nxc = min(Rw, sv.n_lin - jx0), nyc = min(Rw, sv.n_lin - jy0);
+  const uint32_t rx = rr / Qy, ry = rr - rx * Qy;
+  const uint32_t jx0 = rx * RX, jy0 = ry * RY;
+  const uint32_t nxc = min(RX, sv.n_lin - jx0), nyc = min(RY, sv.n_lin - jy0);
   double * first = chunk_sums + static_cast<size_t>(job) * P * RR;
   for (uint32_t k = lane; k < RR; k += 32) {
     double t = first[k];
@@ -352,25 +321,26 @@ __global__ void __launch_bounds__(256) region_chunk_reduce_kernel(
     first[k] = t;
   }
   __syncwarp();
-  job_epilogue([first](uint32_t k) {return first[k];}, sv, job,
-    theta_begin + it * sv.theta_stride, Rw, jx0, jy0, nxc, nyc, lane, job_partials, scores);
+  job_epilogue([first, lane](uint32_t b) {return first[b * 32u + lane];}, sv, job,
+    theta_begin + it * sv.theta_stride, jx0, jy0, nxc, nyc, lane, job_partials, scores);
 }
 
 template<bool SMEM_TAB, bool PRE>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
-  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
-  uint32_t tab_d_bytes, uint32_t tab_thr_bytes, double * __restrict__ job_partials,
-  double * __restrict__ scores, uint32_t * __restrict__ job_counter,
-  unsigned long long * __restrict__ stats, const uint16_t * __restrict__ coords,
-  uint32_t n_pts_pad, uint32_t P, uint32_t chunk_points, double * __restrict__ chunk_sums)
+  ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t RX, uint32_t RY, uint32_t Qx,
+  uint32_t Qy, uint32_t n_jobs, uint32_t tab_d_bytes, uint32_t tab_thr_bytes,
+  double * __restrict__ job_partials, double * __restrict__ scores,
+  uint32_t * __restrict__ job_counter, unsigned long long * __restrict__ stats,
+  const uint16_t * __restrict__ coords, uint32_t n_pts_pad, uint32_t P, uint32_t chunk_points,
+  double * __restrict__ chunk_sums)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long n_useful = 0, n_items = 0;  // warp-uniform tallies (lane 0 reports)
 
-  // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp acc_d / xs / ys / acc_f]
+  // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp double totals]
   const uint32_t * occd_tab;
   const double * thr_x_tab;
   const double * thr_y_tab;
@@ -392,11 +362,7 @@ search_region_kernel(
     thr_x_tab = mv.thr_x;
     thr_y_tab = mv.thr_y;
   }
-  // per warp: xs[32], ys[32] (double), totals, float block sums
-  double * xs = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
-  double * ys = xs + 32;
-  total_t * acc_d = reinterpret_cast<total_t *>(ys + 32);
-  float * acc_f = reinterpret_cast<float *>(acc_d + kAccEntries);
+  double * tot = reinterpret_cast<double *>(sp + static_cast<size_t>(warp) * kWarpSmemBytes);
 
   if (SMEM_TAB) {
     __syncthreads();       // mbarrier initialised before anyone polls it
@@ -432,18 +398,15 @@ static_assert(sizeof(BatchEntry) <= kBatchSlotBytes && sizeof(BatchEntry) % 4 ==
 // no coordinate pre-pass.  All searches share the lattice (theta_begin = 0, stride 1).
 __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_batch_kernel(
-  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
-  uint32_t P, uint32_t chunk_points, uint32_t * __restrict__ job_counter,
-  unsigned long long * __restrict__ stats)
+  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t RX, uint32_t RY, uint32_t Qx,
+  uint32_t Qy, uint32_t n_jobs, uint32_t P, uint32_t chunk_points,
+  uint32_t * __restrict__ job_counter, unsigned long long * __restrict__ stats)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long n_useful = 0, n_items = 0;
   unsigned char * sp = smem_raw + static_cast<size_t>(warp) * (kWarpSmemBytes + kBatchSlotBytes);
-  double * xs = reinterpret_cast<double *>(sp);
-  double * ys = xs + 32;
-  total_t * acc_d = reinterpret_cast<total_t *>(ys + 32);
-  float * acc_f = reinterpret_cast<float *>(acc_d + kAccEntries);
+  double * tot = reinterpret_cast<double *>(sp);
   BatchEntry * slot = reinterpret_cast<BatchEntry *>(sp + kWarpSmemBytes);
   uint32_t cur_search = 0xffffffffu;
   constexpr bool PRE = false, SMEM_TAB = false;
@@ -475,29 +438,48 @@ search_region_batch_kernel(
 #undef NDT2D_BODY_CHUNKS
 }
 
+// Largest region of this lattice: RY rows inside one cell ((RY - 1) * step < cell), RX
+// columns inside two ((RX - 1) * step < 2 cells).
+void full_region(double cell_size, double linear_res, uint32_t n_lin, uint32_t * RX, uint32_t * RY)
+{
+  uint32_t ry = 1, rx = 1;
+  if (linear_res > 0.0 && cell_size > 0.0) {
+    const double ratio = cell_size / linear_res * (1.0 - 1e-9);
+    ry = ratio >= static_cast<double>(kMaxRY) ? kMaxRY : static_cast<uint32_t>(ratio) + 1u;
+    rx = 2.0 * ratio >= static_cast<double>(kMaxRX) ? kMaxRX : static_cast<uint32_t>(2.0 * ratio) + 1u;
+  }
+  if (ry > n_lin) {ry = n_lin ? n_lin : 1u;}
+  if (rx > n_lin) {rx = n_lin ? n_lin : 1u;}
+  *RX = rx;
+  *RY = ry;
+}
+
 // n_searches > 1: a batch of searches of this shape shares the launch, so regions shrink (and
 // points get chunked) only as far as the whole batch needs to fill the machine.
 RegionPlan make_plan(const GridDesc & g, uint32_t n_theta, uint32_t n_lin, double linear_res,
   uint32_t n_searches = 1)
 {
   RegionPlan pl{};
-  // (Rw - 1) * step < cell keeps a region inside a 2 x 2 cell neighbourhood
-  uint32_t Rw = 1;
-  if (linear_res > 0.0 && g.cell_size > 0.0) {
-    const double ratio = g.cell_size / linear_res * (1.0 - 1e-9);
-    Rw = ratio >= static_cast<double>(kMaxRw) ? kMaxRw : static_cast<uint32_t>(ratio) + 1u;
-  }
-  if (Rw > kMaxRw) {Rw = kMaxRw;}
-  if (Rw > n_lin) {Rw = n_lin ? n_lin : 1u;}
-  // small searches: more, smaller regions so that every SM gets work
+  uint32_t RX = 1, RY = 1;
+  full_region(g.cell_size, linear_res, n_lin, &RX, &RY);
+  // small searches: more, smaller regions so that every SM gets work (rows first: the
+  // columns are the lanes)
   for (;;) {
-    const uint32_t q = (n_lin + Rw - 1) / Rw;
-    if (static_cast<uint64_t>(n_theta) * q * q * n_searches >= kTargetJobs || Rw <= 6) {break;}
-    Rw = (Rw + 1) / 2;
+    const uint32_t qx = (n_lin + RX - 1) / RX, qy = (n_lin + RY - 1) / RY;
+    if (static_cast<uint64_t>(n_theta) * qx * qy * n_searches >= kTargetJobs) {break;}
+    if (RY > 6) {
+      RY = (RY + 1) / 2;
+    } else if (RX > 8) {
+      RX = (RX + 1) / 2;
+    } else {
+      break;
+    }
   }
-  pl.Rw = Rw;
-  pl.Q = (n_lin + Rw - 1) / Rw;
-  pl.n_jobs = n_theta * pl.Q * pl.Q;
+  pl.RX = RX;
+  pl.RY = RY;
+  pl.Qx = (n_lin + RX - 1) / RX;
+  pl.Qy = (n_lin + RY - 1) / RY;
+  pl.n_jobs = n_theta * pl.Qx * pl.Qy;
   pl.thr_doubles = g.size_x + 2 + g.size_y + 2;
   const size_t d_bytes = (static_cast<size_t>(g.n_words) * 4 + 15) & ~size_t(15);
   const size_t t_bytes = (static_cast<size_t>(pl.thr_doubles) * 8 + 15) & ~size_t(15);
@@ -520,12 +502,18 @@ void plan_chunks(RegionPlan & pl, uint32_t n_pts, size_t chunk_cap_doubles, uint
   if (pl.n_jobs == 0 || steps < 2 || jobs_in_flight >= kChunkTargetWork) {return;}
   uint32_t P = static_cast<uint32_t>((kChunkTargetWork + jobs_in_flight - 1) / jobs_in_flight);
   if (P > steps) {P = steps;}
-  const size_t per_chunk = static_cast<size_t>(pl.n_jobs) * pl.Rw * pl.Rw;
+  const size_t per_chunk = static_cast<size_t>(pl.n_jobs) * 32u * pl.RY;
   if (per_chunk * P > chunk_cap_doubles) {P = static_cast<uint32_t>(chunk_cap_doubles / per_chunk);}
   if (P < 2) {return;}
   const uint32_t spc = (steps + P - 1) / P;
   pl.P = (steps + spc - 1) / spc;
   pl.chunk_points = spc * 32u;
+}
+
+size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
+{
+  const size_t n_pts_pad = (static_cast<size_t>(n_pts) + 31u) & ~size_t(31);
+  return static_cast<size_t>(n_theta) * (pl.Qx + pl.Qy) * n_pts_pad * sizeof(uint16_t);
 }
 
 template<bool S, bool PRE>
@@ -558,46 +546,41 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
   if (PRE) {
     dim3 grid((sv.n_pts + 127u) / 128u, min(n_theta, 65535u));
-    region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.Rw, pl.Q,
-      n_pts_pad, d_coords);
+    region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.RX, pl.RY,
+      pl.Qx, pl.Qy, n_pts_pad, d_coords);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   const uint32_t d_bytes = pl.smem_tab ? ((mv.g.n_words * 4u + 15u) & ~15u) : 0u;
   const uint32_t t_bytes = pl.smem_tab ? pl.tab_bytes - d_bytes : 0u;
   kernel<<<pl.grid, kWarps * 32, pl.smem_bytes, stream>>>(
-    mv, sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, d_bytes, t_bytes, d_job_partials, d_scores,
-    d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1, d_coords, n_pts_pad, pl.P,
-    pl.chunk_points, d_chunk_sums);
+    mv, sv, theta_begin, pl.RX, pl.RY, pl.Qx, pl.Qy, pl.n_jobs, d_bytes, t_bytes, d_job_partials,
+    d_scores, d_counter, reinterpret_cast<unsigned long long *>(d_counter) + 1, d_coords,
+    n_pts_pad, pl.P, pl.chunk_points, d_chunk_sums);
   NDT2D_LAUNCH_CHECK(ctr);
   if (pl.P > 1) {
     region_chunk_reduce_kernel<<<(pl.n_jobs + 7u) / 8u, 256, 0, stream>>>(
-      sv, theta_begin, pl.Rw, pl.Q, pl.n_jobs, pl.P, d_chunk_sums, d_job_partials, d_scores);
+      sv, theta_begin, pl.RX, pl.RY, pl.Qx, pl.Qy, pl.n_jobs, pl.P, d_chunk_sums, d_job_partials,
+      d_scores);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   return NDT2D_OK;
 }
 
-size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
-{
-  const size_t n_pts_pad = (static_cast<size_t>(n_pts) + 31u) & ~size_t(31);
-  return static_cast<size_t>(n_theta) * 2 * pl.Q * n_pts_pad * sizeof(uint16_t);
-}
-
 // region_chunk_reduce_kernel for a batch: one warp per (search, job).
 __global__ void __launch_bounds__(256) region_chunk_reduce_batch_kernel(
-  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t Rw, uint32_t Q, uint32_t n_jobs,
-  uint32_t P)
+  const BatchEntry * __restrict__ batch, uint32_t n_batch, uint32_t RX, uint32_t RY, uint32_t Qx,
+  uint32_t Qy, uint32_t n_jobs, uint32_t P)
 {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (gw >= n_batch * n_jobs) {return;}
   const uint32_t bj = gw / n_jobs, job = gw - bj * n_jobs;
   const BatchEntry & e = batch[bj];
-  const uint32_t QQ = Q * Q, RR = Rw * Rw;
+  const uint32_t QQ = Qx * Qy, RR = 32u * RY;
   const uint32_t it = job / QQ, rr = job - it * QQ;
-  const uint32_t rx = rr / Q, ry = rr - rx * Q;
-  const uint32_t jx0 = rx * Rw, jy0 = ry * Rw;
+  const uint32_t rx = rr / Qy, ry = rr - rx * Qy;
+  const uint32_t jx0 = rx * RX, jy0 = ry * RY;
   const uint32_t n_lin = e.sv.n_lin;
-  const uint32_t nxc = min(Rw, n_lin - jx0), nyc = min(Rw, n_lin - jy0);
+  const uint32_t nxc = min(RX, n_lin - jx0), nyc = min(RY, n_lin - jy0);
   double * first = e.chunk_sums + static_cast<size_t>(job) * P * RR;
   for (uint32_t k = lane; k < RR; k += 32) {
     double t = first[k];
@@ -605,11 +588,20 @@ __global__ void __launch_bounds__(256) region_chunk_reduce_batch_kernel(
     first[k] = t;
   }
   __syncwarp();
-  job_epilogue([first](uint32_t k) {return first[k];}, e.sv, job, it, Rw, jx0, jy0, nxc, nyc, lane,
-    e.job_partials, nullptr);
+  job_epilogue([first, lane](uint32_t b) {return first[b * 32u + lane];}, e.sv, job, it, jx0, jy0,
+    nxc, nyc, lane, e.job_partials, nullptr);
 }
 
 }  // namespace
+
+uint32_t ndt2d_region_dilate_x(double cell_size, double linear_res, uint32_t n_lin)
+{
+  uint32_t RX = 1, RY = 1;
+  full_region(cell_size, linear_res, n_lin ? n_lin : 1u, &RX, &RY);
+  // columns of one region reach into a third cell column once (RX - 1) * step >= cell
+  return (linear_res > 0.0 && static_cast<double>(RX - 1u) * linear_res >= cell_size * (1.0 - 1e-9)) ?
+         2u : 1u;
+}
 
 int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, double linear_res,
   uint32_t max_pts, uint32_t n_searches, RegionBatchPlan * out)
@@ -620,12 +612,14 @@ int ndt2d_region_batch_plan(double cell_size, uint32_t n_ang, uint32_t n_lin, do
   // chunk the points only while the batch as a whole is short of work, capped so that a
   // search's chunk sums stay small
   plan_chunks(pl, max_pts, size_t(1) << 22, n_searches ? n_searches : 1u);
-  out->Rw = pl.Rw;
-  out->Q = pl.Q;
+  out->RX = pl.RX;
+  out->RY = pl.RY;
+  out->Qx = pl.Qx;
+  out->Qy = pl.Qy;
   out->n_jobs = pl.n_jobs;
   out->P = pl.P;
   out->chunk_points = pl.chunk_points;
-  out->chunk_doubles = pl.P > 1 ? static_cast<size_t>(pl.n_jobs) * pl.P * pl.Rw * pl.Rw : 0;
+  out->chunk_doubles = pl.P > 1 ? static_cast<size_t>(pl.n_jobs) * pl.P * 32u * pl.RY : 0;
   return NDT2D_OK;
 }
 
@@ -650,13 +644,13 @@ int ndt2d_launch_search_region_batch(
   if (total >= (1ull << 32)) {return NDT2D_ERR_SIZE;}
   const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(total, configured_sms[slot]));
   search_region_batch_kernel<<<grid, kWarps * 32, smem, stream>>>(
-    d_batch, n_batch, pl.Rw, pl.Q, pl.n_jobs, pl.P, pl.chunk_points, d_counter,
+    d_batch, n_batch, pl.RX, pl.RY, pl.Qx, pl.Qy, pl.n_jobs, pl.P, pl.chunk_points, d_counter,
     reinterpret_cast<unsigned long long *>(d_counter) + 1);
   NDT2D_LAUNCH_CHECK(ctr);
   if (pl.P > 1) {
     const uint32_t warps = n_batch * pl.n_jobs;
     region_chunk_reduce_batch_kernel<<<(warps + 7u) / 8u, 256, 0, stream>>>(
-      d_batch, n_batch, pl.Rw, pl.Q, pl.n_jobs, pl.P);
+      d_batch, n_batch, pl.RX, pl.RY, pl.Qx, pl.Qy, pl.n_jobs, pl.P);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   return NDT2D_OK;
@@ -676,7 +670,7 @@ size_t ndt2d_region_scratch_doubles(double cell_size, uint32_t n_ang, uint32_t n
     const uint32_t t = static_cast<uint32_t>(nt < na ? nt : na);
     const RegionPlan pl = make_plan(g, t, n_lin ? n_lin : 1, linear_res);
     const uint64_t upto = (2 * nt < na) ? 2 * nt : na;
-    const size_t jobs = static_cast<size_t>(upto) * pl.Q * pl.Q;
+    const size_t jobs = static_cast<size_t>(upto) * pl.Qx * pl.Qy;
     worst = jobs > worst ? jobs : worst;
     if (nt >= na) {break;}
   }
@@ -691,21 +685,21 @@ size_t ndt2d_region_coords_bytes(double cell_size, uint32_t n_ang, uint32_t n_li
   // sized for the full theta range; a launch over a sub-range (other region plan)
   // uses the table only if its own needs fit (ndt2d_launch_search_region)
   const RegionPlan pl = make_plan(g, n_ang ? n_ang : 1, n_lin ? n_lin : 1, linear_res);
-  const size_t worst = pl.Q >= 3 ? coords_bytes(pl, n_ang ? n_ang : 1, n_pts) : 0;
+  const size_t worst = pl.Qx >= 3 ? coords_bytes(pl, n_ang ? n_ang : 1, n_pts) : 0;
   return worst <= cap_bytes ? worst : 0;  // 0: the search computes coordinates per job
 }
 
 size_t ndt2d_region_chunk_doubles(double cell_size, uint32_t n_ang, uint32_t n_lin,
   double linear_res, uint32_t n_pts)
 {
-  // any theta sub-range: at most ~2 * kChunkTargetWork (job, chunk) pairs of Rw^2 sums
-  // (regions of small searches are shrunk to <= 13 x 13 before chunking matters)
+  // any theta sub-range: at most ~2 * kChunkTargetWork (job, chunk) pairs of 32 x RY sums
+  // (regions of small searches are shrunk to <= 13 rows before chunking matters)
   (void)cell_size;
   (void)n_ang;
   (void)n_lin;
   (void)linear_res;
   if (n_pts < 64) {return 0;}
-  return static_cast<size_t>(2) * kChunkTargetWork * 13 * 13;
+  return static_cast<size_t>(2) * kChunkTargetWork * 32 * 13;
 }
 
 int ndt2d_launch_search_region(
@@ -718,7 +712,7 @@ int ndt2d_launch_search_region(
   *n_jobs = pl.n_jobs;
   plan_chunks(pl, sv.n_pts, sv.chunk_sums ? sv.chunk_cap_doubles : 0);
   // the pre-pass pays off when a slice has several regions per axis to share it
-  const bool pre = d_coords && pl.Q >= 3 && sv.n_pts > 0 &&
+  const bool pre = d_coords && pl.Qx >= 3 && sv.n_pts > 0 &&
     coords_bytes(pl, n_theta, sv.n_pts) <= coords_cap_bytes;
 #define NDT2D_REGION_LAUNCH(S, P) \
   launch_one<S, P>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \

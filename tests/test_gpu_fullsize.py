@@ -3,6 +3,8 @@ directly; where it cannot (config 4: 5.4e11 evaluations, hours on a CPU) the res
 through size-independent properties: partition invariance (theta slices, interleaved or
 contiguous, combine to the same answer), agreement of two independently written kernels on a
 sub-volume, candidate-count bookkeeping, and an oracle search of the window around the winner."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -154,6 +156,78 @@ def test_config4_full_search_winner_matches_oracle_window(o, big):
     est = w.query_pose + delta
     assert abs(est[0] - w.true_pose[0]) <= 0.011 and abs(est[1] - w.true_pose[1]) <= 0.011
     assert abs(est[2] - w.true_pose[2]) <= 0.0021
+
+
+GOLDEN4 = Path(__file__).resolve().parent / "golden" / "config4_full.npz"
+
+
+@pytest.fixture(scope="module")
+def golden4():
+    """tests/golden/config4_full.npz (tests/golden/make_config4_full.py): the oracle's sequential
+    search over ALL 3142 theta slices (one 16-double record per slice + their fold in loop order)
+    and, when has_reference == 1, the result of the compiled reference's own matchScan."""
+    g = np.load(GOLDEN4)
+    w = synth.config4()
+    # the fixture stores its inputs: the synthetic generator must still produce them
+    assert np.array_equal(g["map_points"], w.map_points) and np.array_equal(g["query_points"], w.query_points)
+    assert np.array_equal(g["query_pose"], w.query_pose) and np.array_equal(g["map_poses"], w.map_poses)
+    return g
+
+
+def test_config4_full_search_matches_golden(big, golden4):
+    """The production search over all 502,720,000 candidates against the reference-held answer
+    (scan_matcher_ndt.cpp:103-148): same winner, score and the k/u/s covariance to 1e-5."""
+    w, m, (score, delta, written, cov, _) = big
+    g = golden4
+    assert int(g["candidates"][0]) == 502_720_000
+    assert written == bool(g["written"][0])
+    assert np.array_equal(delta, g["delta"]), (delta, g["delta"])
+    np.testing.assert_allclose(score, g["score"][0], rtol=RTOL)
+    np.testing.assert_allclose(cov, g["cov"], rtol=RTOL, atol=RTOL * np.abs(g["cov"]).max())
+    if int(g["has_reference"][0]):
+        # the unmodified reference's own matchScan (oracle/_ref), ~50 minutes on one core
+        assert np.array_equal(delta, g["ref_delta"])
+        np.testing.assert_allclose(score, g["ref_score"][0], rtol=RTOL)
+        np.testing.assert_allclose(cov, g["ref_cov"], rtol=RTOL, atol=RTOL * np.abs(g["ref_cov"]).max())
+
+
+def _check_partial(dev, recs, what):
+    """A device partial record over some theta slices against the oracle's records of those slices."""
+    k = int(np.argmin(recs[:, 0]))                     # first minimum == strict '<' in loop order
+    best, best_idx = recs[k, 0], recs[k, 1]
+    assert dev[12] == recs[:, 12].sum() and dev[13] == recs[0, 13], what
+    np.testing.assert_allclose(dev[0], best, rtol=RTOL, err_msg=str(what))
+    if dev[1] != best_idx:
+        # another candidate may only win where the reference's scores tie within the tolerance
+        near = recs[np.abs(recs[:, 0] - best) <= RTOL * abs(best)]
+        assert near.shape[0] > 1 or abs(dev[0] - best) <= RTOL * abs(best), (what, dev[:2], best, best_idx)
+    sums = recs[:, 2:12].sum(0)
+    np.testing.assert_allclose(dev[2:12], sums, rtol=RTOL, atol=RTOL * np.abs(sums).max(), err_msg=str(what))
+
+
+def test_config4_every_slice_matches_golden(big, golden4):
+    """Every one of the 3142 theta slices on its own (160,000 candidates each: the small-search
+    plans of the region kernel), and the full-size plan in blocks of 64 slices, against the
+    oracle's per-slice records: best score, best candidate, the ten k/u/s sums."""
+    w, m, _ = big
+    recs = golden4["slice_records"]
+    na, nl = m.search_shape()
+    assert recs.shape == (na, 16)
+    m.stage_scan(w.query_pose, w.query_points)
+    n_index_diff = 0
+    for i in range(na):
+        m.search_staged(i, i + 1)
+        p = m.fetch_partial()
+        _check_partial(p, recs[i:i + 1], ("slice", i))
+        n_index_diff += int(p[1] != recs[i, 1])
+    assert n_index_diff <= na // 100, n_index_diff      # near-ties are rare
+    for lo in range(0, na, 64):
+        hi = min(na, lo + 64)
+        m.search_staged(lo, hi)
+        _check_partial(m.fetch_partial(), recs[lo:hi], ("block", lo, hi))
+    # strided, as a rank of an 8-GPU search sees it
+    m.search_staged(3, na, stride=8)
+    _check_partial(m.fetch_partial(), recs[3::8], ("stride", 3, 8))
 
 
 @pytest.mark.parametrize("world", [2, 8])

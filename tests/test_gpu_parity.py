@@ -167,7 +167,7 @@ def test_build_degenerate_cell_is_nan_like_reference(o):
 
 # ------------------------------------------------------------------ search
 @pytest.mark.parametrize("beams", [360, 100])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
 def test_match_scan_config1(o, beams, variant):
     w = synth.config1(laser_max_beams=beams)
     m = ScanMatcherNDT.from_params(w.params, kernel_variant=variant)
