@@ -61,6 +61,8 @@ def _run(cmd, log: Path | None = None):
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
+    # A/B experiments: NDT2D_NVCC_EXTRA="-DNDT2D_REGION_WARPS=20" python -m ndt_2d_b200.build --force
+    extra = os.environ.get("NDT2D_NVCC_EXTRA", "").split()
     OBJDIR.mkdir(parents=True, exist_ok=True)
     jobs = []
     for src in CU_SOURCES + CXX_SOURCES:
@@ -71,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if jobs:
         def compile_one(job):
             s, o = job
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", str(s), "-o", str(o)]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", str(s), "-o", str(o)]
             if verbose:
                 print(" ".join(cmd))
             _run(cmd, log=OBJDIR / (s.name + ".log"))

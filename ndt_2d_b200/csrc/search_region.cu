@@ -56,6 +56,7 @@ using namespace ndt2d_dev;
 
 constexpr uint32_t kMaxRX = 32;                 // region columns (candidates along dx) = lanes
 constexpr uint32_t kMaxRY = 25;                 // region rows (candidates along dy) = registers
+constexpr uint32_t kPairs = (kMaxRY + 1) / 2;   // rows are held and evaluated two at a time
 #ifndef NDT2D_REGION_WARPS
 #define NDT2D_REGION_WARPS 24
 #endif
@@ -144,16 +145,53 @@ __device__ __forceinline__ uint32_t padded_coord(
   return pc;
 }
 
-// One row of the region for this lane's column: b' = B - bs, log2 L = c2 b'^2 + d1 b' + e0.
-// NDT2D_ROW_DOWN(B) sits under `case B + 1` of a switch on the number of rows (enter there,
-// fall through down to row 0); NDT2D_ROW_UP(B) under `case B` of a switch on the first row.
-#define NDT2D_ROW_EVAL(B) \
+// Two rows (2J, 2J + 1) of the region for this lane's column, packed FP32 (sm_100 FFMA2 / FADD2):
+// b' = row - bs, log2 L = c2 b'^2 + d1 b' + e0.  EE carries e0 per row (-inf masks a row).
+#define NDT2D_PAIR(J, EE) \
   { \
-    const float bp = static_cast<float>(B) + nbs; \
-    acc[B] += ex2_ftz(fmaf(fmaf(c2, bp, d1), bp, e0)); \
+    const float2 bp = __fadd2_rn(make_float2(2.0f * (J), 2.0f * (J) + 1.0f), nbsp); \
+    const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
+    acc2[J] = __fadd2_rn(acc2[J], make_float2(ex2_ftz(e.x), ex2_ftz(e.y))); \
   }
-#define NDT2D_ROW_DOWN(B) case (B) + 1: NDT2D_ROW_EVAL(B)
-#define NDT2D_ROW_UP(B) case (B): NDT2D_ROW_EVAL(B)
+
+// Number of k in [0, n) with o + dl[k] < thr, for increasing dl (the replayed lattice): a
+// guess from the nominal step, fixed up with the reference's own additions (exact).
+__device__ __forceinline__ uint32_t count_below(
+  double o, const double * __restrict__ dl, uint32_t n, double thr, double inv_h)
+{
+  const double g = (thr - __dadd_rn(o, __ldg(dl))) * inv_h;
+  uint32_t k = g >= static_cast<double>(n) ? n : (g > 0.0 ? static_cast<uint32_t>(g) + 1u : 0u);
+  k = min(k, n);
+  while (k > 0u && !(__dadd_rn(o, __ldg(dl + k - 1u)) < thr)) {--k;}
+  while (k < n && __dadd_rn(o, __ldg(dl + k)) < thr) {++k;}
+  return k;
+}
+
+// Occupancy bits of padded cells p, p + 1, p + 2 and the record rank of the first occupied
+// one among them (ranks follow the bit order, also across a word boundary).
+__device__ __forceinline__ void occ3(
+  const uint2 * __restrict__ occ, uint32_t p, uint32_t & bits3, uint32_t & rank_base)
+{
+  const uint32_t w = p >> 5, sh = p & 31u;
+  const uint2 a = __ldg(occ + w);
+  const uint32_t hi = sh > 29u ? __ldg(occ + w + 1u).x : 0u;   // (the buffer has 4 words of slack)
+  bits3 = __funnelshift_r(a.x, hi, sh) & 7u;
+  rank_base = a.y + __popc(a.x & ((1u << sh) - 1u));
+}
+
+// Float block sums -> double totals (lane-private column of shared memory).
+__device__ __forceinline__ void flush_pairs(
+  float2 (&acc2)[kPairs], double * __restrict__ tot, uint32_t RY, uint32_t lane)
+{
+#pragma unroll
+  for (uint32_t j = 0; j < kPairs; ++j) {
+    if (2u * j < RY) {
+      tot[(2u * j) * 32u + lane] += static_cast<double>(acc2[j].x);
+      if (2u * j + 1u < RY) {tot[(2u * j + 1u) * 32u + lane] += static_cast<double>(acc2[j].y);}
+      acc2[j] = make_float2(0.0f, 0.0f);
+    }
+  }
+}
 
 // A lane's cell along its candidate column, vertex form, float coefficients.
 struct VtxLine
@@ -199,7 +237,7 @@ __device__ __forceinline__ VtxLine vtx_setup(
 // ((q^T I) q, ndt_model.cpp:113-114) without FMA, so that it cancels exactly where the
 // reference cancels.
 __device__ __forceinline__ void stiff_rows(
-  float (&acc)[kMaxRY], bool occ, const double * __restrict__ rec, uint32_t rank, double xa,
+  float2 (&acc2)[kPairs], bool occ, const double * __restrict__ rec, uint32_t rank, double xa,
   double poy, const double * __restrict__ dlin_rows, uint32_t lo, uint32_t hi)
 {
   double2 mean = make_double2(0.0, 0.0), i0010 = mean, i0111 = mean;
@@ -220,7 +258,7 @@ __device__ __forceinline__ void stiff_rows(
       const double r1 = __dadd_rn(__dmul_rn(qx, i0111.x), __dmul_rn(qy, i0111.y));
       const double e = __dadd_rn(__dmul_rn(r0, qx), __dmul_rn(r1, qy));
       const float f = exp2f(static_cast<float>(e * kLog2e));
-      acc[b] += occ ? f : 0.0f;
+      if (b & 1u) {acc2[b >> 1].y += occ ? f : 0.0f;} else {acc2[b >> 1].x += occ ? f : 0.0f;}
     }
   }
 }
