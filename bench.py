@@ -6,13 +6,17 @@
 Workload (BASELINE.json configs[3], "Large correlative search"): one 1080-beam scan
 matched against a rolling NDT of 10 scans (0.25 m cells), +-2 m @0.01 m x +-pi @0.002 rad
 = 3142 x 400 x 400 = 502,720,000 candidate poses per matchScan.  One step = one
-matchScan.  With N GPUs the theta slices are split contiguously over the ranks
-(strong scaling: total work fixed) and the partial results are combined by ONE
-all-gather of a 128-byte record per rank + a device-side lexicographic reduce.
+matchScan.  With N GPUs the theta slices are INTERLEAVED over the ranks (rank r scores
+slices r, r + N, ...; strong scaling: total work fixed) and the 128-byte partial records are
+exchanged by peer stores from the search's last kernel into mailboxes in every rank's memory
+(NVLink; `--exchange nccl` keeps an all-gather), then reduced lexicographically on the device.
+`--single-process` drives the N GPUs from ONE process through one multi-device handle
+(ndt2d_params.devices), the way the C++ plugin does.
 
 Prints ONE JSON line (rank 0).  Keys: see the contract in the task statement; extra
 keys: `other_workloads` (the remaining BASELINE configs, timed outside the main
-region), `parity` (the checked result of the timed search).
+region), `parity` (the timed search's result against tests/golden/config4_full.npz -- the
+oracle over all 3142 slices + the compiled reference's own matchScan -- at every N).
 """
 from __future__ import annotations
 
@@ -105,12 +109,17 @@ def reference_sample(workload, n_theta: int, threads: int, prefer_ref: bool = Tr
     The UNMODIFIED reference (oracle/_ref, its sources compiled in place) is run with a
     narrower search_angular_size -- a legal parameter value -- so each thread scores
     n_theta x n_lin^2 candidates with exactly the per-candidate work of the full search.
-    Falls back to the C restatement (kind "port") only if oracle/_ref is missing."""
+    The threads' windows are spread EVENLY over the full +-pi range (thread t starts at slice
+    t * n_ang / threads of the full search): how much of the scan overlaps the map, and with it
+    the cost of a slice, varies with theta.  Falls back to the C restatement (kind "port")
+    only if oracle/_ref is missing.
+    -> (candidates/s, wall s, kind, candidates, per-thread seconds)"""
     from oracle import binding as B
     lib = B.load_ref() if prefer_ref else None
     kind = "reference" if lib is not None else "port"
     if lib is None:
         lib = B.load_oracle()
+    full = dict(workload.params)
     p = dict(workload.params)
     p["search_angular_size"] = 0.5 * n_theta * p["search_angular_resolution"]
     matchers = []
@@ -119,13 +128,20 @@ def reference_sample(workload, n_theta: int, threads: int, prefer_ref: bool = Tr
         m.add_scans(workload.map_poses, workload.map_offsets, workload.map_points)
         matchers.append(m)
     o = B.load_oracle()
+    na_full = o.loop_values(full["search_angular_size"], full["search_angular_resolution"], None, 0)
     na = o.loop_values(p["search_angular_size"], p["search_angular_resolution"], None, 0)
     nl = o.loop_values(p["search_linear_size"], p["search_linear_resolution"], None, 0)
     cand_per_thread = na * nl * nl
+    secs = [0.0] * threads
 
     def run(t):
-        pose = workload.query_pose + np.array([0.0, 0.0, t * n_theta * p["search_angular_resolution"]])
+        # centre of this thread's window = full-search slice  t * na_full / threads  (+ half a window)
+        k = (t * na_full) // threads
+        dth = -full["search_angular_size"] + (k + 0.5 * n_theta) * full["search_angular_resolution"]
+        pose = workload.query_pose + np.array([0.0, 0.0, dth])
+        t0 = time.perf_counter()
         matchers[t].match_scan(pose, workload.query_points)
+        secs[t] = time.perf_counter() - t0
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=run, args=(t,)) for t in range(threads)]
@@ -134,7 +150,7 @@ def reference_sample(workload, n_theta: int, threads: int, prefer_ref: bool = Tr
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    return cand_per_thread * threads / dt, dt, kind, cand_per_thread * threads
+    return cand_per_thread * threads / dt, dt, kind, cand_per_thread * threads, secs
 
 
 def run_reference_arm(args):
@@ -145,16 +161,20 @@ def run_reference_arm(args):
     w = synth.config4()
     threads = os.cpu_count() or 1
     n_theta = 2
-    vals, times = [], []
+    vals, times, per_thread = [], [], []
     kind, cands = "reference", 0
     for i in range(args.warmup + args.steps):
-        v, dt, kind, cands = reference_sample(w, n_theta, threads)
+        v, dt, kind, cands, secs = reference_sample(w, n_theta, threads)
         if i >= args.warmup:
             vals.append(v)
             times.append(dt)
+            per_thread.append(secs)
     value = float(np.mean(vals))
-    sample = (f"{threads} threads x {n_theta} theta slices x 400 x 400 candidates x 1080 beams per step "
-              f"(of 3142 slices), unmodified reference matchScan with a narrower search_angular_size")
+    pt = np.array(per_thread) / n_theta if per_thread else np.zeros((1, 1))
+    sample = (f"{threads} threads x {n_theta} theta slices x 400 x 400 candidates x 1080 beams per step, the "
+              f"threads' windows spread evenly over the 3142 slices of +-pi; unmodified reference matchScan "
+              f"with a narrower search_angular_size; seconds per slice across the windows: "
+              f"min {pt.min():.2f} / median {np.median(pt):.2f} / max {pt.max():.2f}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
@@ -487,6 +507,8 @@ def run_ours(args):
     gather_gbps = None
     if L.lib.ndt2d_probe_gather(local_rank, table_bytes, C.byref(g)) == 0:
         gather_gbps = float(g.value)
+    e = C.c_double(0.0)
+    ex2_peak = float(e.value) if L.lib.ndt2d_probe_ex2(local_rank, C.byref(e)) == 0 and e.value > 0 else None
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -495,11 +517,13 @@ def run_ours(args):
         except Exception:
             traffic = None
 
-    # ---- parity of the timed result against the oracle on a bounded window around the winner
-    parity = {"checked": False}
+    # ---- parity of the timed result: against the committed full-size golden at EVERY world
+    # size, plus (N = 1) a live oracle run on a bounded window around the winner
+    parity = golden_parity((score, delta, written, cov), args.scale)
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu, parity = cpu_baseline_and_parity(w, m, (score, delta, written, cov), args)
+        cpu, live = cpu_baseline_and_parity(w, m, (score, delta, written, cov), args)
+        parity["live_oracle_window"] = live
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -523,28 +547,27 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "matchScan_latency_ms": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "search_region_kernel", "kernel_ms": kernel_ms,
-                     "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "algorithmic bytes = 32 B x (candidate, point) pairs of this rank (SURVEY.md "
-                             "8d); the model (<100 KB) is shared-memory/L1 resident and 96% of the pairs are "
-                             "rejected by one bit test of a dilated occupancy bitmap, so DRAM traffic is ~0 "
-                             "and frac exceeds 1 by construction -- gather_roofline / useful_evaluations "
-                             "below are the informative denominators (DESIGN.md section 5)"},
-        "gather_roofline": None if gather_gbps is None else {
-            "peak": gather_gbps, "unit": "GB/s", "table_bytes": table_bytes,
-            "how": "ndt2d_probe_gather: random 32-B record reads from a table of the model's size, this device",
-            "achieved_all_pairs": achieved, "frac_all_pairs": achieved / gather_gbps,
-            "achieved_useful": useful * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9,
-            "frac_useful": useful * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9 / gather_gbps},
-        "sfu_roofline": {
-            "what": "Gaussian evaluations that reach an occupied cell (each needs one ex2 on the SFU) against "
-                    "the SFU issue rate: the arithmetic floor of this search; everything above it is bookkeeping",
-            "achieved": useful / (kernel_ms * 1e-3), "unit": "evaluations/s",
-            "peak": sm_count * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
-            "frac": (useful / (kernel_ms * 1e-3)) / (sm_count * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-            "peak_source": "SMs x 16 MUFU lanes/clk x sampled SM clock"},
+        "roofline": {
+            "bound": "sfu", "achieved": useful / (kernel_ms * 1e-3), "peak": ex2_peak, "unit": "evaluations/s",
+            "frac": (useful / (kernel_ms * 1e-3)) / ex2_peak if ex2_peak else None, "traffic": traffic,
+            "kernel": "search_region_kernel", "kernel_ms": kernel_ms,
+            "what": "Gaussian evaluations the reference makes too (a scan point in an occupied cell: "
+                    f"{useful} per launch, {100.0 * useful / max(my_candidates * n_pts, 1):.2f} % of the "
+                    "(candidate, point) pairs -- the rest are rejected exactly, 800 at a time, by one bit test) "
+                    "per second of the search kernel, against the MEASURED rate of the kernel's own evaluation "
+                    "recipe (2 packed FMAs, one ex2 on the SFU, one packed add per evaluation) run back to back "
+                    "on this device with no bookkeeping",
+            "peak_source": "measured on this device in this run: ndt2d_probe_ex2 (csrc/probe.cu)",
+            "nominal_sfu_issue_rate": sm_count * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6},
+        "algorithmic_gather_8d": {
+            "note": "SURVEY.md 8(d)'s byte model (one 32-B record gather per (candidate, point) pair) against "
+                    "the measured HBM peak; it is > 1 BY CONSTRUCTION for this design (the model is on-chip and "
+                    "96 % of the pairs are rejected by a bit test), so it is reported for reference only and "
+                    "is not the roofline",
+            "achieved_GBps": achieved, "hbm_peak_GBps": peak, "ratio": achieved / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes,
+            "gather_probe_GBps": gather_gbps, "gather_probe_table_bytes": table_bytes,
+            "useful_evaluations_x_32B_GBps": useful * ALGO_BYTES_PER_EVAL / (kernel_ms * 1e-3) / 1e9},
         "useful_evaluations": {"per_launch": useful, "fraction_of_pairs": useful / max(my_candidates * n_pts, 1),
                                "per_second": useful / (kernel_ms * 1e-3),
                                "point_region_items": stats["items"]},
@@ -565,13 +588,46 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def golden_parity(result, scale: float):
+    """The timed search's combined result against tests/golden/config4_full.npz: the oracle's
+    sequential search over ALL 3142 theta slices (tests/golden/make_config4_full.py) and, when the
+    file holds it, the result of the compiled reference's own single-threaded matchScan."""
+    path = ROOT / "tests" / "golden" / "config4_full.npz"
+    if scale != 1.0 or not path.exists():
+        return {"checked": False, "why": "no golden for this window" if scale != 1.0 else "golden file missing"}
+    g = np.load(path)
+    score, delta, written, cov = result
+    cov = np.asarray(cov, dtype=np.float64).reshape(3, 3)
+    scale_c = float(np.abs(g["cov"]).max())
+    out = {
+        "checked": True, "against": "tests/golden/config4_full.npz (oracle, all 3142 theta slices, "
+                                    "502,720,000 candidates, covariance included)",
+        "same_pose": bool(written == bool(g["written"][0]) and np.array_equal(np.asarray(delta), g["delta"])),
+        "score_rel_err": float(abs(score - g["score"][0]) / abs(g["score"][0])),
+        "cov_max_err_rel_to_largest": float(np.abs(cov - g["cov"]).max() / scale_c),
+        "golden_score": float(g["score"][0]), "device_score": float(score),
+        "golden_delta": g["delta"].tolist(), "device_delta": [float(x) for x in delta],
+        "tolerance": 1e-5,
+    }
+    if int(g["has_reference"][0]):
+        out["reference_matchScan"] = {
+            "what": "the unmodified reference's own matchScan over the full search (oracle/_ref, one core, "
+                    f"{float(g['ref_seconds'][0]):.0f} s when the fixture was made)",
+            "same_pose": bool(np.array_equal(np.asarray(delta), g["ref_delta"])),
+            "score_rel_err": float(abs(score - g["ref_score"][0]) / abs(g["ref_score"][0])),
+            "cov_max_err_rel_to_largest": float(np.abs(cov - g["ref_cov"]).max() / scale_c)}
+    out["ok"] = bool(out["same_pose"] and out["score_rel_err"] <= 1e-5 and
+                     out["cov_max_err_rel_to_largest"] <= 1e-5)
+    return out
+
+
 def cpu_baseline_and_parity(w, m, result, args):
     """cpu_baseline: single-threaded reference on a bounded theta sample (rank 0, N=1).
     parity: the reference's matchScan on a window centred on the device's winner must
     find the same candidate with the same score."""
     from oracle import binding as B
     n_theta = 16       # ~14 s of single-thread CPU work
-    value, dt, kind, cands = reference_sample(w, n_theta, 1)
+    value, dt, kind, cands, _ = reference_sample(w, n_theta, 1)
     cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
            "sample": f"{n_theta} of 3142 theta slices x 400 x 400 candidates x 1080 beams "
                      f"({cands} candidates, {dt:.1f} s), single thread, g++ -O3"}

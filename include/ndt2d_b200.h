@@ -408,36 +408,13 @@ NDT2D_API int ndt2d_occupancy_fetch(ndt2d_occupancy * g, int8_t * data, size_t c
 /* GB/s of random 32-byte record reads from a table of table_bytes (L1-, L2- or
  * HBM-resident depending on its size): the gather roofline of SURVEY.md 8(d). */
 NDT2D_API int ndt2d_probe_gather(int device, size_t table_bytes, double * out_gbps);
+/* Gaussian evaluations per second of the search kernel's own evaluation recipe run back to
+ * back with no bookkeeping (2 packed FMAs + one ex2 on the SFU + one packed add per
+ * evaluation, register accumulators, the search kernel's launch shape): the measured
+ * arithmetic bound of the correlative search on this device (bench.py roofline.peak). */
+NDT2D_API int ndt2d_probe_ex2(int device, double * out_evals_per_s);
 /* GB/s (read + write) of a plain device-to-device copy of `bytes`. */
 NDT2D_API int ndt2d_probe_copy(int device, size_t bytes, double * out_gbps);
-
-/* ------------------------------------------------------------------------
- * Synthetic laser world (host code; shared by tests and bench so that the
- * oracle and the device path see identical inputs).  Not part of the
- * reference; SURVEY.md section 8(d) defines it.
- * ---------------------------------------------------------------------- */
-
-/* n_obstacles axis-aligned rectangles (xmin, ymin, xmax, ymax) inside a square
- * arena of side `arena`: sides U[side_min, side_max] m, centres
- * U[5, arena-5]^2, SplitMix64(seed). */
-NDT2D_API int ndt2d_synth_world(
-  uint64_t seed, double arena, int n_obstacles, double side_min, double side_max,
-  double * rects4);
-
-/* Ray-casts `beams` beams (angle -pi + i*2pi/beams in the sensor frame) from
- * each pose against the arena walls and the rectangles, adds N(0, sigma)
- * range noise (stream seed + scan index), drops returns beyond range_max and
- * writes sensor-frame points.  pt_offsets gets n_scans+1 entries; pts_xy must
- * hold 2*beams*n_scans doubles.  Multi-threaded on the host. */
-NDT2D_API int ndt2d_synth_scans(
-  const double * rects4, int n_rects, double arena, const double * poses3, size_t n_scans,
-  int beams, double range_max, double noise_sigma, uint64_t seed, uint64_t * pt_offsets,
-  double * pts_xy);
-
-/* SplitMix64-based uniform doubles in [0,1): out[i] for stream `seed`. */
-NDT2D_API void ndt2d_synth_uniform(uint64_t seed, size_t n, double * out);
-/* Standard normal variates (Box-Muller on the uniform stream). */
-NDT2D_API void ndt2d_synth_normal(uint64_t seed, size_t n, double * out);
 
 #ifdef __cplusplus
 }

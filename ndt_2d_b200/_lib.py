@@ -108,6 +108,7 @@ SIGNATURES = {
                   C.POINTER(C.c_size_t)]),
     "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),
+    "ndt2d_probe_ex2": (C.c_int, [C.c_int, _dp]),
     "ndt2d_filter_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, _vp, C.POINTER(_vp)]),
     "ndt2d_filter_destroy": (C.c_int, [_vp]),
     "ndt2d_filter_set_particles": (C.c_int, [_vp, _dp, _dp, C.c_size_t]),
@@ -122,12 +123,6 @@ SIGNATURES = {
     "ndt2d_filter_stats": (C.c_int, [_vp, _dp, _dp]),
     "ndt2d_filter_set_cov": (C.c_int, [_vp, _dp]),
     "ndt2d_filter_last_draws": (C.c_int, [_vp, _u64p]),
-    "ndt2d_synth_world": (C.c_int, [C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double, _dp]),
-    "ndt2d_synth_scans": (
-        C.c_int, [_dp, C.c_int, C.c_double, _dp, C.c_size_t, C.c_int, C.c_double, C.c_double,
-                  C.c_uint64, _u64p, _dp]),
-    "ndt2d_synth_uniform": (None, [C.c_uint64, C.c_size_t, _dp]),
-    "ndt2d_synth_normal": (None, [C.c_uint64, C.c_size_t, _dp]),
 }
 
 

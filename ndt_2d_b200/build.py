@@ -22,7 +22,9 @@ OBJDIR = LIBDIR / "obj"
 LIB = LIBDIR / "libndt2d_b200.so"
 
 CU_SOURCES = ["api.cu", "build.cu", "search.cu", "search_region.cu", "search_window.cu", "filter.cu", "probe.cu", "frontend.cu", "occupancy.cu"]
-CXX_SOURCES = ["synth.cpp"]
+CXX_SOURCES = []
+SYNTH_SRC = PKG / "synth_src" / "synth.cpp"
+SYNTH_LIB = LIBDIR / "libndt2d_synth.so"
 HEADERS = [CSRC / "ndt2d_internal.h", CSRC / "search_common.cuh", CSRC / "search_region_body.inc",
            ROOT / "include" / "ndt2d_b200.h"]
 
@@ -59,7 +61,18 @@ def _run(cmd, log: Path | None = None):
     return proc
 
 
+def build_synth(force: bool = False) -> Path:
+    """The synthetic-world generator (test / bench infrastructure): its own host-only library."""
+    LIBDIR.mkdir(parents=True, exist_ok=True)
+    deps = [SYNTH_SRC, SYNTH_SRC.parent / "ndt2d_synth.h"]
+    if force or _stale(SYNTH_LIB, deps):
+        _run(["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-Wall",
+              "-shared", f"-I{SYNTH_SRC.parent}", str(SYNTH_SRC), "-o", str(SYNTH_LIB), "-lpthread"])
+    return SYNTH_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    build_synth(force)
     nvcc = _nvcc()
     # A/B experiments: NDT2D_NVCC_EXTRA="-DNDT2D_REGION_WARPS=20" python -m ndt_2d_b200.build --force
     extra = os.environ.get("NDT2D_NVCC_EXTRA", "").split()

@@ -246,7 +246,7 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.n_ang = static_cast<uint32_t>(m->dth.size());
   sv.n_lin = static_cast<uint32_t>(m->dlin.size());
   sv.theta_stride = 1;
-  sv.coords = m->d_coords.as<uint16_t>();
+  sv.coords = m->d_coords.as<uint32_t>();
   sv.coords_cap_bytes = m->d_coords.cap;
   sv.chunk_sums = m->d_chunk.as<double>();
   sv.chunk_cap_doubles = m->d_chunk.cap / sizeof(double);

@@ -76,7 +76,7 @@ struct SearchView
   double pose_x, pose_y;
   double linear_res;     // search_linear_resolution (region sizing, row step of the region kernel)
   uint32_t n_pts, n_ang, n_lin;
-  uint16_t * coords;        // scratch of the coordinate pre-pass (may be null)
+  uint32_t * coords;        // scratch of the coordinate pre-pass (may be null)
   size_t coords_cap_bytes;
   double * chunk_sums;      // scratch of the point-chunked mode of small searches (may be null)
   size_t chunk_cap_doubles;
@@ -197,7 +197,7 @@ size_t ndt2d_region_chunk_doubles(double cell_size, uint32_t n_ang, uint32_t n_l
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
-  uint16_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
+  uint32_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
   uint32_t * n_jobs);
 int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,

@@ -146,12 +146,13 @@ __device__ __forceinline__ uint32_t padded_coord(
 }
 
 // Two rows (2J, 2J + 1) of the region for this lane's column, packed FP32 (sm_100 FFMA2 / FADD2):
-// b' = row - bs, log2 L = c2 b'^2 + d1 b' + e0.  EE carries e0 per row (-inf masks a row).
+// b' = row - bs, log2 L = c2 b'^2 + d1 b' + e0.  bp = (b'(2J), b'(2J + 1)) is carried from pair
+// to pair (STEP = -2 going down, +2 going up), EE carries e0 per row (-inf masks a row).
 #define NDT2D_PAIR(J, EE) \
   { \
-    const float2 bp = __fadd2_rn(make_float2(2.0f * (J), 2.0f * (J) + 1.0f), nbsp); \
     const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
     acc2[J] = __fadd2_rn(acc2[J], make_float2(ex2_ftz(e.x), ex2_ftz(e.y))); \
+    bp = __fadd2_rn(bp, stepp); \
   }
 
 // Number of k in [0, n) with o + dl[k] < thr, for increasing dl (the replayed lattice): a
@@ -217,10 +218,9 @@ __device__ __forceinline__ VtxLine vtx_setup(
     ln.stiff = __double2hiint(SF.y) != 0;
     const double qu = xa - mean.x;
     const double w0 = fma(DB.y, qu, y0 - mean.y);
-    const double rb = w0 * neg_inv_h;
-    if (fabs(rb) < 2097152.0) {   // else the ridge is > 2e6 rows away: L == 0 on this column
-      const double rm = __dadd_rn(rb, kRoundMagic);
-      const double bs = __dadd_rn(rm, -kRoundMagic);      // rint(rb)
+    if (fabs(w0) < 2097152.0 * h) {   // else the ridge is > 2e6 rows away: L == 0 on this column
+      const double rm = fma(w0, neg_inv_h, kRoundMagic);
+      const double bs = __dadd_rn(rm, -kRoundMagic);      // a row within 1/2 (+ 1 ulp) of -w0 / h
       const double dl = fma(bs, h, w0);
       const double Dd = DB.x * dl;
       ln.e0 = static_cast<float>(fma(Dd, dl, (SF.x * qu) * qu));
@@ -263,33 +263,45 @@ __device__ __forceinline__ void stiff_rows(
   }
 }
 
-// Pre-pass of the search: for every (theta slice, scan point) the padded cell
-// coordinate of the FIRST column of each of the Qx region columns (x) and of the
-// first row of each of the Qy region rows (y).  The Qx*Qy regions of a slice share
-// them, so computing them here instead of inside every job removes a factor ~Q
-// of threshold lookups.  Layout: coords[(it * (Qx + Qy) + q) * n_pts_pad + i], u16,
-// q < Qx: x of region column q, q >= Qx: y of region row q - Qx.
+// Pre-pass of the search: everything an item needs that depends on (theta slice, scan point,
+// region column) or (theta slice, scan point, region row) only -- the Qx * Qy regions of a slice
+// share it, so computing it here instead of inside every job removes a factor ~Q of work:
+//   x entry (region column q):  pcx | kx1 << 16 | kx2 << 22
+//       pcx  padded cell coordinate of the region's FIRST column,
+//       kx1 / kx2  columns of the region left of the next / second-next x threshold
+//   y entry (region row q):     pcy | ky << 16      (same for rows; a region spans <= 2 cell rows)
+// all by the reference's own additions against the tabulated thresholds (exact).
+// Layout: coords[(it * (Qx + Qy) + q) * n_pts_pad + i], u32; q < Qx: x, q >= Qx: y of row q - Qx.
 __global__ void __launch_bounds__(128) region_coords_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t RX, uint32_t RY,
-  uint32_t Qx, uint32_t Qy, uint32_t n_pts_pad, uint16_t * __restrict__ coords)
+  uint32_t Qx, uint32_t Qy, uint32_t n_pts_pad, uint32_t * __restrict__ coords)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sv.n_pts) {return;}
   const double2 p = sv.pts[i];
-  const double inv_cell = 1.0 / mv.g.cell_size;
+  const double inv_cell = 1.0 / mv.g.cell_size, inv_h = 1.0 / sv.linear_res;
+  const uint32_t n_lin = sv.n_lin;
   for (uint32_t it = blockIdx.y; it < n_theta; it += gridDim.y) {
     const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
     const double ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
     const double oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-    uint16_t * cx = coords + (static_cast<size_t>(it) * (Qx + Qy)) * n_pts_pad + i;
-    uint16_t * cy = cx + static_cast<size_t>(Qx) * n_pts_pad;
+    uint32_t * cx = coords + (static_cast<size_t>(it) * (Qx + Qy)) * n_pts_pad + i;
+    uint32_t * cy = cx + static_cast<size_t>(Qx) * n_pts_pad;
     for (uint32_t q = 0; q < Qx; ++q) {
-      cx[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
-          __dadd_rn(ox, sv.dlin[q * RX]), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell));
+      const uint32_t j0 = q * RX, n = min(RX, n_lin - j0);
+      const uint32_t pc = padded_coord<false>(
+        __dadd_rn(ox, sv.dlin[j0]), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell);
+      const uint32_t k1 = count_below(ox, sv.dlin + j0, n, mv.thr_x[pc], inv_h);
+      const uint32_t k2 = k1 == n ? n :
+        count_below(ox, sv.dlin + j0, n, mv.thr_x[min(pc + 1u, mv.g.size_x + 1u)], inv_h);
+      cx[static_cast<size_t>(q) * n_pts_pad] = pc | (k1 << 16) | (k2 << 22);
     }
     for (uint32_t q = 0; q < Qy; ++q) {
-      cy[static_cast<size_t>(q) * n_pts_pad] = static_cast<uint16_t>(padded_coord<false>(
-          __dadd_rn(oy, sv.dlin[q * RY]), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell));
+      const uint32_t j0 = q * RY, n = min(RY, n_lin - j0);
+      const uint32_t pc = padded_coord<false>(
+        __dadd_rn(oy, sv.dlin[j0]), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell);
+      const uint32_t k = count_below(oy, sv.dlin + j0, n, mv.thr_y[pc], inv_h);
+      cy[static_cast<size_t>(q) * n_pts_pad] = pc | (k << 16);
     }
   }
 }
@@ -370,7 +382,7 @@ search_region_kernel(
   uint32_t Qy, uint32_t n_jobs, uint32_t tab_d_bytes, uint32_t tab_thr_bytes,
   double * __restrict__ job_partials, double * __restrict__ scores,
   uint32_t * __restrict__ job_counter, unsigned long long * __restrict__ stats,
-  const uint16_t * __restrict__ coords, uint32_t n_pts_pad, uint32_t P, uint32_t chunk_points,
+  const uint32_t * __restrict__ coords, uint32_t n_pts_pad, uint32_t P, uint32_t chunk_points,
   double * __restrict__ chunk_sums)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -450,7 +462,7 @@ search_region_batch_kernel(
   constexpr bool PRE = false, SMEM_TAB = false;
   const uint32_t theta_begin = 0;
   double * const scores = nullptr;
-  const uint16_t * const coords = nullptr;
+  const uint32_t * const coords = nullptr;
   const uint32_t n_pts_pad = 0;
   (void)coords;
   (void)n_pts_pad;
@@ -551,13 +563,13 @@ void plan_chunks(RegionPlan & pl, uint32_t n_pts, size_t chunk_cap_doubles, uint
 size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
 {
   const size_t n_pts_pad = (static_cast<size_t>(n_pts) + 31u) & ~size_t(31);
-  return static_cast<size_t>(n_theta) * (pl.Qx + pl.Qy) * n_pts_pad * sizeof(uint16_t);
+  return static_cast<size_t>(n_theta) * (pl.Qx + pl.Qy) * n_pts_pad * sizeof(uint32_t);
 }
 
 template<bool S, bool PRE>
 int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   uint32_t theta_begin, uint32_t n_theta, double * d_job_partials, double * d_scores,
-  uint32_t * d_counter, uint16_t * d_coords, double * d_chunk_sums, cudaStream_t stream,
+  uint32_t * d_counter, uint32_t * d_coords, double * d_chunk_sums, cudaStream_t stream,
   Counters * ctr)
 {
   auto kernel = search_region_kernel<S, PRE>;
@@ -743,7 +755,7 @@ size_t ndt2d_region_chunk_doubles(double cell_size, uint32_t n_ang, uint32_t n_l
 int ndt2d_launch_search_region(
   const ModelView & mv, const SearchView & sv, double linear_res, uint32_t theta_begin,
   uint32_t n_theta, double * d_job_partials, double * d_scores, uint32_t * d_counter,
-  uint16_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
+  uint32_t * d_coords, size_t coords_cap_bytes, cudaStream_t stream, Counters * ctr,
   uint32_t * n_jobs)
 {
   RegionPlan pl = make_plan(mv.g, n_theta, sv.n_lin, linear_res);

@@ -1,7 +1,9 @@
 """Synthetic laser world and the BASELINE.json workloads.
 
-Thin wrappers over the host-side generator in libndt2d_b200 (csrc/synth.cpp) so
-that tests, bench.py and the oracle all see bit-identical inputs.
+Test / bench infrastructure, host code only: thin wrappers over the generator in its own
+library ndt_2d_b200/lib/libndt2d_synth.so (synth_src/synth.cpp, g++) so that tests, bench.py
+and the oracle all see bit-identical inputs.  Importing this module loads nothing of the
+product (libndt2d_b200.so): the CPU reference arm of bench.py uses it too.
 """
 from __future__ import annotations
 
@@ -11,7 +13,53 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import _lib as L
+from pathlib import Path
+
+_SYNTH_SO = Path(__file__).resolve().parent / "lib" / "libndt2d_synth.so"
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class _L:
+    """The synthetic-world library + the few helpers this module needs."""
+
+    def __init__(self):
+        if not _SYNTH_SO.exists():
+            from . import build as _build
+            _build.build_synth()
+        self.lib = C.CDLL(str(_SYNTH_SO))
+        sig = {
+            "ndt2d_synth_world": (C.c_int, [C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double, _dp]),
+            "ndt2d_synth_scans": (C.c_int, [_dp, C.c_int, C.c_double, _dp, C.c_size_t, C.c_int, C.c_double,
+                                            C.c_double, C.c_uint64, _u64p, _dp]),
+            "ndt2d_synth_uniform": (None, [C.c_uint64, C.c_size_t, _dp]),
+            "ndt2d_synth_normal": (None, [C.c_uint64, C.c_size_t, _dp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = res, args
+
+    @staticmethod
+    def check(status: int, where: str):
+        if status != 0:
+            raise RuntimeError(f"{where}: status {status}")
+
+    @staticmethod
+    def dptr(a):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+        return a.ctypes.data_as(_dp)
+
+    @staticmethod
+    def u64ptr(a):
+        assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need contiguous uint64"
+        return a.ctypes.data_as(_u64p)
+
+    @staticmethod
+    def f64(a) -> np.ndarray:
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+
+L = _L()
 
 ARENA = 100.0
 N_OBSTACLES = 400

@@ -1,4 +1,5 @@
-// synth.cpp -- deterministic synthetic laser world (host code).
+// synth.cpp -- deterministic synthetic laser world (host code; test / bench infrastructure,
+// its own library libndt2d_synth.so -- not part of the product).
 //
 // square arena with outer walls and axis-aligned
 // rectangular obstacles (denser and smaller than the survey's first sketch so
@@ -13,7 +14,7 @@
 #include <thread>
 #include <vector>
 
-#include "ndt2d_b200.h"
+#include "ndt2d_synth.h"
 
 namespace
 {
@@ -72,21 +73,21 @@ inline double ray_box(double px, double py, double dx, double dy,
 
 extern "C" {
 
-NDT2D_API void ndt2d_synth_uniform(uint64_t seed, size_t n, double * out)
+NDT2D_SYNTH_API void ndt2d_synth_uniform(uint64_t seed, size_t n, double * out)
 {
   for (size_t i = 0; i < n; ++i) {out[i] = uniform_at(seed, i);}
 }
 
-NDT2D_API void ndt2d_synth_normal(uint64_t seed, size_t n, double * out)
+NDT2D_SYNTH_API void ndt2d_synth_normal(uint64_t seed, size_t n, double * out)
 {
   for (size_t i = 0; i < n; ++i) {out[i] = normal_at(seed, i);}
 }
 
-NDT2D_API int ndt2d_synth_world(
+NDT2D_SYNTH_API int ndt2d_synth_world(
   uint64_t seed, double arena, int n_obstacles, double side_min, double side_max, double * rects4)
 {
   if (!rects4 || n_obstacles < 0 || !(arena > 10.0) || !(side_min > 0.0) || !(side_max >= side_min)) {
-    return NDT2D_ERR_INVALID;
+    return 1;  /* invalid argument */
   }
   for (int k = 0; k < n_obstacles; ++k) {
     const double cx = 5.0 + (arena - 10.0) * uniform_at(seed, 4 * k + 0);
@@ -98,16 +99,16 @@ NDT2D_API int ndt2d_synth_world(
     rects4[4 * k + 2] = cx + 0.5 * w;
     rects4[4 * k + 3] = cy + 0.5 * h;
   }
-  return NDT2D_OK;
+  return 0;
 }
 
-NDT2D_API int ndt2d_synth_scans(
+NDT2D_SYNTH_API int ndt2d_synth_scans(
   const double * rects4, int n_rects, double arena, const double * poses3, size_t n_scans,
   int beams, double range_max, double noise_sigma, uint64_t seed, uint64_t * pt_offsets,
   double * pts_xy)
 {
   if (!poses3 || !pt_offsets || !pts_xy || beams <= 0 || n_rects < 0 || (n_rects && !rects4)) {
-    return NDT2D_ERR_INVALID;
+    return 1;  /* invalid argument */
   }
   // Pass 1 (parallel): every scan writes into its own fixed-size slot and
   // records its count; pass 2 compacts in scan order.
@@ -160,7 +161,7 @@ NDT2D_API int ndt2d_synth_scans(
     off += counts[s];
   }
   pt_offsets[n_scans] = off;
-  return NDT2D_OK;
+  return 0;
 }
 
 }  // extern "C"

@@ -29,6 +29,7 @@
 #include <ndt_2d_b200/occupancy_grid.hpp>
 #include <ndt_2d_b200/particle_filter.hpp>
 #include <ndt_2d_b200/scan_matcher_ndt.hpp>
+#include <ndt2d_synth.h>
 
 namespace
 {
