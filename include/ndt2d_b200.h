@@ -49,6 +49,8 @@ typedef enum ndt2d_status
 /* Parameters of one ScanMatcherNDT instance: the six ROS parameters the
  * reference declares under "<name>." (scan_matcher_ndt.cpp:37-44, same
  * defaults) plus range_max (:46) and the CUDA placement. */
+#define NDT2D_MAX_DEVICES 16
+
 typedef struct ndt2d_params
 {
   double ndt_resolution;             /* default 0.25   */
@@ -67,6 +69,14 @@ typedef struct ndt2d_params
                                         window where eligible, else dense);
                                         1 = plain per-candidate kernel (reference arithmetic
                                         per evaluation; the on-device cross-check) */
+  int n_devices;                     /* > 1: ONE handle drives the GPUs devices[0 .. n_devices-1] of
+                                        this process (device / stream are ignored): the model and the
+                                        query scan are replicated, a large matchScan scores theta slices
+                                        r, r + N, ... on device r, and the 128-byte partial records are
+                                        exchanged by peer stores from each search's last kernel (peer
+                                        access enabled between the devices; host combine otherwise).
+                                        Everything else runs on devices[0].  0 / 1 = single device. */
+  int devices[NDT2D_MAX_DEVICES];
 } ndt2d_params;
 
 typedef struct ndt2d_matcher ndt2d_matcher;
@@ -225,6 +235,16 @@ NDT2D_API int ndt2d_matcher_search_exchange(
 NDT2D_API int ndt2d_matcher_fetch_result(
   ndt2d_matcher * m, double * out_delta3, int * delta_written, double * out_cov9,
   double * out_score);
+
+/* Multi-device handle (ndt2d_params.n_devices > 1): info4 = number of devices, 1 if the fused
+ * peer-to-peer exchange is in use (0: host combine), matchScans that ran on all devices so far,
+ * sequence number of the last exchange. */
+NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4);
+/* Per-device duration (ms, CUDA events on each device's own stream) of the search kernels of the
+ * last matchScan of a multi-device handle, and its tallies summed over the devices
+ * (totals3 = useful evaluations, (point, region) items, 0). */
+NDT2D_API int ndt2d_matcher_group_search_stats(
+  ndt2d_matcher * m, double * out_ms, size_t cap, uint64_t * totals3);
 
 /* Synchronises the stream and copies the handle-held partial record out. */
 NDT2D_API int ndt2d_matcher_fetch_partial(ndt2d_matcher * m, double * partial16);

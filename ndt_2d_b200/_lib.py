@@ -44,6 +44,8 @@ class Params(C.Structure):
         ("device", C.c_int),
         ("stream", C.c_void_p),
         ("kernel_variant", C.c_int),
+        ("n_devices", C.c_int),
+        ("devices", C.c_int * 16),
     ]
 
 
@@ -83,6 +85,8 @@ SIGNATURES = {
     "ndt2d_matcher_search_exchange": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "ndt2d_matcher_fetch_result": (C.c_int, [_vp, _dp, _ip, _dp, _dp]),
     "ndt2d_matcher_fetch_partial": (C.c_int, [_vp, _dp]),
+    "ndt2d_matcher_group_info": (C.c_int, [_vp, _u64p]),
+    "ndt2d_matcher_group_search_stats": (C.c_int, [_vp, _dp, C.c_size_t, _u64p]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_combine_partials_host": (
         C.c_int, [_dp, C.c_size_t, _dp, C.c_size_t, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),

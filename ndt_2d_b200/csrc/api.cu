@@ -203,6 +203,13 @@ struct ndt2d_matcher
   std::vector<void *> peer_ptrs;        // index = rank; own rank = d_mailbox.p
   uint32_t x_world = 0, x_rank = 0;
   bool x_connected = false;
+  bool x_local = false;                 // peers are raw pointers of this process (no IPC handles)
+  // single-process multi-GPU (ndt2d_params.n_devices > 1): this handle (rank 0, devices[0]) owns
+  // one sub-handle per further device; group[r] = the handle of rank r (group[0] == this)
+  std::vector<ndt2d_matcher *> group;
+  bool group_p2p = false;               // mailboxes mapped: fused exchange; else host combine
+  unsigned long long group_seq = 0;
+  unsigned long long group_searches = 0;  // matchScans that ran on all devices
   bool pipelined = false;
   std::vector<ndt2d_matcher *> lanes;   // sub-handles of match_scan_batch (created on first use)
   PinnedBuffer h_arena;
@@ -242,6 +249,7 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.pose_x = m->pose_x;
   sv.pose_y = m->pose_y;
   sv.linear_res = m->prm.search_linear_resolution;
+  sv.inv_linear_res = 1.0 / sv.linear_res;
   sv.n_pts = m->n_pts;
   sv.n_ang = static_cast<uint32_t>(m->dth.size());
   sv.n_lin = static_cast<uint32_t>(m->dlin.size());
@@ -707,11 +715,17 @@ static int match_scan_batch_locked(
   const double * map_pts_xy,
   const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
   double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
+static int group_create(ndt2d_matcher * m);
+static bool group_worthwhile(const ndt2d_matcher * m, size_t npts);
+static int match_scan_group(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
 static void exchange_close(ndt2d_matcher * m)
 {
   for (uint32_t r = 0; r < m->peer_ptrs.size(); ++r) {
-    if (r != m->x_rank && m->peer_ptrs[r]) {cudaIpcCloseMemHandle(m->peer_ptrs[r]);}
+    if (!m->x_local && r != m->x_rank && m->peer_ptrs[r]) {cudaIpcCloseMemHandle(m->peer_ptrs[r]);}
   }
+  m->x_local = false;
   m->peer_ptrs.clear();
   m->x_connected = false;
 }
@@ -745,6 +759,8 @@ NDT2D_API void ndt2d_default_params(ndt2d_params * p)
   p->device = -1;
   p->stream = nullptr;
   p->kernel_variant = 0;
+  p->n_devices = 0;
+  for (int k = 0; k < NDT2D_MAX_DEVICES; ++k) {p->devices[k] = 0;}
 }
 
 NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher ** out)
@@ -761,7 +777,18 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
       "no CUDA device visible: libndt2d_b200 has no CPU fallback");
     return NDT2D_ERR_NO_DEVICE;
   }
-  int dev = params->device;
+  if (params->n_devices < 0 || params->n_devices > NDT2D_MAX_DEVICES) {return NDT2D_ERR_INVALID;}
+  const bool multi = params->n_devices > 1;
+  if (multi) {
+    const int n_vis = ndt2d_device_count();
+    for (int a = 0; a < params->n_devices; ++a) {
+      if (params->devices[a] < 0 || params->devices[a] >= n_vis) {return NDT2D_ERR_NO_DEVICE;}
+      for (int b = 0; b < a; ++b) {
+        if (params->devices[a] == params->devices[b]) {return NDT2D_ERR_INVALID;}
+      }
+    }
+  }
+  int dev = multi ? params->devices[0] : (params->n_devices == 1 ? params->devices[0] : params->device);
   if (dev < 0) {
     NDT2D_CUDA_TRY(cudaGetDevice(&dev));
   }
@@ -785,7 +812,7 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
     delete m;
     return NDT2D_ERR_NO_DEVICE;
   }
-  if (params->stream) {
+  if (params->stream && !multi) {
     m->stream = static_cast<cudaStream_t>(params->stream);
   } else {
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
@@ -818,6 +845,13 @@ NDT2D_API int ndt2d_matcher_create(const ndt2d_params * params, ndt2d_matcher **
     return rc;
   }
   m->ctr.h2d_bytes += (na + nl) * sizeof(double);
+  if (multi) {
+    rc = group_create(m);
+    if (rc) {
+      ndt2d_matcher_destroy(m);
+      return rc;
+    }
+  }
   *out = m;
   return NDT2D_OK;
 }
@@ -827,6 +861,8 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   if (!m) {return NDT2D_OK;}
   for (ndt2d_matcher * sub : m->lanes) {ndt2d_matcher_destroy(sub);}
   m->lanes.clear();
+  for (size_t r = 1; r < m->group.size(); ++r) {ndt2d_matcher_destroy(m->group[r]);}
+  m->group.clear();
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
@@ -861,6 +897,10 @@ NDT2D_API int ndt2d_matcher_reset(ndt2d_matcher * m)
   std::lock_guard<std::mutex> lock(m->mu);
   m->has_model = false;  // scan_matcher_ndt.cpp:180-183
   m->n_map_points = 0;
+  for (size_t r = 1; r < m->group.size(); ++r) {
+    m->group[r]->has_model = false;
+    m->group[r]->n_map_points = 0;
+  }
   return NDT2D_OK;
 }
 
@@ -871,6 +911,13 @@ NDT2D_API int ndt2d_matcher_add_scans(
   if (!m || (n_scans && (!poses || !pt_offsets))) {return NDT2D_ERR_INVALID;}
   if (n_scans && pt_offsets[n_scans] > pt_offsets[0] && !pts_xy) {return NDT2D_ERR_INVALID;}
   std::lock_guard<std::mutex> lock(m->mu);
+  // a multi-device handle replicates the model: every device builds it from the same scans
+  for (size_t r = 1; r < m->group.size(); ++r) {
+    ndt2d_matcher * s = m->group[r];
+    DeviceGuard guard(s->device);
+    const int rc = add_scans_locked(s, n_scans, poses, pt_offsets, pts_xy);
+    if (rc) {return rc;}
+  }
   DeviceGuard guard(m->device);
   return add_scans_locked(m, n_scans, poses, pt_offsets, pts_xy);
 }
@@ -885,6 +932,9 @@ NDT2D_API int ndt2d_matcher_match_scan(
   if (!m->has_model) {
     if (out_score) {*out_score = 0.0;}  // scan_matcher_ndt.cpp:80
     return NDT2D_ERR_NO_MAP;
+  }
+  if (group_worthwhile(m, npts)) {
+    return match_scan_group(m, pose3, pts_xy, npts, out_delta3, delta_written, out_cov9, out_score);
   }
   DeviceGuard guard(m->device);
   return match_scan_locked(m, pose3, pts_xy, npts, out_delta3, delta_written, out_cov9, out_score);
@@ -1122,6 +1172,7 @@ static int match_scan_batch_fused(
     se.sv.pose_x = pose3[0];
     se.sv.pose_y = pose3[1];
     se.sv.linear_res = m->prm.search_linear_resolution;
+    se.sv.inv_linear_res = 1.0 / se.sv.linear_res;
     se.sv.n_pts = static_cast<uint32_t>(J.n_use);
     se.sv.n_ang = static_cast<uint32_t>(n_ang);
     se.sv.n_lin = static_cast<uint32_t>(n_lin);
@@ -2166,6 +2217,222 @@ NDT2D_API int ndt2d_filter_last_draws(ndt2d_filter * f, uint64_t * out)
     cudaMemcpyDeviceToHost, f->stream));
   NDT2D_CUDA_TRY(cudaStreamSynchronize(f->stream));
   for (size_t i = 0; i < n; ++i) {out[i] = h[i];}
+  return NDT2D_OK;
+}
+
+}  // extern "C"
+
+
+// ---------------------------------------------------------------- one handle, several GPUs
+// (ndt2d_params.n_devices > 1).  The C++ plugin is loaded into ONE process (the node creates its
+// matchers at ndt_mapper.cpp:54, 299-312 and calls matchScan at :552-553, 638-643), so the
+// N-GPU search has to be reachable from one host thread: rank r = devices[r] has its own
+// sub-handle (stream, buffers, replicated model and scan), the host enqueues the strided
+// searches on all devices back to back and fetches the combined record from rank 0.  The
+// exchange is the same mailbox protocol as the one-process-per-GPU path
+// (ndt2d_matcher_search_exchange), the peers' mailboxes being plain device pointers here:
+// peer access is enabled between every pair of devices.
+
+static int group_create(ndt2d_matcher * m)
+{
+  const int n = m->prm.n_devices;
+  m->group.assign(1, m);
+  for (int r = 1; r < n; ++r) {
+    ndt2d_params p = m->prm;
+    p.n_devices = 0;
+    p.device = m->prm.devices[r];
+    p.stream = nullptr;
+    ndt2d_matcher * sub = nullptr;
+    const int rc = ndt2d_matcher_create(&p, &sub);
+    if (rc) {return rc;}
+    m->group.push_back(sub);
+  }
+  // peer access, every ordered pair
+  bool p2p = true;
+  for (int a = 0; a < n && p2p; ++a) {
+    for (int b = 0; b < n && p2p; ++b) {
+      if (a == b) {continue;}
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, m->prm.devices[a], m->prm.devices[b]) != cudaSuccess || !can) {
+        cudaGetLastError();
+        p2p = false;
+        break;
+      }
+      DeviceGuard guard(m->prm.devices[a]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(m->prm.devices[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {p2p = false;}
+      cudaGetLastError();
+    }
+  }
+  if (p2p) {
+    std::vector<void *> boxes(n, nullptr);
+    for (int r = 0; r < n; ++r) {
+      ndt2d_matcher * s = m->group[r];
+      DeviceGuard guard(s->device);
+      exchange_close(s);
+      int rc = s->d_mailbox.ensure(kExchangeMailboxBytes);
+      if (!rc) {rc = s->d_peer_table.ensure(kExchangeMaxRanks * sizeof(void *));}
+      if (rc) {return rc;}
+      NDT2D_CUDA_TRY(cudaMemset(s->d_mailbox.p, 0, kExchangeMailboxBytes));
+      boxes[r] = s->d_mailbox.p;
+    }
+    for (int r = 0; r < n; ++r) {
+      ndt2d_matcher * s = m->group[r];
+      DeviceGuard guard(s->device);
+      s->peer_ptrs = boxes;
+      s->x_world = static_cast<uint32_t>(n);
+      s->x_rank = static_cast<uint32_t>(r);
+      s->x_local = true;
+      NDT2D_CUDA_TRY(cudaMemcpy(s->d_peer_table.p, boxes.data(), n * sizeof(void *),
+        cudaMemcpyHostToDevice));
+      s->x_connected = true;
+    }
+  }
+  m->group_p2p = p2p;
+  return NDT2D_OK;
+}
+
+// A search is spread over the devices when every device gets enough slices to amortise the
+// replicated staging (a local match of 20,000 candidates is latency-bound on one GPU already).
+static bool group_worthwhile(const ndt2d_matcher * m, size_t npts)
+{
+  if (m->group.size() < 2) {return false;}
+  const double n_use = static_cast<double>(subsample_count(m, npts));
+  const double pairs = static_cast<double>(m->dth.size()) * m->dlin.size() * m->dlin.size() * n_use;
+  // (1e10 pairs are ~0.4 ms of one B200)
+  return pairs >= 1.0e10 && m->dth.size() >= 4 * m->group.size();
+}
+
+static int match_scan_group(
+  ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
+  double * out_delta3, int * delta_written, double * out_cov9, double * out_score)
+{
+  const size_t world = m->group.size();
+  const size_t n_ang = m->dth.size();
+  int rc = NDT2D_OK;
+  // stage the scan on every device ((cos, sin) only of the rank's own slices, on first use)
+  for (size_t r = 0; r < world && !rc; ++r) {
+    ndt2d_matcher * s = m->group[r];
+    DeviceGuard guard(s->device);
+    if (!s->has_model) {return NDT2D_ERR_STATE;}
+    rc = stage_scan_locked(s, pose3, pts_xy, npts, true);
+    if (!rc) {rc = ensure_trig_locked(s, r, n_ang, world);}
+  }
+  if (rc) {return rc;}
+  const unsigned long long seq = ++m->group_seq;
+  // enqueue all searches before waiting for any: the devices run concurrently
+  for (size_t r = 0; r < world && !rc; ++r) {
+    ndt2d_matcher * s = m->group[r];
+    DeviceGuard guard(s->device);
+    SearchView sv = search_view(s);
+    sv.theta_stride = static_cast<uint32_t>(world);
+    ExchangeView xv;
+    xv.peers = s->d_peer_table.as<void *>();
+    xv.world = static_cast<uint32_t>(world);
+    xv.rank = static_cast<uint32_t>(r);
+    xv.seq = seq;
+    xv.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    rc = ndt2d_launch_search(model_view(s), sv, static_cast<uint32_t>(r),
+        static_cast<uint32_t>(n_ang), m->prm.kernel_variant, s->d_blockpart.as<double>(),
+        s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &s->ctr,
+        s->ev_begin, s->ev_end, m->group_p2p ? &xv : nullptr);
+    s->ev_valid = rc == NDT2D_OK;
+  }
+  if (rc) {
+    for (size_t r = 0; r < world; ++r) {cudaStreamSynchronize(m->group[r]->stream);}
+    return rc;
+  }
+  m->group_searches += 1;
+  if (m->group_p2p) {
+    // every rank holds the combined record; rank 0's is the answer
+    double r32[32];
+    {
+      DeviceGuard guard(m->device);
+      if ((rc = fetch_result_locked(m, r32))) {return rc;}
+    }
+    for (size_t r = 1; r < world; ++r) {
+      ndt2d_matcher * s = m->group[r];
+      DeviceGuard guard(s->device);
+      NDT2D_CUDA_TRY(cudaStreamSynchronize(s->stream));
+      m->ctr.launches += s->ctr.launches;
+      m->ctr.h2d_bytes += s->ctr.h2d_bytes;
+      s->ctr = Counters{0, 0, 0};
+    }
+    if (r32[31] != 0.0) {
+      snprintf(g_last_error, sizeof(g_last_error),
+        "fused exchange timed out: not every device published its partial record");
+      return NDT2D_ERR_STATE;
+    }
+    unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
+    return NDT2D_OK;
+  }
+  // no peer access between the devices: fetch the N partial records and fold them on the host
+  std::vector<double> parts(world * NDT2D_PARTIAL_DOUBLES);
+  for (size_t r = 0; r < world; ++r) {
+    ndt2d_matcher * s = m->group[r];
+    DeviceGuard guard(s->device);
+    double r32[32];
+    if ((rc = fetch_result_locked(s, r32))) {return rc;}
+    memcpy(parts.data() + r * NDT2D_PARTIAL_DOUBLES, r32, NDT2D_PARTIAL_DOUBLES * sizeof(double));
+    if (r) {
+      m->ctr.launches += s->ctr.launches;
+      m->ctr.h2d_bytes += s->ctr.h2d_bytes;
+      m->ctr.d2h_bytes += s->ctr.d2h_bytes;
+      s->ctr = Counters{0, 0, 0};
+    }
+  }
+  if (delta_written) {*delta_written = 0;}
+  return ndt2d_combine_partials_host(m->dth.data(), m->dth.size(), m->dlin.data(), m->dlin.size(),
+           parts.data(), world, out_delta3, delta_written, out_cov9, out_score);
+}
+
+extern "C" {
+
+/* info4 = devices of the handle, whether the fused peer-to-peer exchange is in use, matchScans
+ * that ran on all devices so far, sequence number of the last exchange */
+NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4)
+{
+  if (!m || !info4) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  info4[0] = m->group.empty() ? 1 : m->group.size();
+  info4[1] = m->group_p2p ? 1 : 0;
+  info4[2] = m->group_searches;
+  info4[3] = m->group_seq;
+  return NDT2D_OK;
+}
+
+/* Multi-device handle: duration (ms, CUDA events on each device's stream) of the search kernels of
+ * the last matchScan on every device and the tallies of that search summed over the devices:
+ * out_ms[n_devices]; totals3 = useful evaluations, (point, region) items, 0. */
+NDT2D_API int ndt2d_matcher_group_search_stats(
+  ndt2d_matcher * m, double * out_ms, size_t cap, uint64_t * totals3)
+{
+  if (!m || !out_ms) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  const size_t n = m->group.empty() ? 1 : m->group.size();
+  if (cap < n) {return NDT2D_ERR_SIZE;}
+  if (totals3) {totals3[0] = totals3[1] = totals3[2] = 0;}
+  for (size_t r = 0; r < n; ++r) {
+    ndt2d_matcher * s = m->group.empty() ? m : m->group[r];
+    out_ms[r] = 0.0;
+    if (!s->d_counter.p) {continue;}
+    DeviceGuard guard(s->device);
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    uint64_t h[6] = {0, 0, 0, 0, 0, 0};
+    NDT2D_CUDA_TRY(cudaMemcpy(h, s->d_counter.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (totals3) {
+      totals3[0] += h[3];
+      totals3[1] += h[4];
+    }
+    if (s->ev_valid && s->ev_begin && s->ev_end) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end) == cudaSuccess) {
+        out_ms[r] = ms;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   return NDT2D_OK;
 }
 

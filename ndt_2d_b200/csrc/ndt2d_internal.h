@@ -75,6 +75,7 @@ struct SearchView
   const double * dlin;   // n_lin
   double pose_x, pose_y;
   double linear_res;     // search_linear_resolution (region sizing, row step of the region kernel)
+  double inv_linear_res; // 1 / linear_res
   uint32_t n_pts, n_ang, n_lin;
   uint32_t * coords;        // scratch of the coordinate pre-pass (may be null)
   size_t coords_cap_bytes;

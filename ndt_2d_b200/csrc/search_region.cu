@@ -63,7 +63,10 @@ constexpr uint32_t kPairs = (kMaxRY + 1) / 2;   // rows are held and evaluated t
 constexpr uint32_t kWarps = NDT2D_REGION_WARPS;  // warps per CTA; one persistent CTA per SM
 // per warp: double totals, [row][lane]
 constexpr uint32_t kWarpSmemBytes = kMaxRY * 32u * static_cast<uint32_t>(sizeof(double));
-constexpr size_t kSmemTabBudget = 64 * 1024;    // D + thresholds in shared memory up to this
+// D + thresholds in shared memory up to this: what the warps' totals leave of the 227 KB a CTA
+// can opt in to, at most 64 KB
+constexpr size_t kSmemLeft = 227 * 1024 - 1024 - static_cast<size_t>(kWarpSmemBytes) * kWarps;
+constexpr size_t kSmemTabBudget = kSmemLeft < 64 * 1024 ? kSmemLeft : 64 * 1024;
 constexpr uint32_t kBatchSlotBytes = 320;        // per-warp BatchEntry slot of the batch kernel (>= sizeof)
 constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accumulation block
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
@@ -208,7 +211,7 @@ struct VtxLine
 // A lane without an occupied cell gets e0 = -inf (2^-inf == +0).
 __device__ __forceinline__ VtxLine vtx_setup(
   bool occ, const double * __restrict__ rec_vtx, uint32_t rank, double xa, double y0, double h,
-  double neg_inv_h, double two_h)
+  double inv_h)
 {
   VtxLine ln{0.0f, 0.0f, -INFINITY, 0.0f, false};
   if (occ) {
@@ -219,12 +222,12 @@ __device__ __forceinline__ VtxLine vtx_setup(
     const double qu = xa - mean.x;
     const double w0 = fma(DB.y, qu, y0 - mean.y);
     if (fabs(w0) < 2097152.0 * h) {   // else the ridge is > 2e6 rows away: L == 0 on this column
-      const double rm = fma(w0, neg_inv_h, kRoundMagic);
+      const double rm = fma(-w0, inv_h, kRoundMagic);
       const double bs = __dadd_rn(rm, -kRoundMagic);      // a row within 1/2 (+ 1 ulp) of -w0 / h
       const double dl = fma(bs, h, w0);
       const double Dd = DB.x * dl;
       ln.e0 = static_cast<float>(fma(Dd, dl, (SF.x * qu) * qu));
-      ln.d1 = static_cast<float>(two_h * Dd);
+      ln.d1 = static_cast<float>((h + h) * Dd);
       ln.c2 = __int_as_float(__double2loint(SF.y));
       ln.nbs = __int_as_float(0x4B400000 - __double2loint(rm)) - 12582912.0f;   // float(-bs)
     }
@@ -388,7 +391,6 @@ search_region_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t * mbar = reinterpret_cast<uint64_t *>(smem_raw);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  unsigned long long n_useful = 0, n_items = 0;  // warp-uniform tallies (lane 0 reports)
 
   // ---- shared memory: [mbar 16][D][thr_x thr_y][per-warp double totals]
   const uint32_t * occd_tab;
@@ -454,7 +456,6 @@ search_region_batch_kernel(
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  unsigned long long n_useful = 0, n_items = 0;
   unsigned char * sp = smem_raw + static_cast<size_t>(warp) * (kWarpSmemBytes + kBatchSlotBytes);
   double * tot = reinterpret_cast<double *>(sp);
   BatchEntry * slot = reinterpret_cast<BatchEntry *>(sp + kWarpSmemBytes);

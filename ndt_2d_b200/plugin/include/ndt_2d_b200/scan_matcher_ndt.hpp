@@ -110,6 +110,14 @@ public:
   // a stream owned by the handle).
   void setDevice(int device, void * cuda_stream = nullptr);
 
+  // Several GPUs of this process behind this one matcher (ndt2d_params.n_devices), before
+  // initialize(): the model and the query scan are replicated, a large matchScan (a global
+  // search) scores theta slices r, r + N, ... on device r and the partial records are
+  // exchanged GPU to GPU by the searches' last kernels; local matches stay on devices[0].
+  // Also settable without code: the extra ROS parameter "<name>.n_gpus" (default 1) uses
+  // devices 0 .. n_gpus - 1.
+  void setDevices(const std::vector<int> & devices);
+
   ndt2d_matcher * handle() const {return handle_;}
   const ndt2d_params & params() const {return params_;}
 
@@ -119,6 +127,7 @@ private:
   ndt2d_params params_{};
   int device_ = -1;
   void * stream_ = nullptr;
+  std::vector<int> devices_;
   ndt2d_matcher * handle_ = nullptr;  // device state lives behind the handle, so the
                                       // const methods of the interface can use it
 };

@@ -72,6 +72,14 @@ void ScanMatcherNDT::setDevice(int device, void * cuda_stream)
   stream_ = cuda_stream;
 }
 
+void ScanMatcherNDT::setDevices(const std::vector<int> & devices)
+{
+  if (devices.size() > NDT2D_MAX_DEVICES) {
+    throw std::invalid_argument("ndt_2d_b200::ScanMatcherNDT::setDevices: too many devices");
+  }
+  devices_ = devices;
+}
+
 void ScanMatcherNDT::require_handle(const char * where) const
 {
   if (!handle_) {
@@ -96,6 +104,14 @@ void ScanMatcherNDT::initialize(const std::string & name, rclcpp::Node * node, d
   params_.range_max = range_max;
   params_.device = device_;
   params_.stream = stream_;
+  // extension: "<name>.n_gpus" GPUs (0 .. n_gpus - 1) behind this matcher; setDevices() wins
+  const int n_gpus = node->declare_parameter<int>(name + ".n_gpus", 1);
+  std::vector<int> devices = devices_;
+  if (devices.empty() && n_gpus > 1) {
+    for (int d = 0; d < n_gpus && d < NDT2D_MAX_DEVICES; ++d) {devices.push_back(d);}
+  }
+  params_.n_devices = static_cast<int>(devices.size());
+  for (size_t d = 0; d < devices.size(); ++d) {params_.devices[d] = devices[d];}
   if (handle_) {
     ndt2d_matcher_destroy(handle_);
     handle_ = nullptr;

@@ -162,11 +162,15 @@ def graph_find_nearest(scans, scan: Scan, dist: float, limit_scan_index: int = -
 class ScanMatcherNDT:
     """B200 backend behind the reference's ScanMatcher interface."""
 
-    def __init__(self, device: int = -1, stream: int = 0, kernel_variant: int = 0):
+    def __init__(self, device: int = -1, stream: int = 0, kernel_variant: int = 0,
+                 devices: Optional[Sequence[int]] = None):
+        """devices: several GPUs of this process behind ONE handle (ndt2d_params.n_devices): large
+        searches are theta-sliced over them, everything else runs on devices[0]."""
         self._h = C.c_void_p()
         self._device = device
         self._stream = stream
         self._variant = kernel_variant
+        self._devices = list(devices) if devices else []
         self.params: Optional[L.Params] = None
 
     # ---- ScanMatcher::initialize (scan_matcher_ndt.cpp:35-47)
@@ -183,6 +187,9 @@ class ScanMatcherNDT:
         p.device = self._device
         p.stream = self._stream or None
         p.kernel_variant = self._variant
+        p.n_devices = len(self._devices)
+        for k, d in enumerate(self._devices):
+            p.devices[k] = int(d)
         self._destroy()
         L.check(L.lib.ndt2d_matcher_create(C.byref(p), C.byref(self._h)), "ndt2d_matcher_create")
         self.params = p
@@ -437,6 +444,21 @@ class ScanMatcherNDT:
         L.check(L.lib.ndt2d_matcher_counters(self.handle, L.u64ptr(out)), "counters")
         return dict(launches=int(out[0]), h2d_bytes=int(out[1]), d2h_bytes=int(out[2]),
                     valid_cells=int(out[3]))
+
+    def group_info(self) -> dict:
+        """Multi-device handle: devices, fused P2P exchange in use, searches spread over all devices."""
+        out = np.zeros(4, dtype=np.uint64)
+        L.check(L.lib.ndt2d_matcher_group_info(self.handle, L.u64ptr(out)), "group_info")
+        return dict(devices=int(out[0]), p2p=bool(out[1]), group_searches=int(out[2]), seq=int(out[3]))
+
+    def group_search_stats(self) -> dict:
+        """Per-device search-kernel durations of the last matchScan + tallies over all devices."""
+        ms = np.zeros(16)
+        tot = np.zeros(3, dtype=np.uint64)
+        L.check(L.lib.ndt2d_matcher_group_search_stats(self.handle, L.dptr(ms), 16, L.u64ptr(tot)),
+                "group_search_stats")
+        n = self.group_info()["devices"]
+        return dict(kernel_ms=ms[:n].tolist(), useful_evaluations=int(tot[0]), items=int(tot[1]))
 
     def search_stats(self) -> dict:
         """Work done by the last search launch (ndt2d_matcher_search_stats)."""

@@ -1,10 +1,12 @@
 """Theta-sliced search over several ranks (one process per GPU, torch.distributed).
 
 The correlative search shards by theta slice: the model and the scan are tiny and
-replicated, rank r scores the slices [theta_range(n_ang, r, world)), and ONE exchange
--- an all-gather of a 128-byte partial record per rank -- precedes a lexicographic
-(score, candidate index) reduce + covariance sums, so the result is what a single
-sequential search returns (first-wins argmin included).  The reference has no
+replicated, rank r scores the INTERLEAVED slices r, r + world, ... (theta_slices), and ONE
+exchange of a 128-byte partial record per rank -- peer stores from the search's last kernel
+into mailboxes in every rank's memory ("p2p"), or an all-gather ("nccl") -- precedes a
+lexicographic (score, candidate index) reduce + covariance sums, so the result is what a
+single sequential search returns (first-wins argmin included).  (A single process can drive
+several GPUs through one handle instead: ndt2d_params.n_devices / ScanMatcherNDT(devices=...).)  The reference has no
 multi-device path; this is the N > 1 form of ScanMatcherNDT::matchScan
 (scan_matcher_ndt.cpp:76-149).
 
@@ -126,7 +128,26 @@ class ShardedSearch:
             return
         self.m.search_staged(self.lo, self.hi, self.mine.data_ptr(), stride=self.stride)
         if self.world > 1:
+            # the search ran on the matcher's stream, the collective runs on torch's current
+            # stream: order them explicitly in both directions (they may be different streams)
+            self._order(self._matcher_stream(), None)
             exchange_partials(self.mine.clone(), self.gathered, self.group)
+            self._order(None, self._matcher_stream())
+
+    def _matcher_stream(self):
+        import torch
+        h = self.m.stream()
+        return torch.cuda.ExternalStream(h) if h else torch.cuda.default_stream()
+
+    @staticmethod
+    def _order(first, then):
+        """Work enqueued on `then` from now on waits for what is on `first` now (None = torch's
+        current stream); no-op when they are the same stream."""
+        import torch
+        first = first if first is not None else torch.cuda.current_stream()
+        then = then if then is not None else torch.cuda.current_stream()
+        if first.cuda_stream != then.cuda_stream:
+            then.wait_event(first.record_event())
 
     def result(self):
         """-> (score, delta, written, cov) of the whole search; every rank holds the same."""

