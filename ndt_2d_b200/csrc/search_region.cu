@@ -150,13 +150,25 @@ __device__ __forceinline__ uint32_t padded_coord(
 
 // Two rows (2J, 2J + 1) of the region for this lane's column, packed FP32 (sm_100 FFMA2 / FADD2):
 // b' = row - bs, log2 L = c2 b'^2 + d1 b' + e0.  bp = (b'(2J), b'(2J + 1)) is carried from pair
-// to pair (STEP = -2 going down, +2 going up), EE carries e0 per row (-inf masks a row).
-#define NDT2D_PAIR(J, EE) \
+// to pair (step -2 going down, +2 going up), EE carries e0 per row (-inf masks a row).  The
+// chain is software-pipelined by one pair: a block first adds the PREVIOUS pair's two
+// likelihoods to their accumulators (JPREV) and then starts its own pair, so the SFU latency
+// of a pair overlaps the arithmetic of the next one (every block is a jump target, the
+// scheduler cannot move code across them by itself).
+#define NDT2D_PAIR_FIRST(EE) \
   { \
     const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
-    acc2[J] = __fadd2_rn(acc2[J], make_float2(ex2_ftz(e.x), ex2_ftz(e.y))); \
+    prev = make_float2(ex2_ftz(e.x), ex2_ftz(e.y)); \
     bp = __fadd2_rn(bp, stepp); \
   }
+#define NDT2D_PAIR_NEXT(JPREV, EE) \
+  { \
+    acc2[JPREV] = __fadd2_rn(acc2[JPREV], prev); \
+    const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
+    prev = make_float2(ex2_ftz(e.x), ex2_ftz(e.y)); \
+    bp = __fadd2_rn(bp, stepp); \
+  }
+#define NDT2D_PAIR_LAST(JPREV) {acc2[JPREV] = __fadd2_rn(acc2[JPREV], prev);}
 
 // Number of k in [0, n) with o + dl[k] < thr, for increasing dl (the replayed lattice): a
 // guess from the nominal step, fixed up with the reference's own additions (exact).
@@ -322,22 +334,27 @@ __device__ __forceinline__ void job_epilogue(
   Best best{0.0, kNoIndex};
   double sum[6] = {0, 0, 0, 0, 0, 0};
   if (lane < nxc) {
+    // this lane's column: sums over its rows of score * {1, dy, dy^2}, the dx factors once
     const double dx = sv.dlin[jx0 + lane];
     const uint64_t g0 = static_cast<uint64_t>(itheta) * n_cand +
       static_cast<uint64_t>(jx0 + lane) * n_lin + jy0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (uint32_t b = 0; b < nyc; ++b) {
       const double score = -sums(b);
       const double dy = sv.dlin[jy0 + b];
       const uint64_t gi = g0 + b;
       if (scores) {scores[gi] = score;}
       best_merge(best, score, static_cast<double>(gi));
-      sum[0] += score;
-      sum[1] += dx * score;
-      sum[2] += dy * score;
-      sum[3] += (dx * dx) * score;
-      sum[4] += (dx * dy) * score;
-      sum[5] += (dy * dy) * score;
+      s0 += score;
+      s1 += dy * score;
+      s2 += (dy * dy) * score;
     }
+    sum[0] = s0;
+    sum[1] = dx * s0;
+    sum[2] = s1;
+    sum[3] = (dx * dx) * s0;
+    sum[4] = dx * s1;
+    sum[5] = s2;
   }
   warp_best(best);
 #pragma unroll
