@@ -389,6 +389,10 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if lib.ndt2d_device_count() <= 0 or not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: ndt_2d_b200 has no CPU fallback")
+    if args.single_process:
+        if world != 1:
+            raise RuntimeError("--single-process is launched as ONE plain python process")
+        return run_single_process(args, torch)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -447,10 +451,10 @@ def run_ours(args):
         device_step()
         e1.record(stream)
         evs.append((e0, e1))
-        # the library brackets the search kernel alone with its own CUDA events on the launch
-        # stream; reading them waits for the step (steps are serialised on one stream anyway)
-        kernel_ms_steps.append(m.search_stats()["kernel_ms"])
     barrier()
+    # the library brackets pre-pass + search kernel with its own CUDA events on the launch
+    # stream (read after the timed region: the steps above were enqueued without host waits)
+    kernel_ms_steps.append(m.search_stats()["kernel_ms"])
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     c1 = m.counters()
@@ -621,6 +625,63 @@ def golden_parity(result, scale: float):
     return out
 
 
+def run_single_process(args, torch):
+    """N GPUs behind ONE multi-device handle in ONE process (ndt2d_params.n_devices): the route the
+    C++ plugin takes (ScanMatcherNDT::setDevices / "<name>.n_gpus").  Every step is the public
+    matchScan call with host buffers, so `value` and `e2e` are the same measurement here."""
+    from ndt_2d_b200 import ScanMatcherNDT, synth
+    n = args.gpus
+    w = synth.config4(scale=args.scale)
+    m = ScanMatcherNDT.from_params(w.params, devices=list(range(n)), kernel_variant=args.variant)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    na, nl = m.search_shape()
+    total = na * nl * nl
+    flush = [torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n)]
+    for _ in range(max(args.warmup, 1)):
+        r = m.match_scan_raw(w.query_pose, w.query_points)
+    sampler = ClockSampler(0)
+    sampler.start()
+    c0 = m.counters()
+    times, kms = [], []
+    for _ in range(args.steps):
+        for f in flush:
+            f.zero_()
+        for d in range(n):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        r = m.match_scan_raw(w.query_pose, w.query_points)
+        times.append(time.perf_counter() - t0)
+        kms.append(max(m.group_search_stats()["kernel_ms"]))
+    clocks = sampler.stop()
+    c1 = m.counters()
+    ms = float(np.mean(times) * 1e3)
+    st = m.group_search_stats()
+    gi = m.group_info()
+    line = {
+        "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config4_large_search (BASELINE.json configs[3])", "candidates_per_step": total,
+                   "parallelism": f"ONE process, one multi-device handle over {gi['devices']} GPUs (theta slices "
+                                  f"interleaved; fused peer-store exchange: {gi['p2p']}); wall clock around the "
+                                  "public matchScan call, host buffers in, result out",
+                   "l2_flush": "256 MiB memset on every device between steps, outside the timed call",
+                   "matchScan_latency_ms_p50_p99": [float(np.percentile(times, 50) * 1e3),
+                                                    float(np.percentile(times, 99) * 1e3)],
+                   "search_kernels_ms_max_over_devices": float(np.mean(kms))},
+        "clocks": clocks,
+        "e2e": {"value": total / (ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int((c1["h2d_bytes"] - c0["h2d_bytes"]) // args.steps),
+                "d2h_bytes_per_step": int((c1["d2h_bytes"] - c0["d2h_bytes"]) // args.steps),
+                "matchScan_latency_ms": ms},
+        "gpu_launches": int((c1["launches"] - c0["launches"]) // max(args.steps, 1)),
+        "useful_evaluations": {"per_launch_all_devices": st["useful_evaluations"], "items": st["items"]},
+        "parity": golden_parity(r[:4], args.scale),
+        "single_process": True,
+    }
+    print(json.dumps(line))
+
+
 def cpu_baseline_and_parity(w, m, result, args):
     """cpu_baseline: single-threaded reference on a bounded theta sample (rank 0, N=1).
     parity: the reference's matchScan on a window centred on the device's winner must
@@ -659,6 +720,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="search kernel variant (A/B runs)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="cross-GPU exchange of the partial records (N > 1)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive the --gpus N devices from ONE process through one multi-device handle")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()

@@ -240,6 +240,10 @@ NDT2D_API int ndt2d_matcher_fetch_result(
  * peer-to-peer exchange is in use (0: host combine), matchScans that ran on all devices so far,
  * sequence number of the last exchange. */
 NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4);
+/* A matchScan of a multi-device handle is spread over the devices when it has at least
+ * min_pairs (candidate, scan point) pairs (default 1e10, ~0.4 ms of one B200: smaller searches
+ * are latency-bound and stay on devices[0]). */
+NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pairs);
 /* Per-device duration (ms, CUDA events on each device's own stream) of the search kernels of the
  * last matchScan of a multi-device handle, and its tallies summed over the devices
  * (totals3 = useful evaluations, (point, region) items, 0). */

@@ -15,9 +15,12 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -157,6 +160,20 @@ void axis_thresholds(double origin, double cell, uint32_t size, std::vector<doub
 // ---------------------------------------------------------------- matcher
 constexpr size_t kBatchLanes = 4;
 
+// Host thread bound to one device of a multi-device handle: the per-device host work of a
+// search (staging, the libm cos / sin of the device's theta slices, the launches) runs on all
+// devices at once instead of one after the other.
+struct GroupWorker
+{
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> task;
+  bool has_task = false, done = false, quit = false;
+  int rc = 0;
+  char err[512] = "";
+};
+
 struct ndt2d_matcher
 {
   std::mutex mu;
@@ -207,9 +224,11 @@ struct ndt2d_matcher
   // single-process multi-GPU (ndt2d_params.n_devices > 1): this handle (rank 0, devices[0]) owns
   // one sub-handle per further device; group[r] = the handle of rank r (group[0] == this)
   std::vector<ndt2d_matcher *> group;
+  GroupWorker * worker = nullptr;       // of a sub-handle (rank >= 1)
   bool group_p2p = false;               // mailboxes mapped: fused exchange; else host combine
   unsigned long long group_seq = 0;
   unsigned long long group_searches = 0;  // matchScans that ran on all devices
+  double group_min_pairs = 1.0e10;        // smallest search spread over the devices
   bool pipelined = false;
   std::vector<ndt2d_matcher *> lanes;   // sub-handles of match_scan_batch (created on first use)
   PinnedBuffer h_arena;
@@ -716,6 +735,7 @@ static int match_scan_batch_locked(
   const double * query_poses, const uint64_t * query_pt_offsets, const double * query_pts_xy,
   double * out_delta3, int * delta_written, double * out_cov9, double * out_score);
 static int group_create(ndt2d_matcher * m);
+static int group_run(ndt2d_matcher * m, const std::function<int(size_t, ndt2d_matcher *)> & fn);
 static bool group_worthwhile(const ndt2d_matcher * m, size_t npts);
 static int match_scan_group(
   ndt2d_matcher * m, const double * pose3, const double * pts_xy, size_t npts,
@@ -861,7 +881,20 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   if (!m) {return NDT2D_OK;}
   for (ndt2d_matcher * sub : m->lanes) {ndt2d_matcher_destroy(sub);}
   m->lanes.clear();
-  for (size_t r = 1; r < m->group.size(); ++r) {ndt2d_matcher_destroy(m->group[r]);}
+  for (size_t r = 1; r < m->group.size(); ++r) {
+    ndt2d_matcher * s = m->group[r];
+    if (s->worker) {
+      {
+        std::lock_guard<std::mutex> wl(s->worker->mu);
+        s->worker->quit = true;
+      }
+      s->worker->cv.notify_all();
+      if (s->worker->th.joinable()) {s->worker->th.join();}
+      delete s->worker;
+      s->worker = nullptr;
+    }
+    ndt2d_matcher_destroy(s);
+  }
   m->group.clear();
   {
     DeviceGuard guard(m->device);
@@ -911,12 +944,12 @@ NDT2D_API int ndt2d_matcher_add_scans(
   if (!m || (n_scans && (!poses || !pt_offsets))) {return NDT2D_ERR_INVALID;}
   if (n_scans && pt_offsets[n_scans] > pt_offsets[0] && !pts_xy) {return NDT2D_ERR_INVALID;}
   std::lock_guard<std::mutex> lock(m->mu);
-  // a multi-device handle replicates the model: every device builds it from the same scans
-  for (size_t r = 1; r < m->group.size(); ++r) {
-    ndt2d_matcher * s = m->group[r];
-    DeviceGuard guard(s->device);
-    const int rc = add_scans_locked(s, n_scans, poses, pt_offsets, pts_xy);
-    if (rc) {return rc;}
+  // a multi-device handle replicates the model: every device builds it from the same scans,
+  // all devices at once (one host thread per device)
+  if (m->group.size() > 1) {
+    return group_run(m, [&](size_t, ndt2d_matcher * s) {
+               return add_scans_locked(s, n_scans, poses, pt_offsets, pts_xy);
+             });
   }
   DeviceGuard guard(m->device);
   return add_scans_locked(m, n_scans, poses, pt_offsets, pts_xy);
@@ -2289,7 +2322,65 @@ static int group_create(ndt2d_matcher * m)
     }
   }
   m->group_p2p = p2p;
+  for (int r = 1; r < n; ++r) {
+    ndt2d_matcher * s = m->group[r];
+    GroupWorker * w = new (std::nothrow) GroupWorker();
+    if (!w) {return NDT2D_ERR_INVALID;}
+    s->worker = w;
+    const int dev = s->device;
+    w->th = std::thread([w, dev]() {
+          cudaSetDevice(dev);
+          std::unique_lock<std::mutex> lk(w->mu);
+          for (;;) {
+            w->cv.wait(lk, [w]() {return w->has_task || w->quit;});
+            if (w->quit) {return;}
+            std::function<int()> task = std::move(w->task);
+            w->has_task = false;
+            lk.unlock();
+            g_last_error[0] = 0;
+            const int rc = task();
+            lk.lock();
+            w->rc = rc;
+            snprintf(w->err, sizeof(w->err), "%s", g_last_error);
+            w->done = true;
+            w->cv.notify_all();
+          }
+        });
+  }
   return NDT2D_OK;
+}
+
+// fn(rank, handle) on every device of the group at once: ranks >= 1 on their worker threads
+// (already bound to their device), rank 0 on the calling thread.  Returns the first failure.
+static int group_run(ndt2d_matcher * m, const std::function<int(size_t, ndt2d_matcher *)> & fn)
+{
+  const size_t world = m->group.size();
+  for (size_t r = 1; r < world; ++r) {
+    ndt2d_matcher * s = m->group[r];
+    GroupWorker * w = s->worker;
+    {
+      std::lock_guard<std::mutex> wl(w->mu);
+      w->task = [&fn, r, s]() {return fn(r, s);};
+      w->has_task = true;
+      w->done = false;
+    }
+    w->cv.notify_all();
+  }
+  int rc = NDT2D_OK;
+  {
+    DeviceGuard guard(m->device);
+    rc = fn(0, m);
+  }
+  for (size_t r = 1; r < world; ++r) {
+    GroupWorker * w = m->group[r]->worker;
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [w]() {return w->done;});
+    if (w->rc && !rc) {
+      rc = w->rc;
+      snprintf(g_last_error, sizeof(g_last_error), "%s", w->err);
+    }
+  }
+  return rc;
 }
 
 // A search is spread over the devices when every device gets enough slices to amortise the
@@ -2299,8 +2390,8 @@ static bool group_worthwhile(const ndt2d_matcher * m, size_t npts)
   if (m->group.size() < 2) {return false;}
   const double n_use = static_cast<double>(subsample_count(m, npts));
   const double pairs = static_cast<double>(m->dth.size()) * m->dlin.size() * m->dlin.size() * n_use;
-  // (1e10 pairs are ~0.4 ms of one B200)
-  return pairs >= 1.0e10 && m->dth.size() >= 4 * m->group.size();
+  // (the default, 1e10 pairs, is ~0.4 ms of one B200)
+  return pairs >= m->group_min_pairs && m->dth.size() >= 4 * m->group.size();
 }
 
 static int match_scan_group(
@@ -2309,35 +2400,41 @@ static int match_scan_group(
 {
   const size_t world = m->group.size();
   const size_t n_ang = m->dth.size();
-  int rc = NDT2D_OK;
-  // stage the scan on every device ((cos, sin) only of the rank's own slices, on first use)
-  for (size_t r = 0; r < world && !rc; ++r) {
-    ndt2d_matcher * s = m->group[r];
-    DeviceGuard guard(s->device);
-    if (!s->has_model) {return NDT2D_ERR_STATE;}
-    rc = stage_scan_locked(s, pose3, pts_xy, npts, true);
-    if (!rc) {rc = ensure_trig_locked(s, r, n_ang, world);}
+  for (size_t r = 0; r < world; ++r) {
+    if (!m->group[r]->has_model) {return NDT2D_ERR_STATE;}
   }
-  if (rc) {return rc;}
   const unsigned long long seq = ++m->group_seq;
-  // enqueue all searches before waiting for any: the devices run concurrently
-  for (size_t r = 0; r < world && !rc; ++r) {
-    ndt2d_matcher * s = m->group[r];
-    DeviceGuard guard(s->device);
-    SearchView sv = search_view(s);
-    sv.theta_stride = static_cast<uint32_t>(world);
-    ExchangeView xv;
-    xv.peers = s->d_peer_table.as<void *>();
-    xv.world = static_cast<uint32_t>(world);
-    xv.rank = static_cast<uint32_t>(r);
-    xv.seq = seq;
-    xv.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
-    rc = ndt2d_launch_search(model_view(s), sv, static_cast<uint32_t>(r),
-        static_cast<uint32_t>(n_ang), m->prm.kernel_variant, s->d_blockpart.as<double>(),
-        s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &s->ctr,
-        s->ev_begin, s->ev_end, m->group_p2p ? &xv : nullptr);
-    s->ev_valid = rc == NDT2D_OK;
-  }
+  const bool p2p = m->group_p2p;
+  const int variant = m->prm.kernel_variant;
+  // every device at once (one host thread each): stage the scan, the libm (cos, sin) of the
+  // device's own theta slices, the strided search + fused exchange, then wait for the stream
+  int rc = group_run(m, [&](size_t r, ndt2d_matcher * s) {
+        int rc1 = stage_scan_locked(s, pose3, pts_xy, npts, true);
+        if (!rc1) {rc1 = ensure_trig_locked(s, r, n_ang, world);}
+        if (rc1) {return rc1;}
+        SearchView sv = search_view(s);
+        sv.theta_stride = static_cast<uint32_t>(world);
+        ExchangeView xv;
+        xv.peers = s->d_peer_table.as<void *>();
+        xv.world = static_cast<uint32_t>(world);
+        xv.rank = static_cast<uint32_t>(r);
+        xv.seq = seq;
+        xv.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+        rc1 = ndt2d_launch_search(model_view(s), sv, static_cast<uint32_t>(r),
+            static_cast<uint32_t>(n_ang), variant, s->d_blockpart.as<double>(),
+            s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &s->ctr,
+            s->ev_begin, s->ev_end, p2p ? &xv : nullptr);
+        s->ev_valid = rc1 == NDT2D_OK;
+        if (r != 0) {
+          // rank 0's stream is waited for by the fetch below
+          const cudaError_t e = cudaStreamSynchronize(s->stream);
+          if (e != cudaSuccess && !rc1) {
+            ndt2d_set_error("cudaStreamSynchronize", e, __FILE__, __LINE__);
+            rc1 = NDT2D_ERR_CUDA;
+          }
+        }
+        return rc1;
+      });
   if (rc) {
     for (size_t r = 0; r < world; ++r) {cudaStreamSynchronize(m->group[r]->stream);}
     return rc;
@@ -2352,8 +2449,6 @@ static int match_scan_group(
     }
     for (size_t r = 1; r < world; ++r) {
       ndt2d_matcher * s = m->group[r];
-      DeviceGuard guard(s->device);
-      NDT2D_CUDA_TRY(cudaStreamSynchronize(s->stream));
       m->ctr.launches += s->ctr.launches;
       m->ctr.h2d_bytes += s->ctr.h2d_bytes;
       s->ctr = Counters{0, 0, 0};
@@ -2398,6 +2493,14 @@ NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4)
   info4[1] = m->group_p2p ? 1 : 0;
   info4[2] = m->group_searches;
   info4[3] = m->group_seq;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pairs)
+{
+  if (!m || !(min_pairs >= 0.0)) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->group_min_pairs = min_pairs;
   return NDT2D_OK;
 }
 

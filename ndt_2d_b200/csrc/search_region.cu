@@ -291,33 +291,35 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t RX, uint32_t RY,
   uint32_t Qx, uint32_t Qy, uint32_t n_pts_pad, uint32_t * __restrict__ coords)
 {
+  // one thread per table entry: x = scan point, y = region column / row q, z = theta slice
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t q = blockIdx.y;
   if (i >= sv.n_pts) {return;}
   const double2 p = sv.pts[i];
-  const double inv_cell = 1.0 / mv.g.cell_size, inv_h = 1.0 / sv.linear_res;
+  const double inv_cell = 1.0 / mv.g.cell_size, inv_h = sv.inv_linear_res;
   const uint32_t n_lin = sv.n_lin;
-  for (uint32_t it = blockIdx.y; it < n_theta; it += gridDim.y) {
+  const bool is_x = q < Qx;
+  const uint32_t qq = is_x ? q : q - Qx, R = is_x ? RX : RY;
+  const uint32_t j0 = qq * R, n = min(R, n_lin - j0);
+  const double * __restrict__ thr = is_x ? mv.thr_x : mv.thr_y;
+  const uint32_t size = is_x ? mv.g.size_x : mv.g.size_y;
+  const double origin = is_x ? mv.g.origin_x : mv.g.origin_y;
+  const double d0 = sv.dlin[j0];
+  for (uint32_t it = blockIdx.z; it < n_theta; it += gridDim.z) {
     const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
-    const double ox = __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x);
-    const double oy = __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-    uint32_t * cx = coords + (static_cast<size_t>(it) * (Qx + Qy)) * n_pts_pad + i;
-    uint32_t * cy = cx + static_cast<size_t>(Qx) * n_pts_pad;
-    for (uint32_t q = 0; q < Qx; ++q) {
-      const uint32_t j0 = q * RX, n = min(RX, n_lin - j0);
-      const uint32_t pc = padded_coord<false>(
-        __dadd_rn(ox, sv.dlin[j0]), mv.thr_x, mv.g.size_x, mv.g.origin_x, inv_cell);
-      const uint32_t k1 = count_below(ox, sv.dlin + j0, n, mv.thr_x[pc], inv_h);
+    // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
+    const double o = is_x ?
+      __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x) :
+      __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
+    const uint32_t pc = padded_coord<false>(__dadd_rn(o, d0), thr, size, origin, inv_cell);
+    const uint32_t k1 = count_below(o, sv.dlin + j0, n, thr[pc], inv_h);
+    uint32_t e = pc | (k1 << 16);
+    if (is_x) {
       const uint32_t k2 = k1 == n ? n :
-        count_below(ox, sv.dlin + j0, n, mv.thr_x[min(pc + 1u, mv.g.size_x + 1u)], inv_h);
-      cx[static_cast<size_t>(q) * n_pts_pad] = pc | (k1 << 16) | (k2 << 22);
+        count_below(o, sv.dlin + j0, n, thr[min(pc + 1u, size + 1u)], inv_h);
+      e |= k2 << 22;
     }
-    for (uint32_t q = 0; q < Qy; ++q) {
-      const uint32_t j0 = q * RY, n = min(RY, n_lin - j0);
-      const uint32_t pc = padded_coord<false>(
-        __dadd_rn(oy, sv.dlin[j0]), mv.thr_y, mv.g.size_y, mv.g.origin_y, inv_cell);
-      const uint32_t k = count_below(oy, sv.dlin + j0, n, mv.thr_y[pc], inv_h);
-      cy[static_cast<size_t>(q) * n_pts_pad] = pc | (k << 16);
-    }
+    coords[(static_cast<size_t>(it) * (Qx + Qy) + q) * n_pts_pad + i] = e;
   }
 }
 
@@ -613,7 +615,7 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   // first moves the statistics to [3..4] for ndt2d_matcher_search_stats
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
   if (PRE) {
-    dim3 grid((sv.n_pts + 127u) / 128u, min(n_theta, 65535u));
+    dim3 grid((sv.n_pts + 127u) / 128u, pl.Qx + pl.Qy, min(n_theta, 65535u));
     region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.RX, pl.RY,
       pl.Qx, pl.Qy, n_pts_pad, d_coords);
     NDT2D_LAUNCH_CHECK(ctr);

@@ -451,6 +451,10 @@ class ScanMatcherNDT:
         L.check(L.lib.ndt2d_matcher_group_info(self.handle, L.u64ptr(out)), "group_info")
         return dict(devices=int(out[0]), p2p=bool(out[1]), group_searches=int(out[2]), seq=int(out[3]))
 
+    def set_group_threshold(self, min_pairs: float) -> None:
+        """Smallest search (candidate x point pairs) a multi-device handle spreads over its devices."""
+        L.check(L.lib.ndt2d_matcher_set_group_threshold(self.handle, float(min_pairs)), "set_group_threshold")
+
     def group_search_stats(self) -> dict:
         """Per-device search-kernel durations of the last matchScan + tallies over all devices."""
         ms = np.zeros(16)

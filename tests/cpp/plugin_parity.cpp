@@ -383,10 +383,10 @@ int main(int argc, char ** argv)
     const int n_gpus = std::min(ndt2d_device_count(), 8);
     rclcpp::Node big;
     big.overrides["global_scan_matcher.ndt_resolution"] = 0.25;
-    big.overrides["global_scan_matcher.search_linear_size"] = 1.5;
+    big.overrides["global_scan_matcher.search_linear_size"] = 1.0;
     big.overrides["global_scan_matcher.search_linear_resolution"] = 0.01;
-    big.overrides["global_scan_matcher.search_angular_size"] = 1.6;
-    big.overrides["global_scan_matcher.search_angular_resolution"] = 0.002;
+    big.overrides["global_scan_matcher.search_angular_size"] = 0.8;
+    big.overrides["global_scan_matcher.search_angular_resolution"] = 0.004;
     big.overrides["global_scan_matcher.laser_max_beams"] = 360;
     rclcpp::Node big_n = big;
     big_n.overrides["global_scan_matcher.n_gpus"] = n_gpus;
@@ -394,6 +394,9 @@ int main(int argc, char ** argv)
     one->initialize("global_scan_matcher", &big, 10.0);
     many->initialize("global_scan_matcher", &big_n, 10.0);
     for (auto & m : {one, many}) {m->addScans(scans.begin(), scans.end());}
+    // (this test's search is smaller than the default threshold for spreading a search)
+    ndt2d_matcher_set_group_threshold(
+      dynamic_cast<ndt_2d_b200::ScanMatcherNDT *>(many.get())->handle(), 1.0e8);
     ndt_2d::ScanPtr q3(new ndt_2d::Scan(300));
     q3->setPose(ndt_2d::Pose2d(truth.x - 0.4, truth.y + 0.3, truth.theta - 0.3));
     q3->setPoints(query->getPoints());

@@ -24,6 +24,7 @@ def main():
     w = synth.config4(scale=0.25)
     one = ScanMatcherNDT.from_params(w.params, device=0)
     many = ScanMatcherNDT.from_params(w.params, devices=devices)
+    many.set_group_threshold(1.0e9)          # this reduced window is below the default threshold
     for m in (one, many):
         m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
     full = one.match_scan_raw(w.query_pose, w.query_points)
