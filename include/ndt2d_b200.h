@@ -244,6 +244,10 @@ NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4);
  * min_pairs (candidate, scan point) pairs (default 1e10, ~0.4 ms of one B200: smaller searches
  * are latency-bound and stay on devices[0]). */
 NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pairs);
+/* Small searches and small model builds (the per-scan local match: tens of microseconds) skip
+ * the CUDA event records that feed search_stats / build_stats kernel times unless on != 0
+ * (default off; large searches and builds are always timed). */
+NDT2D_API int ndt2d_matcher_set_timing(ndt2d_matcher * m, int on);
 /* Per-device duration (ms, CUDA events on each device's own stream) of the search kernels of the
  * last matchScan of a multi-device handle, and its tallies summed over the devices
  * (totals3 = useful evaluations, (point, region) items, 0). */
@@ -439,6 +443,21 @@ NDT2D_API int ndt2d_probe_gather(int device, size_t table_bytes, double * out_gb
 NDT2D_API int ndt2d_probe_ex2(int device, double * out_evals_per_s);
 /* GB/s (read + write) of a plain device-to-device copy of `bytes`. */
 NDT2D_API int ndt2d_probe_copy(int device, size_t bytes, double * out_gbps);
+/* Self-check of the build's divide-by-point-count (csrc/build_common.cuh: a correctly rounded
+ * quotient from the count's reciprocal, 3 dependent operations instead of the IEEE divide's ~10
+ * on the critical path of Cell::addPoint's recurrence, ndt_model.cpp:50-63): `trials`
+ * pseudo-random (numerator, count <= 2^20) pairs against __ddiv_rn; *out_mismatches must be 0. */
+NDT2D_API int ndt2d_probe_div_by_count(int device, uint64_t seed, uint64_t trials,
+  uint64_t * out_mismatches);
+/* Latency of the node's per-scan calls as a C / C++ caller sees them (no binding overhead):
+ * `calls` repetitions, each timed with the host's steady clock, microseconds into out_us[calls].
+ *   what = 0  ndt2d_matcher_match_scan(pose3, pts)                      (ndt_mapper.cpp:513)
+ *   what = 1  reset + add_scans + score_points + match_scan             (ndt_mapper.cpp:508-515)
+ * The map arguments are only read for what = 1. */
+NDT2D_API int ndt2d_probe_call_latency(
+  ndt2d_matcher * m, int what, size_t n_scans, const double * map_poses,
+  const uint64_t * map_pt_offsets, const double * map_pts_xy, const double * pose3,
+  const double * pts_xy, size_t npts, size_t calls, double * out_us);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ SIGNATURES = {
     "ndt2d_matcher_fetch_partial": (C.c_int, [_vp, _dp]),
     "ndt2d_matcher_group_info": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_set_group_threshold": (C.c_int, [_vp, C.c_double]),
+    "ndt2d_matcher_set_timing": (C.c_int, [_vp, C.c_int]),
     "ndt2d_matcher_group_search_stats": (C.c_int, [_vp, _dp, C.c_size_t, _u64p]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_combine_partials_host": (
@@ -113,6 +114,9 @@ SIGNATURES = {
                   C.POINTER(C.c_size_t)]),
     "ndt2d_probe_gather": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ndt2d_probe_copy": (C.c_int, [C.c_int, C.c_size_t, _dp]),
+    "ndt2d_probe_div_by_count": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _u64p]),
+    "ndt2d_probe_call_latency": (C.c_int, [_vp, C.c_int, C.c_size_t, _dp, _u64p, _dp, _dp, _dp,
+                                           C.c_size_t, C.c_size_t, _dp]),
     "ndt2d_probe_ex2": (C.c_int, [C.c_int, _dp]),
     "ndt2d_filter_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, _vp, C.POINTER(_vp)]),
     "ndt2d_filter_destroy": (C.c_int, [_vp]),

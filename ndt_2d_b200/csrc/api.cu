@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <condition_variable>
@@ -189,13 +190,14 @@ struct ndt2d_matcher
 
   bool has_model = false;
   GridDesc g{};
-  DeviceBuffer d_occ, d_occd, d_rec, d_rec_fast, d_rec_vtx, d_thr, d_nvalid;
+  DeviceBuffer d_occ, d_occd, d_rec, d_rec_fast, d_rec_vtx, d_nvalid;
+  double * d_thr = nullptr;          // thr_x, thr_y: the head of d_build_in
   uint32_t rec_cap = 0;
   uint32_t n_valid = 0;
 
   BuildScratch bs{};
   DeviceBuffer d_sx, d_sy, d_heads, d_nheads, d_wx, d_wy, d_key0, d_key1, d_val0, d_val1, d_seglen, d_hist, d_scantmp;
-  DeviceBuffer d_scan_tf, d_offsets, d_mappts;
+  DeviceBuffer d_build_in;           // [thresholds | scan transforms | offsets | map points]
   size_t n_map_points = 0;
   int sorted_buf = 0;
 
@@ -236,6 +238,10 @@ struct ndt2d_matcher
   DeviceBuffer d_batch_results, d_batch_arena;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the last search kernel
   bool ev_valid = false;
+  // small searches / builds skip the event records (two driver calls and a bubble between the
+  // kernels each) unless asked for: ndt2d_matcher_set_timing
+  bool time_small = false;
+  unsigned long long host_seq = 0;   // HostMailbox sequence of the last search
   cudaEvent_t evb_begin = nullptr, evb_end = nullptr;  // bracket the kernels of the last build
   bool evb_valid = false;
 };
@@ -252,8 +258,8 @@ ModelView model_view(const ndt2d_matcher * m)
   mv.rec = m->d_rec.as<double>();
   mv.rec_fast = m->d_rec_fast.as<double>();
   mv.rec_vtx = m->d_rec_vtx.as<double>();
-  mv.thr_x = m->d_thr.as<double>();
-  mv.thr_y = m->d_thr.as<double>() + (m->g.size_x + 2);
+  mv.thr_x = m->d_thr;
+  mv.thr_y = m->d_thr + (m->g.size_x + 2);
   mv.n_valid_cap = m->rec_cap;
   return mv;
 }
@@ -406,12 +412,20 @@ int add_scans_impl(
   const size_t thr_bytes = (static_cast<size_t>(g.size_x) + 2 + g.size_y + 2) * sizeof(double);
   int rc = NDT2D_OK;
 
-  // ---- device buffers
+  // ---- device buffers.  Everything the build reads from the host sits in ONE buffer,
+  // [thr_x thr_y | per-scan transforms | offsets | points], so that a small model (every
+  // rolling window) is uploaded by a single copy from one pinned staging block.
   const size_t np1 = n_points ? n_points : 1;
-  if ((rc = m->d_scan_tf.ensure(tf_bytes ? tf_bytes : 32))) {return rc;}
-  if ((rc = m->d_offsets.ensure(off_bytes))) {return rc;}
-  if ((rc = m->d_thr.ensure(thr_bytes))) {return rc;}
-  if ((rc = m->d_mappts.ensure(np1 * sizeof(double2)))) {return rc;}
+  const size_t o_tf = (thr_bytes + 31) & ~size_t(31);
+  const size_t o_off = o_tf + tf_bytes;
+  const size_t o_pts = (o_off + off_bytes + 15) & ~size_t(15);
+  const size_t in_bytes = o_pts + np1 * sizeof(double2);
+  if ((rc = m->d_build_in.ensure(in_bytes))) {return rc;}
+  char * const d_in = m->d_build_in.as<char>();
+  m->d_thr = reinterpret_cast<double *>(d_in);
+  double4 * const d_scan_tf = reinterpret_cast<double4 *>(d_in + o_tf);
+  uint64_t * const d_offsets = reinterpret_cast<uint64_t *>(d_in + o_off);
+  double2 * const d_mappts = reinterpret_cast<double2 *>(d_in + o_pts);
   if ((rc = m->d_wx.ensure(np1 * sizeof(double)))) {return rc;}
   if ((rc = m->d_wy.ensure(np1 * sizeof(double)))) {return rc;}
   if ((rc = m->d_sx.ensure(np1 * sizeof(double)))) {return rc;}
@@ -451,34 +465,35 @@ int add_scans_impl(
   m->bs.hist = m->d_hist.as<uint32_t>();
   m->bs.scan_tmp = m->d_scantmp.as<uint32_t>();
 
-  // ---- uploads: the points first
+  // ---- uploads.  Large model: the points (the bulk of the bytes) go first, straight from the
+  // caller's buffer, and the host-side staging below overlaps that copy.  Small model
+  // (pipelined: nobody waits for the device): points and staging share one arena block and
+  // one copy.
   cudaStream_t st = m->stream;
-  if (n_points) {
-    const double * src = pts_xy + 2 * off0;
-    if (m->pipelined) {
-      // pageable sources make cudaMemcpyAsync wait for the stream: go through the arena
-      char * hp = nullptr;
-      if ((rc = stage_alloc(m, n_points * sizeof(double2), &hp))) {return rc;}
-      memcpy(hp, src, n_points * sizeof(double2));
-      src = reinterpret_cast<const double *>(hp);
+  const double * src_pts = pts_xy + 2 * off0;
+  char * hs = nullptr;
+  const bool one_copy = m->pipelined;
+  if (one_copy) {
+    if ((rc = stage_alloc(m, in_bytes, &hs))) {return rc;}
+    if (n_points) {memcpy(hs + o_pts, src_pts, n_points * sizeof(double2));}
+  } else {
+    if (n_points) {
+      NDT2D_CUDA_TRY(cudaMemcpyAsync(d_mappts, src_pts, n_points * sizeof(double2),
+        cudaMemcpyHostToDevice, st));
     }
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_mappts.p, src, n_points * sizeof(double2),
-      cudaMemcpyHostToDevice, st));
+    if ((rc = stage_alloc(m, o_pts, &hs))) {
+      cudaStreamSynchronize(st);  // the points copy reads the caller's buffer
+      return rc;
+    }
   }
 
-  // ---- host staging: per-scan transform, rebased offsets, axis thresholds -- computed while
-  // the points (the bulk of the bytes) are already on their way
+  // ---- host staging: axis thresholds, per-scan transform, rebased offsets
   std::vector<double> thr_x, thr_y;
   axis_thresholds(g.origin_x, g.cell_size, g.size_x, thr_x);
   axis_thresholds(g.origin_y, g.cell_size, g.size_y, thr_y);
-  char * hs = nullptr;
-  if ((rc = stage_alloc(m, tf_bytes + off_bytes + thr_bytes, &hs))) {
-    cudaStreamSynchronize(st);  // the points copy reads the caller's buffer
-    return rc;
-  }
-  double4 * h_tf = reinterpret_cast<double4 *>(hs);
-  uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + tf_bytes);
-  double * h_thr = reinterpret_cast<double *>(hs + tf_bytes + off_bytes);
+  double * h_thr = reinterpret_cast<double *>(hs);
+  double4 * h_tf = reinterpret_cast<double4 *>(hs + o_tf);
+  uint64_t * h_off = reinterpret_cast<uint64_t *>(hs + o_off);
   for (size_t k = 0; k < n_scans; ++k) {
     const double * pose = poses + 3 * k;
     // ndt_model.cpp:135-136
@@ -489,21 +504,21 @@ int add_scans_impl(
   memcpy(h_thr, thr_x.data(), thr_x.size() * sizeof(double));
   memcpy(h_thr + thr_x.size(), thr_y.data(), thr_y.size() * sizeof(double));
 
-  if (tf_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_scan_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
-  }
-  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_offsets.p, h_off, off_bytes, cudaMemcpyHostToDevice, st));
-  NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_thr.p, h_thr, thr_bytes, cudaMemcpyHostToDevice, st));
+  NDT2D_CUDA_TRY(cudaMemcpyAsync(d_in, hs, one_copy ? o_pts + n_points * sizeof(double2) : o_off + off_bytes,
+    cudaMemcpyHostToDevice, st));
   m->ctr.h2d_bytes += tf_bytes + off_bytes + thr_bytes + n_points * sizeof(double2);
 
-  if (m->evb_begin) {cudaEventRecord(m->evb_begin, st);}
-  rc = ndt2d_launch_build(g, m->d_scan_tf.as<double4>(), m->d_offsets.as<uint64_t>(), n_scans,
-      m->d_mappts.as<double2>(), n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
+  const bool small_build = ndt2d_build_is_small(g, n_points);
+  const bool timed_build = !small_build || m->time_small;
+  m->evb_valid = false;
+  if (timed_build && m->evb_begin) {cudaEventRecord(m->evb_begin, st);}
+  rc = ndt2d_launch_build(g, d_scan_tf, d_offsets, n_scans,
+      d_mappts, n_points, m->bs, m->d_occ.as<uint2>(), m->d_occd.as<uint32_t>(),
       m->d_rec.as<double>(), m->d_rec_fast.as<double>(), m->d_rec_vtx.as<double>(), m->rec_cap,
       m->d_nvalid.as<uint32_t>(), st,
       &m->ctr, &m->sorted_buf);
   if (rc) {return rc;}
-  if (m->evb_end) {
+  if (timed_build && m->evb_end) {
     cudaEventRecord(m->evb_end, st);
     m->evb_valid = true;
   }
@@ -613,6 +628,50 @@ void unpack_result(const double * r32, double * out_delta3, int * delta_written,
   if (out_score) {*out_score = r32[29];}
 }
 
+// Host side of the HostMailbox (ndt2d_internal.h): the record lives in h_result[0..31], the
+// flag in h_result[32].  mailbox_arm() before the launch, mailbox_wait() after it.
+HostMailbox mailbox_arm(ndt2d_matcher * m)
+{
+  double * h = m->h_result.as<double>();
+  unsigned long long * flag = reinterpret_cast<unsigned long long *>(h + 32);
+  *reinterpret_cast<volatile unsigned long long *>(flag) = 0ull;
+  m->host_seq += 1;
+  return HostMailbox{h, flag, m->host_seq};
+}
+
+// `spin`: poll the flag (a local match finishes in tens of microseconds: waking up from a
+// blocking synchronisation would cost as much as the search); falls back to the blocking wait
+// after ~2 ms or on a stream error.  Large searches block right away.
+int mailbox_wait(ndt2d_matcher * m, const HostMailbox & hm, bool spin, double * r32)
+{
+  const volatile unsigned long long * flag = hm.flag;
+  bool seen = false;
+  if (spin) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t it = 0;; ++it) {
+      if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == hm.seq) {
+        seen = true;
+        break;
+      }
+      __builtin_ia32_pause();
+      if ((it & 1023u) == 1023u) {
+        if (cudaStreamQuery(m->stream) != cudaErrorNotReady) {break;}   // done or failed
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {break;}
+      }
+    }
+  }
+  if (!seen) {
+    NDT2D_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) != hm.seq) {
+      ndt2d_set_error("search result mailbox not written", cudaErrorUnknown, __FILE__, __LINE__);
+      return NDT2D_ERR_CUDA;
+    }
+  }
+  m->ctr.d2h_bytes += 32 * sizeof(double);
+  memcpy(r32, hm.out32, 32 * sizeof(double));
+  return NDT2D_OK;
+}
+
 int fetch_result_locked(ndt2d_matcher * m, double * r32)
 {
   double * h = m->h_result.as<double>();
@@ -665,13 +724,20 @@ int match_scan_locked(
 {
   int rc = stage_scan_locked(m, pose3, pts_xy, npts);
   if (rc) {return rc;}
+  // a small search (the local match of every scan): no event records, result through the
+  // host mailbox with a polling wait
+  const bool small = static_cast<double>(m->dth.size()) * m->dlin.size() * m->dlin.size() *
+    m->n_pts < 2.0e7;
+  const bool timed = !small || m->time_small;
+  const HostMailbox hm = mailbox_arm(m);
   rc = ndt2d_launch_search(model_view(m), search_view(m), 0, static_cast<uint32_t>(m->dth.size()),
       m->prm.kernel_variant, m->d_blockpart.as<double>(), m->d_partial.as<double>(), nullptr,
-      m->d_counter.as<uint32_t>(), m->stream, &m->ctr, m->ev_begin, m->ev_end);
+      m->d_counter.as<uint32_t>(), m->stream, &m->ctr, timed ? m->ev_begin : nullptr,
+      timed ? m->ev_end : nullptr, nullptr, &hm);
   if (rc) {return rc;}
-  m->ev_valid = true;
+  m->ev_valid = timed;
   double r32[32];
-  if ((rc = fetch_result_locked(m, r32))) {return rc;}
+  if ((rc = mailbox_wait(m, hm, small, r32))) {return rc;}
   unpack_result(r32, out_delta3, delta_written, out_cov9, out_score);
   return NDT2D_OK;
 }
@@ -685,14 +751,27 @@ int score_poses_locked(
   const size_t pts_bytes = n_use * sizeof(double2);
   const size_t tf_bytes = n_poses * sizeof(double4);
   const size_t out_bytes = n_poses * sizeof(double);
-  int rc = m->h_stage.ensure(pts_bytes + tf_bytes + 64);
+  const size_t up_bytes = tf_bytes + pts_bytes;
+  // a handful of poses (scoreScan / scorePoints of the node: one pose) is latency-bound: staged
+  // from the pinned arena (no wait for the upload), scores through the host mailbox
+  const bool small = n_poses <= 8 && up_bytes + 64 <= (size_t(1) << 20);
+  int rc = NDT2D_OK;
+  char * hs = nullptr;
+  if (small) {
+    if ((rc = m->h_arena.ensure(size_t(8) << 20))) {return rc;}
+    const bool was = m->pipelined;
+    m->pipelined = true;
+    rc = stage_alloc(m, up_bytes + 64, &hs);
+    m->pipelined = was;
+  } else {
+    rc = stage_alloc(m, up_bytes + 64, &hs);
+  }
   if (rc) {return rc;}
-  if ((rc = m->d_pts.ensure(pts_bytes ? pts_bytes : 16))) {return rc;}
-  if ((rc = m->d_pose_tf.ensure(tf_bytes ? tf_bytes : 32))) {return rc;}
+  // poses and points share one device buffer: one H2D copy per call
+  if ((rc = m->d_pose_tf.ensure(up_bytes + 32))) {return rc;}
   if ((rc = m->d_out.ensure(out_bytes ? out_bytes : 8))) {return rc;}
   if ((rc = m->h_result.ensure(std::max<size_t>(out_bytes, 64 * sizeof(double))))) {return rc;}
-  m->staged = false;  // d_pts is overwritten
-  double4 * h_tf = m->h_stage.as<double4>();
+  double4 * h_tf = reinterpret_cast<double4 *>(hs);
   double * h_pts = reinterpret_cast<double *>(h_tf + n_poses);
   for (size_t p = 0; p < n_poses; ++p) {
     const double * pose = poses3 + 3 * p;
@@ -706,16 +785,27 @@ int score_poses_locked(
     }
   }
   cudaStream_t st = m->stream;
-  if (pts_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pts.p, h_pts, pts_bytes, cudaMemcpyHostToDevice, st));
+  if (up_bytes) {
+    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pose_tf.p, hs, up_bytes, cudaMemcpyHostToDevice, st));
   }
-  if (tf_bytes) {
-    NDT2D_CUDA_TRY(cudaMemcpyAsync(m->d_pose_tf.p, h_tf, tf_bytes, cudaMemcpyHostToDevice, st));
+  m->ctr.h2d_bytes += up_bytes;
+  const double2 * d_pts = reinterpret_cast<const double2 *>(m->d_pose_tf.as<char>() + tf_bytes);
+  if (small && n_poses) {
+    const HostMailbox hm = mailbox_arm(m);
+    rc = ndt2d_launch_score_poses(model_view(m), d_pts, static_cast<uint32_t>(n_use),
+        m->d_pose_tf.as<double4>(), static_cast<uint32_t>(n_poses), sign, normalise,
+        m->d_out.as<double>(), st, &m->ctr, &hm);
+    if (rc) {return rc;}
+    double r32[32];
+    if ((rc = mailbox_wait(m, hm, true, r32))) {return rc;}
+    m->ctr.d2h_bytes -= 32 * sizeof(double);
+    m->ctr.d2h_bytes += out_bytes;
+    memcpy(out_scores, r32, out_bytes);
+    return NDT2D_OK;
   }
-  m->ctr.h2d_bytes += pts_bytes + tf_bytes;
-  rc = ndt2d_launch_score_poses(model_view(m), m->d_pts.as<double2>(),
-      static_cast<uint32_t>(n_use), m->d_pose_tf.as<double4>(), static_cast<uint32_t>(n_poses),
-      sign, normalise, m->d_out.as<double>(), st, &m->ctr);
+  rc = ndt2d_launch_score_poses(model_view(m), d_pts, static_cast<uint32_t>(n_use),
+      m->d_pose_tf.as<double4>(), static_cast<uint32_t>(n_poses), sign, normalise,
+      m->d_out.as<double>(), st, &m->ctr);
   if (rc) {return rc;}
   if (out_bytes) {
     NDT2D_CUDA_TRY(cudaMemcpyAsync(m->h_result.p, m->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
@@ -906,9 +996,9 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
   {
     DeviceGuard guard(m->device);
     if (m->stream) {cudaStreamSynchronize(m->stream);}
-    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_rec_vtx, &m->d_thr, &m->d_nvalid,
+    DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_rec_vtx, &m->d_nvalid,
       &m->d_sx, &m->d_sy, &m->d_heads, &m->d_nheads, &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
-      &m->d_hist, &m->d_scantmp, &m->d_scan_tf, &m->d_offsets, &m->d_mappts, &m->d_pts,
+      &m->d_hist, &m->d_scantmp, &m->d_build_in, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results, &m->d_batch_arena};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();
@@ -2504,6 +2594,14 @@ NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pa
   return NDT2D_OK;
 }
 
+NDT2D_API int ndt2d_matcher_set_timing(ndt2d_matcher * m, int on)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->time_small = on != 0;
+  return NDT2D_OK;
+}
+
 /* Multi-device handle: duration (ms, CUDA events on each device's stream) of the search kernels of
  * the last matchScan on every device and the tallies of that search summed over the devices:
  * out_ms[n_devices]; totals3 = useful evaluations, (point, region) items, 0. */
@@ -2535,6 +2633,31 @@ NDT2D_API int ndt2d_matcher_group_search_stats(
         cudaGetLastError();
       }
     }
+  }
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_probe_call_latency(
+  ndt2d_matcher * m, int what, size_t n_scans, const double * map_poses,
+  const uint64_t * map_pt_offsets, const double * map_pts_xy, const double * pose3,
+  const double * pts_xy, size_t npts, size_t calls, double * out_us)
+{
+  if (!m || !pose3 || !out_us || (npts && !pts_xy) || (what != 0 && what != 1)) {
+    return NDT2D_ERR_INVALID;
+  }
+  for (size_t k = 0; k < calls; ++k) {
+    double delta[3], cov[9], score = 0.0, s0 = 0.0;
+    int written = 0, rc = NDT2D_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (what == 1) {
+      rc = ndt2d_matcher_reset(m);
+      if (!rc) {rc = ndt2d_matcher_add_scans(m, n_scans, map_poses, map_pt_offsets, map_pts_xy);}
+      if (!rc) {rc = ndt2d_matcher_score_points(m, pts_xy, npts, pose3, &s0);}
+    }
+    if (!rc) {rc = ndt2d_matcher_match_scan(m, pose3, pts_xy, npts, delta, &written, cov, &score);}
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) {return rc;}
+    out_us[k] = std::chrono::duration<double, std::micro>(t1 - t0).count();
   }
   return NDT2D_OK;
 }

@@ -23,9 +23,12 @@
 #include <stdint.h>
 
 #include "ndt2d_internal.h"
+#include "build_common.cuh"
 
 namespace
 {
+
+using ndt2d_dev::div_by_count;
 
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
@@ -622,6 +625,8 @@ struct SmallSmem
   uint32_t cnt[32][256];                           // per-warp digit counters / offsets
   double wx[kSmallMaxPoints];
   double wy[kSmallMaxPoints];
+  double rcp[kSmallMaxPoints + 1];                 // rcp[n] = RN(1 / n): div_by_count's reciprocals
+  double one;                                      // 1.0: the second factor of the mean lanes
   uint32_t occw[kSmallMaxWords];
   uint32_t pref[kSmallMaxWords];
   uint2 heads[kSmallMaxHeads];
@@ -660,7 +665,11 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
   while (n2 < n_points) {n2 <<= 1;}
 
   for (uint32_t w = tid; w < g.n_words; w += kSmallThreads) {sm.occw[w] = 0u;}
-  if (tid == 0) {sm.n_heads = 0u;}
+  for (uint32_t k = tid + 1u; k <= n_points; k += kSmallThreads) {sm.rcp[k] = __drcp_rn(static_cast<double>(k));}
+  if (tid == 0) {
+    sm.n_heads = 0u;
+    sm.one = 1.0;
+  }
   // ---- K1: transform + key (NDT::addScan, ndt_model.cpp:132-152)
   for (uint32_t p = tid; p < n2; p += kSmallThreads) {
     if (p < n_points) {
@@ -801,42 +810,73 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
     }
     occ_dilated[w] = d;
   }
-  // ---- K3b: moment recurrences, 8 lanes per listed cell (see segment_moments_kernel)
-  const uint32_t group = tid >> 3, r = tid & 7u;
-  const uint32_t n_heads = sm.n_heads;
-  for (uint32_t base = 0; base < n_heads; base += kSmallThreads / 8) {
-    const uint32_t cell = base + group;
-    const bool have = cell < n_heads;
-    const uint2 h = have ? sm.heads[cell] : make_uint2(0u, 0u);
-    double v = 0.0, n = 0.0;
-    if (have && r < 5u) {
-      for (uint32_t j = 0; j < h.y; ++j) {
-        const uint32_t p = static_cast<uint32_t>(sm.items[h.x + j]);
-        const double x = sm.wx[p], y = sm.wy[p];
-        const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
-          r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
-        const double n1 = __dadd_rn(n, 1.0);
-        v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
-        n = n1;
+  // ---- K3b: moment recurrences, 5 lanes per listed cell, 6 cells per warp (as
+  // segment_moments_kernel): 192 cells per round of the CTA, so a rolling window (config 1: 141
+  // cells) is one round.  One SM runs all of it, so the phase is bound by the instructions per
+  // recurrence step: every lane forms its term as ONE product a[p] * b[p * stride] -- (x, 1),
+  // (y, 1), (x, x), (x, y), (y, y) chosen by two lane-invariant pointers, x * 1.0 being exact --
+  // instead of selecting among five candidates, the reciprocal of the point count comes from
+  // a table (div_by_count), and the loads of four points are issued ahead of the steps that
+  // consume them.
+  {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t sub = lane / 5u, r = lane - sub * 5u;      // lanes 30, 31: sub == 6, no cell
+    const uint32_t src = (sub < kMomentCellsPerWarp ? sub : kMomentCellsPerWarp - 1u) * 5u;
+    const double * const pa = (r == 1u || r == 4u) ? sm.wy : sm.wx;
+    const double * const pb = r < 2u ? &sm.one : (r == 2u ? sm.wx : sm.wy);
+    const uint32_t sb = r < 2u ? 0u : 1u;
+    const uint32_t n_heads = sm.n_heads;
+    constexpr uint32_t kPerRound = (kSmallThreads / 32u) * kMomentCellsPerWarp;
+    for (uint32_t base = 0; base < n_heads; base += kPerRound) {
+      const uint32_t cell = base + warp * kMomentCellsPerWarp + sub;
+      const bool have = sub < kMomentCellsPerWarp && cell < n_heads;
+      const uint2 h = have ? sm.heads[cell] : make_uint2(0u, 0u);
+      double v = 0.0, n = 0.0;
+      if (have) {
+        const unsigned long long * it = sm.items + h.x;
+        const double * rc = sm.rcp + 1;
+        uint32_t j = 0;
+        for (; j + 4 <= h.y; j += 4) {
+          double t[4], q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t p = static_cast<uint32_t>(it[j + u]);
+            t[u] = __dmul_rn(pa[p], pb[p * sb]);
+            q[u] = rc[j + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double n1 = __dadd_rn(n, 1.0);
+            v = div_by_count(__dadd_rn(__dmul_rn(v, n), t[u]), n1, q[u]);
+            n = n1;
+          }
+        }
+        for (; j < h.y; ++j) {
+          const uint32_t p = static_cast<uint32_t>(it[j]);
+          const double term = __dmul_rn(pa[p], pb[p * sb]);
+          const double n1 = __dadd_rn(n, 1.0);
+          v = div_by_count(__dadd_rn(__dmul_rn(v, n), term), n1, rc[j]);
+          n = n1;
+        }
       }
-    }
-    CellStats c;
-    c.n = static_cast<double>(h.y);
-    c.mean[0] = __shfl_sync(0xffffffffu, v, 0, 8);
-    c.mean[1] = __shfl_sync(0xffffffffu, v, 1, 8);
-    c.corr[0] = __shfl_sync(0xffffffffu, v, 2, 8);
-    c.corr[1] = __shfl_sync(0xffffffffu, v, 3, 8);
-    c.corr[2] = __shfl_sync(0xffffffffu, v, 4, 8);
-    if (have && r == 0u) {
-      stats_finalize(c);
-      const uint32_t k = static_cast<uint32_t>(sm.items[h.x] >> 32);
-      const uint32_t pi = padded_index(g, k);
-      const uint32_t bits = sm.occw[pi >> 5];
-      const uint32_t rank = sm.pref[pi >> 5] + __popc(bits & ((1u << (pi & 31u)) - 1u));
-      if (rank < rec_cap) {
-        write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-          rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-          rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+      CellStats c;
+      c.n = static_cast<double>(h.y);
+      c.mean[0] = __shfl_sync(0xffffffffu, v, src + 0u);
+      c.mean[1] = __shfl_sync(0xffffffffu, v, src + 1u);
+      c.corr[0] = __shfl_sync(0xffffffffu, v, src + 2u);
+      c.corr[1] = __shfl_sync(0xffffffffu, v, src + 3u);
+      c.corr[2] = __shfl_sync(0xffffffffu, v, src + 4u);
+      if (have && r == 0u) {
+        stats_finalize(c);
+        const uint32_t k = static_cast<uint32_t>(sm.items[h.x] >> 32);
+        const uint32_t pi = padded_index(g, k);
+        const uint32_t bits = sm.occw[pi >> 5];
+        const uint32_t rank = sm.pref[pi >> 5] + __popc(bits & ((1u << (pi & 31u)) - 1u));
+        if (rank < rec_cap) {
+          write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+            rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
+            rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+        }
       }
     }
   }

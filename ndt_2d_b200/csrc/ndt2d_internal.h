@@ -176,6 +176,17 @@ struct ExchangeView
   unsigned long long timeout_ns; // bound of the wait (a rank that never arrives must not hang the GPU)
 };
 
+// Result mailbox in MAPPED PINNED HOST memory: the last kernel of a search stores the
+// 32-double result record there itself (zero-copy store over PCIe), fences system-wide and
+// releases `seq` into the flag; the host polls the flag instead of paying for a device-to-host
+// copy plus a stream synchronisation (the local match of every scan is latency-bound).
+struct HostMailbox
+{
+  double * out32;                // device-visible address of the pinned record (null: unused)
+  unsigned long long * flag;     // device-visible address of the pinned sequence flag
+  unsigned long long seq;        // value released when the record is complete
+};
+
 // ---- search.cu ----------------------------------------------------------
 // Search theta slices [theta_begin, theta_end); writes the 32-double record
 // (partial + finished outputs, see ndt2d_launch_combine) to d_partial32.  d_block_partials: scratch, >= capacity returned by
@@ -205,7 +216,8 @@ int ndt2d_launch_search(
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
   uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin = nullptr,
   cudaEvent_t ev_end = nullptr,   // events (optional) bracket the search kernel alone
-  const ExchangeView * exchange = nullptr);  // non-null: fused cross-GPU exchange + combine
+  const ExchangeView * exchange = nullptr,   // non-null: fused cross-GPU exchange + combine
+  const HostMailbox * host = nullptr);       // non-null: result record also stored to the host
 
 // Combine n 16-double partial records (device) into one 32-double record
 // (device): [0..15] partial, [16..18] delta, [19] delta_written,
@@ -219,7 +231,7 @@ int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d
 int ndt2d_launch_score_poses(
   const ModelView & mv, const double2 * d_pts, uint32_t n_pts, const double4 * d_pose_tf,
   uint32_t n_poses, double sign, int normalise, double * d_out, cudaStream_t stream,
-  Counters * ctr);
+  Counters * ctr, const HostMailbox * host = nullptr);  // host: n_poses <= 8 only (one block)
 
 // ---- batched searches (match_scan_batch): several models / scans, one launch each for
 // build, search and final reduction ------------------------------------------------------

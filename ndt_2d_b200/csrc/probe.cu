@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "ndt2d_internal.h"
+#include "build_common.cuh"
 
 namespace
 {
@@ -27,6 +28,29 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(
     acc ^= a.x ^ a.w ^ b.y ^ b.z;
   }
   if (acc == 0x9e3779b9u) {sink[0] = acc;}  // keeps the loads alive
+}
+
+// div_by_count (build_common.cuh) against the IEEE divide on pseudo-random operands: counts in
+// [1, 2^20], numerators of every sign / 53-bit mantissa over 120 binades.
+__global__ void __launch_bounds__(256) div_check_kernel(
+  unsigned long long seed, uint32_t trials_per_thread, unsigned long long * __restrict__ mismatches)
+{
+  unsigned long long x = seed + (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) *
+    0x9E3779B97F4A7C15ull;
+  unsigned long long bad = 0;
+  for (uint32_t it = 0; it < trials_per_thread; ++it) {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    const double b = static_cast<double>(1ull + (x % 1048576ull));
+    const unsigned long long m = x * 0x9E3779B97F4A7C15ull;
+    const int e = static_cast<int>((m >> 52) % 120ull) - 60;
+    double a = ldexp(static_cast<double>(m & ((1ull << 53) - 1ull)), e - 52);
+    if (m >> 63) {a = -a;}
+    const double q = __ddiv_rn(a, b), f = ndt2d_dev::div_by_count(a, b, __drcp_rn(b));
+    bad += __double_as_longlong(q) != __double_as_longlong(f) ? 1ull : 0ull;
+  }
+  if (bad) {atomicAdd(mismatches, bad);}
 }
 
 __global__ void __launch_bounds__(256) copy_probe_kernel(
@@ -177,6 +201,26 @@ NDT2D_API int ndt2d_probe_copy(int device, size_t bytes, double * out_gbps)
   cudaFree(b);
   NDT2D_CUDA_TRY(cudaGetLastError());
   *out_gbps = best;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_probe_div_by_count(int device, uint64_t seed, uint64_t trials,
+  uint64_t * out_mismatches)
+{
+  if (!out_mismatches) {return NDT2D_ERR_INVALID;}
+  if (ndt2d_device_count() <= 0) {return NDT2D_ERR_NO_DEVICE;}
+  if (device >= 0) {NDT2D_CUDA_TRY(cudaSetDevice(device));}
+  unsigned long long * d_bad = nullptr;
+  NDT2D_CUDA_TRY(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+  NDT2D_CUDA_TRY(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+  const uint32_t threads = 1024u * 256u;
+  const uint32_t per_thread = static_cast<uint32_t>((trials + threads - 1) / threads);
+  div_check_kernel<<<1024, 256>>>(seed, per_thread, d_bad);
+  unsigned long long bad = 0;
+  const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  NDT2D_CUDA_TRY(e);
+  *out_mismatches = bad;
   return NDT2D_OK;
 }
 

@@ -409,8 +409,11 @@ __device__ void exchange_and_combine(ExchangeView xv, double * out32, const doub
 __global__ void __launch_bounds__(256) search_finish_kernel(
   const double * __restrict__ stage1, uint32_t n_records, int direct, SearchView sv,
   double n_candidates, double * __restrict__ out32, ExchangeView xv,
-  unsigned long long * __restrict__ counters)
+  unsigned long long * __restrict__ counters, HostMailbox hm)
 {
+  // launched with programmatic stream serialisation: the block may already be resident while
+  // the search kernel still runs; everything below needs that kernel's results
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   Best best{0.0, kNoIndex};
   double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (threadIdx.x == 0 && counters) {
@@ -454,6 +457,17 @@ __global__ void __launch_bounds__(256) search_finish_kernel(
     __threadfence();
     __syncthreads();   // this rank's record is complete and visible to warp 0
     if (threadIdx.x < 32) {exchange_and_combine(xv, out32, sv.dth, sv.dlin, sv.n_lin);}
+  }
+  if (hm.out32) {
+    // the result record goes straight into the caller's mapped pinned memory (HostMailbox);
+    // warp 0 wrote / combined out32 above
+    if (threadIdx.x < 32) {
+      __syncwarp();
+      hm.out32[threadIdx.x] = out32[threadIdx.x];
+      __threadfence_system();
+      __syncwarp();
+      if (threadIdx.x == 0) {st_release_sys(hm.flag, hm.seq);}
+    }
   }
 }
 
@@ -504,14 +518,30 @@ constexpr uint32_t kDirectFinishMax = 4096;   // job records one block folds wit
 
 int launch_final(const double * d_block_partials, uint32_t n_blocks, double * d_stage1,
   const SearchView & sv, double n_candidates, double * d_partial32, cudaStream_t stream,
-  Counters * ctr, const ExchangeView * exchange, uint32_t * d_counter)
+  Counters * ctr, const ExchangeView * exchange, uint32_t * d_counter, const HostMailbox * host)
 {
   ExchangeView xv{};
   if (exchange) {xv = *exchange;}
+  HostMailbox hm{nullptr, nullptr, 0ull};
+  if (host) {hm = *host;}
   unsigned long long * counters = reinterpret_cast<unsigned long long *>(d_counter);
   if (n_blocks <= kDirectFinishMax) {
-    search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, n_blocks, 1, sv, n_candidates,
-      d_partial32, xv, counters);
+    // programmatic dependent launch: a search kernel that executes griddepcontrol.launch_dependents
+    // (the window kernel does, at its start) lets this block become resident while it runs, so the
+    // launch latency of the finish is off the critical path of a local match; the kernel waits
+    // for the search's completion + memory flush itself (griddepcontrol.wait)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NDT2D_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_finish_kernel, d_block_partials, n_blocks, 1, sv,
+      n_candidates, d_partial32, xv, counters, hm));
     NDT2D_LAUNCH_CHECK(ctr);
     return NDT2D_OK;
   }
@@ -519,7 +549,7 @@ int launch_final(const double * d_block_partials, uint32_t n_blocks, double * d_
   search_reduce_kernel<<<nb, 256, 0, stream>>>(d_block_partials, n_blocks, d_stage1);
   NDT2D_LAUNCH_CHECK(ctr);
   search_finish_kernel<<<1, 256, 0, stream>>>(d_stage1, nb, 0, sv, n_candidates, d_partial32, xv,
-    counters);
+    counters, hm);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
 }
@@ -550,13 +580,18 @@ __global__ void combine_kernel(
 }
 
 // An empty theta range still has to produce a neutral record.
-__global__ void empty_partial_kernel(SearchView sv, double * __restrict__ out32)
+__global__ void empty_partial_kernel(SearchView sv, double * __restrict__ out32, HostMailbox hm)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) {return;}
   for (int k = 0; k < 32; ++k) {out32[k] = 0.0;}
   out32[1] = kNoIndex;
   out32[13] = static_cast<double>(sv.n_pts);
   finish_record(out32, sv.dth, sv.dlin, sv.n_lin);
+  if (hm.out32) {
+    for (int k = 0; k < 32; ++k) {hm.out32[k] = out32[k];}
+    __threadfence_system();
+    st_release_sys(hm.flag, hm.seq);
+  }
 }
 
 // ------------------------------------------------------------------ K5
@@ -567,24 +602,33 @@ __global__ void empty_partial_kernel(SearchView sv, double * __restrict__ out32)
 __global__ void __launch_bounds__(256) score_poses_kernel(
   ModelView mv, const double2 * __restrict__ pts, uint32_t n_pts,
   const double4 * __restrict__ pose_tf, uint32_t n_poses, double sign, int normalise,
-  double * __restrict__ out)
+  double * __restrict__ out, HostMailbox hm)
 {
   const uint32_t pose = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (pose >= n_poses) {return;}
-  const double4 tf = pose_tf[pose];  // x, y, cos, sin
-  double acc = 0.0;
-  for (uint32_t i = lane; i < n_pts; i += 32) {
-    const double2 p = pts[i];
-    const double x = __dadd_rn(__dadd_rn(__dmul_rn(tf.z, p.x), __dmul_rn(-tf.w, p.y)), tf.x);
-    const double y = __dadd_rn(__dadd_rn(__dmul_rn(tf.w, p.x), __dmul_rn(tf.z, p.y)), tf.y);
-    acc += point_likelihood_exact(mv, x, y);
+  if (pose < n_poses) {
+    const double4 tf = pose_tf[pose];  // x, y, cos, sin
+    double acc = 0.0;
+    for (uint32_t i = lane; i < n_pts; i += 32) {
+      const double2 p = pts[i];
+      const double x = __dadd_rn(__dadd_rn(__dmul_rn(tf.z, p.x), __dmul_rn(-tf.w, p.y)), tf.x);
+      const double y = __dadd_rn(__dadd_rn(__dmul_rn(tf.w, p.x), __dmul_rn(tf.z, p.y)), tf.y);
+      acc += point_likelihood_exact(mv, x, y);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      double v = sign * acc;
+      if (normalise) {v = v / static_cast<double>(n_pts);}
+      out[pose] = v;
+      if (hm.out32) {
+        hm.out32[pose] = v;   // single-block launch: the scores go straight to the host mailbox
+        __threadfence_system();
+      }
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    double v = sign * acc;
-    if (normalise) {v = v / static_cast<double>(n_pts);}
-    out[pose] = v;
+  if (hm.out32) {
+    __syncthreads();
+    if (threadIdx.x == 0) {st_release_sys(hm.flag, hm.seq);}
   }
 }
 
@@ -615,7 +659,7 @@ int ndt2d_launch_search(
   const ModelView & mv, const SearchView & sv, uint32_t theta_begin, uint32_t theta_end,
   int variant, double * d_block_partials, double * d_partial32, double * d_scores,
   uint32_t * d_counter, cudaStream_t stream, Counters * ctr, cudaEvent_t ev_begin,
-  cudaEvent_t ev_end, const ExchangeView * exchange)
+  cudaEvent_t ev_end, const ExchangeView * exchange, const HostMailbox * host)
 {
   if (theta_end <= theta_begin || sv.n_lin == 0) {
     if (exchange) {
@@ -623,11 +667,12 @@ int ndt2d_launch_search(
       // the same finish kernel (zero stage-1 records)
       ExchangeView xv = *exchange;
       search_finish_kernel<<<1, 256, 0, stream>>>(d_block_partials, 0, 1, sv, 0.0, d_partial32, xv,
-        nullptr);
+        nullptr, host ? *host : HostMailbox{nullptr, nullptr, 0ull});
       NDT2D_LAUNCH_CHECK(ctr);
       return NDT2D_OK;
     }
-    empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32);
+    empty_partial_kernel<<<1, 32, 0, stream>>>(sv, d_partial32,
+      host ? *host : HostMailbox{nullptr, nullptr, 0ull});
     NDT2D_LAUNCH_CHECK(ctr);
     return NDT2D_OK;
   }
@@ -657,7 +702,7 @@ int ndt2d_launch_search(
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, ndt2d_window_records(n_theta, sv.n_lin),
              d_block_partials + stage1_offset, sv, n_candidates, d_partial32, stream, ctr, exchange,
-             nullptr);
+             nullptr, host);
   }
   if (dense) {
     const uint32_t bx = dense_blocks_x(sv.n_lin);
@@ -674,7 +719,7 @@ int ndt2d_launch_search(
     }
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr, exchange, nullptr);
+             n_candidates, d_partial32, stream, ctr, exchange, nullptr, host);
   }
   if (variant != 1) {
     uint32_t n_jobs = 0;
@@ -685,7 +730,7 @@ int ndt2d_launch_search(
     if (rc != NDT2D_OK) {return rc;}
     if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
     return launch_final(d_block_partials, n_jobs, d_block_partials + stage1_offset, sv,
-             n_candidates, d_partial32, stream, ctr, exchange, d_counter);
+             n_candidates, d_partial32, stream, ctr, exchange, d_counter, host);
   }
   const uint32_t bx = plain_blocks_x(sv.n_lin);
   // gridDim.y is limited to 65535: slice the theta range if needed
@@ -702,7 +747,7 @@ int ndt2d_launch_search(
   }
   if (ev_end) {NDT2D_CUDA_TRY(cudaEventRecord(ev_end, stream));}
   return launch_final(d_block_partials, n_theta * bx, d_block_partials + stage1_offset, sv,
-           n_candidates, d_partial32, stream, ctr, exchange, nullptr);
+           n_candidates, d_partial32, stream, ctr, exchange, nullptr, host);
 }
 
 uint32_t ndt2d_dense_batch_records(uint32_t n_ang, uint32_t n_lin)
@@ -745,13 +790,15 @@ int ndt2d_launch_combine(const double * d_partials, uint32_t n, const double * d
 int ndt2d_launch_score_poses(
   const ModelView & mv, const double2 * d_pts, uint32_t n_pts, const double4 * d_pose_tf,
   uint32_t n_poses, double sign, int normalise, double * d_out, cudaStream_t stream,
-  Counters * ctr)
+  Counters * ctr, const HostMailbox * host)
 {
   if (n_poses == 0) {return NDT2D_OK;}
   const uint32_t warps_per_block = 256 / 32;
   const uint32_t grid = (n_poses + warps_per_block - 1) / warps_per_block;
+  HostMailbox hm{nullptr, nullptr, 0ull};
+  if (host && grid == 1) {hm = *host;}   // (the flag protocol needs a single block)
   score_poses_kernel<<<grid, 256, 0, stream>>>(
-    mv, d_pts, n_pts, d_pose_tf, n_poses, sign, normalise, d_out);
+    mv, d_pts, n_pts, d_pose_tf, n_poses, sign, normalise, d_out, hm);
   NDT2D_LAUNCH_CHECK(ctr);
   return NDT2D_OK;
 }

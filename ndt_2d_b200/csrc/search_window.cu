@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(kWinMaxThreads) search_window_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t tile, uint32_t n_groups,
   double * __restrict__ block_partials, double * __restrict__ scores)
 {
+  // the finish kernel of this search may be scheduled now (it waits for this grid's completion
+  // with griddepcontrol.wait): its launch latency overlaps the search
+  asm volatile("griddepcontrol.launch_dependents;");
   window_block<K>(mv, sv, theta_begin, tile, n_groups, block_partials, scores);
 }
 

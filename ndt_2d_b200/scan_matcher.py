@@ -455,6 +455,30 @@ class ScanMatcherNDT:
         """Smallest search (candidate x point pairs) a multi-device handle spreads over its devices."""
         L.check(L.lib.ndt2d_matcher_set_group_threshold(self.handle, float(min_pairs)), "set_group_threshold")
 
+    def probe_call_latency(self, pose, points, calls: int = 200, map_scans=None) -> np.ndarray:
+        """Microseconds per call as a C caller sees them (ndt2d_probe_call_latency): matchScan alone,
+        or, with map_scans = (poses, offsets, points), reset + addScans + scoreScan + matchScan."""
+        pose3 = _pose3(pose)
+        pts = L.f64(points).reshape(-1, 2)
+        out = np.zeros(calls)
+        if map_scans is None:
+            L.check(L.lib.ndt2d_probe_call_latency(self.handle, 0, 0, None, None, None, L.dptr(pose3),
+                                                   L.dptr(pts), pts.shape[0], calls, L.dptr(out)),
+                    "probe_call_latency")
+        else:
+            poses = L.f64(map_scans[0]).reshape(-1, 3)
+            offs = np.ascontiguousarray(map_scans[1], dtype=np.uint64)
+            mpts = L.f64(map_scans[2]).reshape(-1, 2)
+            L.check(L.lib.ndt2d_probe_call_latency(self.handle, 1, poses.shape[0], L.dptr(poses),
+                                                   L.u64ptr(offs), L.dptr(mpts), L.dptr(pose3),
+                                                   L.dptr(pts), pts.shape[0], calls, L.dptr(out)),
+                    "probe_call_latency")
+        return out
+
+    def set_timing(self, on: bool) -> None:
+        """CUDA event timing of small searches / builds too (ndt2d_matcher_set_timing; default off)."""
+        L.check(L.lib.ndt2d_matcher_set_timing(self.handle, int(bool(on))), "set_timing")
+
     def group_search_stats(self) -> dict:
         """Per-device search-kernel durations of the last matchScan + tallies over all devices."""
         ms = np.zeros(16)

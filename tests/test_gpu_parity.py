@@ -82,6 +82,39 @@ def o(oracle, gpu):
 
 
 # ------------------------------------------------------------------ build
+def test_divide_by_point_count_is_the_ieee_divide(o):
+    """The single-CTA build replaces Cell::addPoint's divide by n + 1 (ndt_model.cpp:55-61) with a
+    quotient formed from the count's reciprocal (csrc/build_common.cuh); it has to be the correctly
+    rounded quotient bit for bit -- 2.6e8 pseudo-random (numerator, count) pairs per seed."""
+    for seed in (1, 0xDEADBEEF, 2 ** 61 + 7):
+        bad = np.zeros(1, dtype=np.uint64)
+        L.check(L.lib.ndt2d_probe_div_by_count(0, seed, 1 << 28, L.u64ptr(bad)), "probe_div_by_count")
+        assert int(bad[0]) == 0
+
+
+def test_build_long_cells_small_model(o):
+    """A rolling window whose points pile up in a few cells (hundreds of points per cell): the
+    longest dependency chains of the single-CTA build, cells still bit-identical."""
+    rng = np.random.default_rng(11)
+    n_scans, per = 8, 500
+    poses = np.zeros((n_scans, 3))
+    poses[:, 0] = 0.01 * np.arange(n_scans)
+    poses[:, 2] = 0.002 * np.arange(n_scans)
+    centres = np.array([[2.1, 0.3], [2.4, 0.35], [-1.2, 3.3], [0.4, -2.7]])
+    pts = (centres[rng.integers(0, 4, n_scans * per)] + rng.normal(0, 0.05, (n_scans * per, 2)))
+    offsets = (per * np.arange(n_scans + 1)).astype(np.uint64)
+    prm = synth.config1().params
+    m = ScanMatcherNDT.from_params(prm)
+    mo = o.new_matcher(prm)
+    m.add_scans_raw(poses, offsets, pts)
+    mo.add_scans(poses, offsets, pts)
+    assert m.grid_info() == mo.grid()
+    cells = m.dump_cells()
+    assert cells[:, 1].max() >= 300
+    check_cells(cells, mo.dump_cells())
+    m.close()
+
+
 @pytest.mark.parametrize("cfg", ["config1", "config4"])
 def test_build_parity(o, cfg):
     w = getattr(synth, cfg)()
