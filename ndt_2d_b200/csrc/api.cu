@@ -198,6 +198,7 @@ struct ndt2d_matcher
   BuildScratch bs{};
   DeviceBuffer d_sx, d_sy, d_heads, d_nheads, d_wx, d_wy, d_key0, d_key1, d_val0, d_val1, d_seglen, d_hist, d_scantmp;
   DeviceBuffer d_build_in;           // [thresholds | scan transforms | offsets | map points]
+  DeviceBuffer d_rcp;                // reciprocals of the point counts (BuildScratch::rcp)
   size_t n_map_points = 0;
   int sorted_buf = 0;
 
@@ -464,6 +465,11 @@ int add_scans_impl(
   m->bs.seglen = m->d_seglen.as<uint32_t>();
   m->bs.hist = m->d_hist.as<uint32_t>();
   m->bs.scan_tmp = m->d_scantmp.as<uint32_t>();
+  if (!m->d_rcp.p) {
+    if ((rc = m->d_rcp.ensure((NDT2D_RCP_TABLE + 1) * sizeof(double)))) {return rc;}
+    m->bs.rcp_ready = false;
+  }
+  m->bs.rcp = m->d_rcp.as<double>();
 
   // ---- uploads.  Large model: the points (the bulk of the bytes) go first, straight from the
   // caller's buffer, and the host-side staging below overlaps that copy.  Small model
@@ -998,7 +1004,7 @@ NDT2D_API int ndt2d_matcher_destroy(ndt2d_matcher * m)
     if (m->stream) {cudaStreamSynchronize(m->stream);}
     DeviceBuffer * bufs[] = {&m->d_dth, &m->d_dlin, &m->d_occ, &m->d_occd, &m->d_rec, &m->d_rec_fast, &m->d_rec_vtx, &m->d_nvalid,
       &m->d_sx, &m->d_sy, &m->d_heads, &m->d_nheads, &m->d_wx, &m->d_wy, &m->d_key0, &m->d_key1, &m->d_val0, &m->d_val1, &m->d_seglen,
-      &m->d_hist, &m->d_scantmp, &m->d_build_in, &m->d_pts,
+      &m->d_hist, &m->d_scantmp, &m->d_build_in, &m->d_rcp, &m->d_pts,
       &m->d_trig, &m->d_blockpart, &m->d_partial, &m->d_pose_tf, &m->d_out, &m->d_counter, &m->d_coords, &m->d_chunk, &m->d_batch_results, &m->d_batch_arena};
     for (DeviceBuffer * b : bufs) {b->release();}
     m->h_stage.release();

@@ -456,13 +456,24 @@ __device__ __forceinline__ void write_records(
 // instead of five); 6 cells per warp (lanes 30, 31 idle), warps stride over the head list
 // (its length is only known on the device: the grid is sized for the machine, not for the
 // worst case).  The kernel is issue-bound -- config 5: 51,725 cells of 5..469 points --, so
-// what counts is lanes busy per instruction (profiles/r01_build_kernels_config5.md).
+// what counts is instructions per step and lanes busy per instruction
+// (profiles/r01_build_kernels_config5.md): a lane's term is ONE product a[i] * b[i * stride]
+// -- (x, 1), (y, 1), (x, x), (x, y), (y, y) picked by two lane-invariant pointers, x * 1.0 being
+// exact -- and the divide by the point count is div_by_count with the reciprocal read from a
+// table (rcp[0] = 1.0 doubles as the unit factor; counts beyond the table compute it in line).
 constexpr uint32_t kMomentCellsPerWarp = 6;
+
+__global__ void rcp_table_kernel(double * __restrict__ rcp)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= NDT2D_RCP_TABLE) {rcp[k] = k == 0u ? 1.0 : __drcp_rn(static_cast<double>(k));}
+}
 
 __global__ void __launch_bounds__(256) segment_moments_kernel(
   GridDesc g, const uint32_t * __restrict__ key, const uint2 * __restrict__ heads,
   const uint32_t * __restrict__ n_heads, const double * __restrict__ sx,
-  const double * __restrict__ sy, const uint2 * __restrict__ occ, double * __restrict__ rec,
+  const double * __restrict__ sy, const double * __restrict__ rcp,
+  const uint2 * __restrict__ occ, double * __restrict__ rec,
   double * __restrict__ rec_fast, double * __restrict__ rec_vtx, uint32_t rec_cap,
   uint32_t * __restrict__ n_valid)
 {
@@ -476,6 +487,9 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
   const uint32_t warp = t >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t sub = lane / 5u, r = lane - sub * 5u;      // lanes 30, 31: sub == 6, no cell
   const uint32_t src = (sub < kMomentCellsPerWarp ? sub : kMomentCellsPerWarp - 1u) * 5u;
+  const double * const pa = (r == 1u || r == 4u) ? sy : sx;
+  const double * const pb = r < 2u ? rcp : (r == 2u ? sx : sy);
+  const size_t sb = r < 2u ? 0u : 1u;
   const uint32_t total = *n_heads;
   for (uint32_t first = warp * kMomentCellsPerWarp; first < total;
     first += n_warps * kMomentCellsPerWarp)
@@ -488,30 +502,31 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
     double v = 0.0, n = 0.0;
     if (have) {
       // the loads of four points are issued before the (dependent) recurrence steps
-      // that consume them: the chain is then bound by the divide, not by memory latency
+      // that consume them
+      const double * a = pa + i;
+      const double * b = pb + i * sb;
+      const uint32_t tab = min(len, static_cast<uint32_t>(NDT2D_RCP_TABLE));
       uint32_t j = 0;
-      for (; j + 4 <= len; j += 4) {
-        double x[4], y[4];
+      for (; j + 4 <= tab; j += 4) {
+        double tm[4], q[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          x[u] = sx[i + j + u];
-          y[u] = sy[i + j + u];
+          tm[u] = __dmul_rn(a[j + u], b[(j + u) * sb]);
+          q[u] = rcp[j + u + 1];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const double term = r == 0u ? x[u] : r == 1u ? y[u] : r == 2u ? __dmul_rn(x[u], x[u]) :
-            r == 3u ? __dmul_rn(x[u], y[u]) : __dmul_rn(y[u], y[u]);
           const double n1 = __dadd_rn(n, 1.0);
-          v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+          v = div_by_count(__dadd_rn(__dmul_rn(v, n), tm[u]), n1, q[u]);
           n = n1;
         }
       }
       for (; j < len; ++j) {
-        const double x = sx[i + j], y = sy[i + j];
-        const double term = r == 0u ? x : r == 1u ? y : r == 2u ? __dmul_rn(x, x) :
-          r == 3u ? __dmul_rn(x, y) : __dmul_rn(y, y);
+        const double term = __dmul_rn(a[j], b[j * sb]);
         const double n1 = __dadd_rn(n, 1.0);
-        v = __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
+        const double q = j < NDT2D_RCP_TABLE ? rcp[j + 1] : __drcp_rn(n1);
+        v = n1 <= 1048576.0 ? div_by_count(__dadd_rn(__dmul_rn(v, n), term), n1, q) :
+          __ddiv_rn(__dadd_rn(__dmul_rn(v, n), term), n1);
         n = n1;
       }
     }
@@ -1026,8 +1041,14 @@ int ndt2d_launch_build(
     // one 5-lane group per listed cell, warps stride over the list (at most rec_cap long)
     const uint32_t want = (rec_cap + 8u * kMomentCellsPerWarp - 1u) / (8u * kMomentCellsPerWarp);
     const uint32_t nb = want < 148u * 8u ? (want ? want : 1u) : 148u * 8u;
+    if (!s.rcp_ready) {
+      rcp_table_kernel<<<(NDT2D_RCP_TABLE + 256) / 256, 256, 0, stream>>>(s.rcp);
+      NDT2D_LAUNCH_CHECK(ctr);
+      s.rcp_ready = true;
+    }
     segment_moments_kernel<<<nb, 256, 0, stream>>>(
-      g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, d_occ, d_rec, d_rec_fast, d_rec_vtx, rec_cap, d_n_valid);
+      g, s.key[cur], s.heads, s.n_heads, s.sx, s.sy, s.rcp, d_occ, d_rec, d_rec_fast, d_rec_vtx, rec_cap,
+      d_n_valid);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   *sorted_buf = cur;

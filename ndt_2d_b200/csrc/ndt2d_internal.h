@@ -96,6 +96,7 @@ struct Counters
 };
 
 // ---- build.cu -----------------------------------------------------------
+#define NDT2D_RCP_TABLE 8192
 struct BuildScratch
 {
   // all device pointers, capacities in elements
@@ -108,6 +109,8 @@ struct BuildScratch
   uint32_t * seglen;        // per sorted position: segment length (heads only)
   uint32_t * hist;          // radix histogram [256][n_blocks]
   uint32_t * scan_tmp;      // scratch of the scan kernel
+  double * rcp;             // rcp[0] = 1.0, rcp[k] = RN(1 / k), k <= NDT2D_RCP_TABLE (filled by the first build)
+  bool rcp_ready;
   size_t cap_points, cap_hist;
 };
 

@@ -72,6 +72,7 @@ constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accu
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight
 constexpr double kRoundMagic = 6755399441055744.0;      // 1.5 * 2^52: (x + M) - M == rint(x)
+constexpr uint32_t kCoordsSlices = 16;          // theta slices per thread of the coordinate pre-pass
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
@@ -305,7 +306,10 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
   const uint32_t size = is_x ? mv.g.size_x : mv.g.size_y;
   const double origin = is_x ? mv.g.origin_x : mv.g.origin_y;
   const double d0 = sv.dlin[j0];
-  for (uint32_t it = blockIdx.z; it < n_theta; it += gridDim.z) {
+  // kCoordsSlices consecutive slices per thread (one entry per thread meant 820k blocks of 128
+  // threads at config 4)
+  const uint32_t it_end = min(n_theta, (blockIdx.z + 1u) * kCoordsSlices);
+  for (uint32_t it = blockIdx.z * kCoordsSlices; it < it_end; ++it) {
     const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
     // outer = (p.x*c - p.y*s) + pose.x , (p.x*s + p.y*c) + pose.y   (scan_matcher_ndt.cpp:111-114)
     const double o = is_x ?
@@ -615,7 +619,7 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   // first moves the statistics to [3..4] for ndt2d_matcher_search_stats
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
   if (PRE) {
-    dim3 grid((sv.n_pts + 127u) / 128u, pl.Qx + pl.Qy, min(n_theta, 65535u));
+    dim3 grid((sv.n_pts + 127u) / 128u, pl.Qx + pl.Qy, (n_theta + kCoordsSlices - 1u) / kCoordsSlices);
     region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.RX, pl.RY,
       pl.Qx, pl.Qy, n_pts_pad, d_coords);
     NDT2D_LAUNCH_CHECK(ctr);

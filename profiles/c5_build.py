@@ -1,7 +1,10 @@
 """Profiling helper: the large model build (BASELINE config 5: 20,000 scans, 5.6 M points, 0.1 m cells)."""
 import time
 
-from ndt_2d_b200 import ScanMatcherNDT, synth
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from ndt_2d_b200 import ScanMatcherNDT, synth  # noqa: E402
 
 w = synth.config5()
 m = ScanMatcherNDT.from_params(w.params)
