@@ -292,13 +292,23 @@ def other_workloads(torch, dev_index: int):
             t0 = time.perf_counter()
             m.match_scan_raw(w.query_pose, w.query_points)
             lat.append((time.perf_counter() - t0) * 1e3)
+        c_abi = {}
+        for name, ms in (("matchScan", None),
+                         ("reset_addScans_scoreScan_matchScan", (w.map_poses, w.map_offsets, w.map_points))):
+            m.probe_call_latency(w.query_pose, w.query_points, 50, ms)
+            us = m.probe_call_latency(w.query_pose, w.query_points, 500, ms)
+            c_abi[name + "_us_p50"] = float(np.percentile(us, 50))
+            c_abi[name + "_us_p99"] = float(np.percentile(us, 99))
         na, nl = m.search_shape()
         out[f"config1_local_match_beams{beams}"] = {
             "candidates": na * nl * nl, "matchScan_ms": t_match * 1e3,
             "matchScan_latency_ms_p50": float(np.percentile(lat, 50)),
             "matchScan_latency_ms_p99": float(np.percentile(lat, 99)), "latency_calls": len(lat),
             "reset_addScans_scoreScan_matchScan_ms": t_triple * 1e3,
-            "candidates_per_s": na * nl * nl / t_match}
+            "candidates_per_s": na * nl * nl / t_match,
+            # the same calls timed inside the library (ndt2d_probe_call_latency): what a C / C++
+            # caller such as the node sees, without the ctypes / numpy cost of this harness
+            "c_abi": c_abi}
         m.close()
     # config 2: particle filter measure + resample
     w = synth.config2()
@@ -347,6 +357,24 @@ def other_workloads(torch, dev_index: int):
         "grid": [meta["width"], meta["height"]], "getMsg_ms": t_og * 1e3,
         "getMsg_without_d2h_of_the_grid_ms": t_og_dev * 1e3, "rays_per_s": w.map_points.shape[0] / t_og}
     og.close()
+    # the floor of the search kernel: config 4's lattice in a cluttered short-range world
+    # (a third of the (candidate, point) pairs are useful instead of 3.4 %)
+    w = synth.config4_dense()
+    m = ScanMatcherNDT.from_params(w.params, device=dev_index)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    t_dense = timed(lambda: m.match_scan_raw(w.query_pose, w.query_points), reps=3, warm=1)
+    st = m.search_stats()
+    na, nl = m.search_shape()
+    n_use = min(int(w.params["laser_max_beams"]), int(w.query_points.shape[0]))
+    out["config4_dense_clutter_floor"] = {
+        "what": "config 4's 3142 x 400 x 400 lattice, 10,000 small obstacles, range_max 5 m, 0.5 m cells",
+        "candidates": na * nl * nl, "beams_used": n_use, "matchScan_ms": t_dense * 1e3,
+        "candidates_per_s": na * nl * nl / t_dense,
+        "useful_evaluations": st["useful_evaluations"],
+        "useful_fraction_of_pairs": st["useful_evaluations"] / (na * nl * nl * n_use),
+        "useful_evaluations_per_s": st["useful_evaluations"] / (st["kernel_ms"] * 1e-3) if st["kernel_ms"] else None,
+        "kernel_ms": st["kernel_ms"]}
+    m.close()
     # config 3: loop-closure batch
     w = synth.config3()
     m = ScanMatcherNDT.from_params(w.params, device=dev_index)

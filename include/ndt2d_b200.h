@@ -165,13 +165,16 @@ NDT2D_API int ndt2d_matcher_match_scan_batch(
  * scans [i-1 (i if i == 0), i+1 if i < rolling else i) (:628-635); a finite score below
  * typical_response (:645) is accepted and moves the query scan's pose by the correction
  * (:652-655) BEFORE the next candidate is matched; at most search_limit candidates are
- * processed (:671).  Internally all remaining candidates are matched speculatively in one
+ * processed (:671) -- search_limit == 0 means NO limit, as in the reference, whose size_t
+ * countdown `--num_scans_to_check == 0` wraps.  A candidate whose window is empty (i == 0 with
+ * rolling == 0) has no map: it scores 0.0, like matchScan without a model
+ * (scan_matcher_ndt.cpp:80), is not accepted and counts as processed.  Internally all remaining candidates are matched speculatively in one
  * batch and the remainder is re-issued after every acceptance, so the outputs equal the
  * sequential loop's.
  *   scan_poses / scan_pt_offsets / scan_pts_xy : the graph's scans (n_scans)
  *   query_pose3   in: pose of the new scan; out: its pose after all accepted corrections
  *   out_*         one entry per processed candidate (room for min(search_limit,
- *                 n_candidates)): candidate index, score, accepted flag, scan pose after
+ *                 n_candidates), n_candidates if search_limit == 0): candidate index, score, accepted flag, scan pose after
  *                 this candidate, covariance of the match
  *   *n_batches    number of batch submissions it took (1 + number of acceptances that
  *                 were not the last processed candidate) */

@@ -1472,9 +1472,11 @@ NDT2D_API int ndt2d_matcher_close_loop(
   std::lock_guard<std::mutex> lock(m->mu);
   DeviceGuard guard(m->device);
   // candidates the reference would look at, in order: empty scans are skipped without
-  // counting (:625), at most search_limit are processed (:671)
+  // counting (:625), at most search_limit are processed (:671) -- the reference counts down
+  // `--num_scans_to_check == 0` on a size_t, so a limit of 0 wraps and means "no limit"
+  const size_t limit = search_limit == 0 ? std::numeric_limits<size_t>::max() : search_limit;
   std::vector<uint64_t> todo;
-  for (size_t k = 0; k < n_candidates && todo.size() < search_limit; ++k) {
+  for (size_t k = 0; k < n_candidates && todo.size() < limit; ++k) {
     const uint64_t i = candidates[k];
     if (i >= n_scans) {return NDT2D_ERR_INVALID;}
     if (scan_pt_offsets[i + 1] == scan_pt_offsets[i]) {continue;}
@@ -1484,17 +1486,25 @@ NDT2D_API int ndt2d_matcher_close_loop(
   std::vector<uint64_t> job_offsets, q_offsets;
   std::vector<double> q_poses, delta, cov, score;
   std::vector<int> written;
+  std::vector<size_t> slot_of;   // candidate of the round -> job of the batch (npos: empty window)
+  constexpr size_t npos = std::numeric_limits<size_t>::max();
   while (next < todo.size()) {
-    const size_t n_jobs = todo.size() - next;
+    const size_t n_round = todo.size() - next;
     // job j: window [i-1 (or i), i+1 if i < rolling else i) of the graph's scans (:628-631);
-    // the windows are contiguous scan ranges, so they index the caller's arrays directly
+    // the windows are contiguous scan ranges, so they index the caller's arrays directly.  A
+    // candidate whose window is empty (i == 0 with rolling == 0) has no map: it scores 0.0 like
+    // matchScan without a model (scan_matcher_ndt.cpp:80) and is never accepted -- the batch
+    // goes on (the reference itself would size an NDT from an empty bounding box there).
     job_offsets.assign(1, 0);
+    slot_of.assign(n_round, npos);
     std::vector<double> w_poses;
     std::vector<uint64_t> w_offsets(1, 0);
     std::vector<double> w_points;
-    for (size_t j = 0; j < n_jobs; ++j) {
+    size_t n_jobs = 0;
+    for (size_t j = 0; j < n_round; ++j) {
       const uint64_t i = todo[next + j];
       const uint64_t begin = i > 0 ? i - 1 : i, end = i < rolling ? i + 1 : i;
+      if (end <= begin) {continue;}
       for (uint64_t s = begin; s < end; ++s) {
         w_poses.insert(w_poses.end(), scan_poses + 3 * s, scan_poses + 3 * s + 3);
         w_points.insert(w_points.end(), scan_pts_xy + 2 * scan_pt_offsets[s],
@@ -1502,6 +1512,7 @@ NDT2D_API int ndt2d_matcher_close_loop(
         w_offsets.push_back(w_points.size() / 2);
       }
       job_offsets.push_back(w_poses.size() / 3);
+      slot_of[j] = n_jobs++;
     }
     q_poses.resize(3 * n_jobs);
     q_offsets.resize(n_jobs + 1);
@@ -1518,15 +1529,27 @@ NDT2D_API int ndt2d_matcher_close_loop(
     cov.assign(9 * n_jobs, 0.0);
     score.assign(n_jobs, 0.0);
     written.assign(n_jobs, 0);
-    const int rc = match_scan_batch_locked(m, n_jobs, job_offsets.data(), w_poses.data(),
-        w_offsets.data(), w_points.data(), q_poses.data(), q_offsets.data(), q_points.data(),
-        delta.data(), written.data(), cov.data(), score.data());
-    if (rc) {return rc;}
-    if (n_batches) {*n_batches += 1;}
+    if (n_jobs) {
+      const int rc = match_scan_batch_locked(m, n_jobs, job_offsets.data(), w_poses.data(),
+          w_offsets.data(), w_points.data(), q_poses.data(), q_offsets.data(), q_points.data(),
+          delta.data(), written.data(), cov.data(), score.data());
+      if (rc) {return rc;}
+      if (n_batches) {*n_batches += 1;}
+    }
     // consume in order up to the first acceptance
-    size_t j = 0;
-    for (; j < n_jobs; ++j) {
+    size_t jr = 0;
+    for (; jr < n_round; ++jr) {
       const size_t o = *n_processed;
+      const size_t j = slot_of[jr];
+      if (j == npos) {
+        if (out_candidate) {out_candidate[o] = todo[next + jr];}
+        if (out_score) {out_score[o] = 0.0;}
+        if (out_accepted) {out_accepted[o] = 0;}
+        if (out_pose3) {memcpy(out_pose3 + 3 * o, query_pose3, 3 * sizeof(double));}
+        if (out_cov9) {memset(out_cov9 + 9 * o, 0, 9 * sizeof(double));}
+        *n_processed = o + 1;
+        continue;
+      }
       const bool accept = std::isfinite(score[j]) && score[j] < typical_response;  // :645
       if (accept) {
         // correction += scan pose; scan->setPose(correction)  (:652-655); an unwritten
@@ -1535,18 +1558,18 @@ NDT2D_API int ndt2d_matcher_close_loop(
         query_pose3[1] = (written[j] ? delta[3 * j + 1] : 0.0) + query_pose3[1];
         query_pose3[2] = (written[j] ? delta[3 * j + 2] : 0.0) + query_pose3[2];
       }
-      if (out_candidate) {out_candidate[o] = todo[next + j];}
+      if (out_candidate) {out_candidate[o] = todo[next + jr];}
       if (out_score) {out_score[o] = score[j];}
       if (out_accepted) {out_accepted[o] = accept ? 1 : 0;}
       if (out_pose3) {memcpy(out_pose3 + 3 * o, query_pose3, 3 * sizeof(double));}
       if (out_cov9) {memcpy(out_cov9 + 9 * o, &cov[9 * j], 9 * sizeof(double));}
       *n_processed = o + 1;
       if (accept) {
-        ++j;
+        ++jr;
         break;
       }
     }
-    next += j;
+    next += jr;
   }
   return NDT2D_OK;
 }

@@ -241,7 +241,8 @@ std::vector<ScanMatcherNDT::LoopClosure> ScanMatcherNDT::closeLoop(
   const ndt_2d::Pose2d pose0 = scan->getPose();
   double query_pose[3] = {pose0.x, pose0.y, pose0.theta};
   const std::vector<ndt_2d::Point> points = scan->getPoints();
-  const size_t cap = std::max<size_t>(1, std::min(search_limit, cand.size()));
+  // (a limit of 0 means no limit: the reference's size_t countdown wraps, ndt_mapper.cpp:619,671)
+  const size_t cap = std::max<size_t>(1, search_limit ? std::min(search_limit, cand.size()) : cand.size());
   std::vector<uint64_t> out_cand(cap);
   std::vector<double> out_score(cap), out_pose(3 * cap), out_cov(9 * cap);
   std::vector<int> out_acc(cap);

@@ -332,7 +332,8 @@ class ScanMatcherNDT:
         cand = np.ascontiguousarray(candidates, dtype=np.uint64)
         qp = _pose3(query_pose).copy()
         qpts = L.f64(query_points).reshape(-1, 2)
-        cap = max(1, min(int(search_limit), cand.shape[0]))
+        # (a limit of 0 means no limit: the reference's size_t countdown wraps, ndt_mapper.cpp:619,671)
+        cap = max(1, min(int(search_limit), cand.shape[0]) if int(search_limit) > 0 else cand.shape[0])
         oc = np.zeros(cap, dtype=np.uint64)
         osc, oacc = np.zeros(cap), np.zeros(cap, dtype=np.int32)
         opose, ocov = np.zeros((cap, 3)), np.zeros((cap, 3, 3))

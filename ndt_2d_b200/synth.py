@@ -174,6 +174,28 @@ def config4(scale: float = 1.0) -> MatchWorkload:
                          pts[: int(offs[10])].copy(), guess, pts[q0:q1].copy(), true_pose)
 
 
+def config4_dense(scale: float = 1.0) -> MatchWorkload:
+    """The large search of config4 in a CLUTTERED, short-range setting: 10,000 small obstacles in
+    the arena, range_max 5 m, 0.5 m NDT cells.  About 36 % of the (candidate, scan point) pairs land
+    in an occupied cell (config4: 3.4 %), so the search kernel's sparsity shortcuts buy little here:
+    the floor of the design's candidates/s (bench.py other_workloads)."""
+    rects = world(seed=7, n_obstacles=10000, side_min=0.2, side_max=0.8)
+    x0, y0 = free_start(rects, margin=0.3)
+    poses = np.zeros((11, 3))
+    poses[:, 0] = x0 + 0.2 * np.arange(11)
+    poses[:, 1] = y0
+    poses[:, 2] = -0.05 + 0.1 * uniform(11, 11)
+    offs, pts = scans(rects, poses, 1080, 5.0, seed=143)
+    true_pose = poses[10].copy()
+    guess = true_pose - np.array([0.5, -0.3, 0.4])
+    params = dict(ndt_resolution=0.5, search_angular_resolution=0.002,
+                  search_angular_size=math.pi * scale, search_linear_resolution=0.01,
+                  search_linear_size=2.0 * scale, laser_max_beams=1080, range_max=5.0)
+    q0, q1 = int(offs[10]), int(offs[11])
+    return MatchWorkload("config4_dense_clutter", params, poses[:10].copy(), offs[:11].copy(),
+                         pts[: int(offs[10])].copy(), guess, pts[q0:q1].copy(), true_pose)
+
+
 @dataclass
 class FilterWorkload:
     name: str

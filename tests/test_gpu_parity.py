@@ -275,6 +275,24 @@ def test_match_scan_config4_reduced(o):
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
+def test_match_scan_dense_clutter_reduced(o):
+    """The cluttered short-range world of bench.py's floor workload (a third of the (candidate,
+    point) pairs in occupied 0.5 m cells), on a window the oracle finishes in seconds: full score
+    volume, pose and covariance."""
+    w = synth.config4_dense(scale=0.04)
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    mo = o.new_matcher(w.params)
+    mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+    assert m.grid_info() == mo.grid()
+    check_cells(m.dump_cells(), mo.dump_cells())
+    for guess in (w.true_pose - np.array([0.05, -0.03, 0.06]), w.true_pose + np.array([0.9, 0.4, 2.0])):
+        so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+        sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+        check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
+    m.close()
+
+
 SWEEP = [
     # ndt_res, ang_res, ang_size, lin_res, lin_size, beams   -- what it exercises
     (0.05, 0.01, 0.03, 0.05, 0.25, 360),     # step == cell: one-candidate regions
@@ -550,6 +568,24 @@ def test_match_scan_batch_other_kernel_paths(o):
     _batch_against_oracle(o, w.params, [(poses17, offs17, pts17, g, w.query_points) for g in guesses[:2]])
 
 
+def test_close_loop_empty_window_is_skipped_per_candidate(o):
+    """rolling == 0 makes candidate 0's window empty (ndt_mapper.cpp:628-631): it scores 0.0 like a
+    matcher without a map and is not accepted; the other candidates are matched as usual."""
+    w = synth.config1()
+    poses, offs, pts = w.map_poses, w.map_offsets.astype(np.int64), w.map_points
+    m = ScanMatcherNDT.from_params(w.params)
+    mo = o.new_matcher(w.params)
+    qp, got, _ = m.close_loop(poses, offs.astype(np.uint64), pts, np.array([0, 3], dtype=np.uint64), 0, 0,
+                              -10.0, w.query_pose, w.query_points)
+    assert [g["candidate"] for g in got] == [0, 3]
+    assert got[0]["score"] == 0.0 and not got[0]["accepted"]
+    oo = offs[2:4]
+    mo.add_scans(poses[2:3], oo - oo[0], pts[int(oo[0]):int(oo[1])])                # window [2, 3)
+    s, *_ = mo.match_scan(w.query_pose, w.query_points)
+    np.testing.assert_allclose(got[1]["score"], s, rtol=RTOL, atol=ATOL_SCORE)
+    m.close()
+
+
 def _sequential_loop_closure(mo, poses, offs, pts, candidates, rolling, limit, typical, qpose, qpts):
     """The reference's inner loop (ndt_mapper.cpp:619-671) with the oracle matcher, one
     candidate at a time."""
@@ -574,7 +610,7 @@ def _sequential_loop_closure(mo, poses, offs, pts, candidates, rolling, limit, t
     return qpose, out
 
 
-@pytest.mark.parametrize("typical,limit", [(-0.05, 5), (-0.3, 6), (-10.0, 3), (0.5, 4)])
+@pytest.mark.parametrize("typical,limit", [(-0.05, 5), (-0.3, 6), (-10.0, 3), (0.5, 4), (-10.0, 0)])
 def test_close_loop_matches_sequential_reference_loop(o, typical, limit):
     """Speculative batches + exact re-issue after an acceptance == the sequential loop."""
     w = synth.config1()
