@@ -26,6 +26,7 @@ CXX_SOURCES = []
 SYNTH_SRC = PKG / "synth_src" / "synth.cpp"
 SYNTH_LIB = LIBDIR / "libndt2d_synth.so"
 HEADERS = [CSRC / "ndt2d_internal.h", CSRC / "search_common.cuh", CSRC / "search_region_body.inc",
+           CSRC / "build_common.cuh",
            ROOT / "include" / "ndt2d_b200.h"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

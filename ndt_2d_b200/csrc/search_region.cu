@@ -72,7 +72,7 @@ constexpr uint32_t kFlushSteps = 4;             // 32-point steps per float accu
 constexpr uint32_t kTargetJobs = 148 * 16;      // shrink regions of small searches
 constexpr uint32_t kChunkTargetWork = 148 * kWarps * 3;  // (job, point chunk) pairs wanted in flight
 constexpr double kRoundMagic = 6755399441055744.0;      // 1.5 * 2^52: (x + M) - M == rint(x)
-constexpr uint32_t kCoordsSlices = 16;          // theta slices per thread of the coordinate pre-pass
+constexpr uint32_t kCoordsSlices = 1;           // theta slices per thread of the coordinate pre-pass
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
@@ -156,9 +156,21 @@ __device__ __forceinline__ uint32_t padded_coord(
 // likelihoods to their accumulators (JPREV) and then starts its own pair, so the SFU latency
 // of a pair overlaps the arithmetic of the next one (every block is a jump target, the
 // scheduler cannot move code across them by itself).
+#ifdef NDT2D_COUNT_ZERO_PAIRS   // experiment: how many executed pairs are zero on every lane
+#define NDT2D_ZERO_TALLY(e) \
+  { \
+    dbg_pairs += 1u; \
+    const bool z = __all_sync(0xffffffffu, e.x < -126.0f && e.y < -126.0f); \
+    dbg_zero += z ? 1u : 0u; \
+    dbg_phase_nz |= z ? 0u : 1u; \
+  }
+#else
+#define NDT2D_ZERO_TALLY(e)
+#endif
 #define NDT2D_PAIR_FIRST(EE) \
   { \
     const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
+    NDT2D_ZERO_TALLY(e) \
     prev = make_float2(ex2_ftz(e.x), ex2_ftz(e.y)); \
     bp = __fadd2_rn(bp, stepp); \
   }
@@ -166,17 +178,30 @@ __device__ __forceinline__ uint32_t padded_coord(
   { \
     acc2[JPREV] = __fadd2_rn(acc2[JPREV], prev); \
     const float2 e = __ffma2_rn(__ffma2_rn(c2p, bp, d1p), bp, EE); \
+    NDT2D_ZERO_TALLY(e) \
     prev = make_float2(ex2_ftz(e.x), ex2_ftz(e.y)); \
     bp = __fadd2_rn(bp, stepp); \
   }
 #define NDT2D_PAIR_LAST(JPREV) {acc2[JPREV] = __fadd2_rn(acc2[JPREV], prev);}
 
-// Number of k in [0, n) with o + dl[k] < thr, for increasing dl (the replayed lattice): a
-// guess from the nominal step, fixed up with the reference's own additions (exact).
+// Number of k in [0, n) with o + dl[k] < thr, for the replayed lattice dl[k] ~ dl[0] + k h.
+// g = (thr - (o + dl[0])) / h counts the steps below the threshold.  The accumulated lattice and
+// the roundings of o + dl[k] deviate from the nominal positions dl[0] + k h by at most
+// n ulp(|o| + |dl|) / h steps -- below 4e-8 for n <= 16384 positions whose coordinates stay under
+// 1e7 steps -- so whenever g is farther than 1e-6 from an integer the count is floor(g) + 1 with
+// no further work.  Everything else (near-integer g, huge lattices or coordinates, NaN / inf)
+// is decided by the reference's own additions, exact either way.
 __device__ __forceinline__ uint32_t count_below(
   double o, const double * __restrict__ dl, uint32_t n, double thr, double inv_h)
 {
-  const double g = (thr - __dadd_rn(o, __ldg(dl))) * inv_h;
+  const double dl0 = __ldg(dl);
+  const double g = (thr - __dadd_rn(o, dl0)) * inv_h;
+  const double gf = floor(g);
+  const double fr = g - gf;
+  if (fr > 1.0e-6 && fr < 1.0 - 1.0e-6 && n <= 16384u && (fabs(o) + fabs(dl0)) * inv_h < 1.0e7) {
+    if (g <= 0.0) {return 0u;}
+    return g >= static_cast<double>(n) ? n : static_cast<uint32_t>(gf) + 1u;
+  }
   uint32_t k = g >= static_cast<double>(n) ? n : (g > 0.0 ? static_cast<uint32_t>(g) + 1u : 0u);
   k = min(k, n);
   while (k > 0u && !(__dadd_rn(o, __ldg(dl + k - 1u)) < thr)) {--k;}
@@ -292,22 +317,23 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t n_theta, uint32_t RX, uint32_t RY,
   uint32_t Qx, uint32_t Qy, uint32_t n_pts_pad, uint32_t * __restrict__ coords)
 {
-  // one thread per table entry: x = scan point, y = region column / row q, z = theta slice
+  // one thread per (scan point, axis, theta slice): it walks the axis' Q regions in order.  All
+  // entries of the row follow from K(c) = #{k < n_lin : o + dlin[k] < thr[c]} for the ~n_lin h /
+  // cell thresholds c the lattice crosses (each found exactly, with the reference's additions):
+  // lattice position j lies in padded cell #{c : K(c) <= j}, and a region starting at j0 in
+  // cell c has min(n, K(c) - j0) positions left of the next threshold -- about half the
+  // searches of doing every region on its own.
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t q = blockIdx.y;
   if (i >= sv.n_pts) {return;}
+  const bool is_x = blockIdx.y == 0u;
   const double2 p = sv.pts[i];
   const double inv_cell = 1.0 / mv.g.cell_size, inv_h = sv.inv_linear_res;
   const uint32_t n_lin = sv.n_lin;
-  const bool is_x = q < Qx;
-  const uint32_t qq = is_x ? q : q - Qx, R = is_x ? RX : RY;
-  const uint32_t j0 = qq * R, n = min(R, n_lin - j0);
+  const uint32_t R = is_x ? RX : RY, Q = is_x ? Qx : Qy, q_base = is_x ? 0u : Qx;
   const double * __restrict__ thr = is_x ? mv.thr_x : mv.thr_y;
   const uint32_t size = is_x ? mv.g.size_x : mv.g.size_y;
   const double origin = is_x ? mv.g.origin_x : mv.g.origin_y;
-  const double d0 = sv.dlin[j0];
-  // kCoordsSlices consecutive slices per thread (one entry per thread meant 820k blocks of 128
-  // threads at config 4)
+  const double d0 = sv.dlin[0];
   const uint32_t it_end = min(n_theta, (blockIdx.z + 1u) * kCoordsSlices);
   for (uint32_t it = blockIdx.z * kCoordsSlices; it < it_end; ++it) {
     const double2 cs = sv.trig[theta_begin + it * sv.theta_stride];
@@ -315,15 +341,21 @@ __global__ void __launch_bounds__(128) region_coords_kernel(
     const double o = is_x ?
       __dadd_rn(__dsub_rn(__dmul_rn(p.x, cs.x), __dmul_rn(p.y, cs.y)), sv.pose_x) :
       __dadd_rn(__dadd_rn(__dmul_rn(p.x, cs.y), __dmul_rn(p.y, cs.x)), sv.pose_y);
-    const uint32_t pc = padded_coord<false>(__dadd_rn(o, d0), thr, size, origin, inv_cell);
-    const uint32_t k1 = count_below(o, sv.dlin + j0, n, thr[pc], inv_h);
-    uint32_t e = pc | (k1 << 16);
-    if (is_x) {
-      const uint32_t k2 = k1 == n ? n :
-        count_below(o, sv.dlin + j0, n, thr[min(pc + 1u, size + 1u)], inv_h);
-      e |= k2 << 22;
+    uint32_t c = padded_coord<false>(__dadd_rn(o, d0), thr, size, origin, inv_cell);   // cell of position 0
+    uint32_t Kc = count_below(o, sv.dlin, n_lin, thr[c], inv_h);                        // > 0
+    uint32_t Kn = Kc >= n_lin ? n_lin : count_below(o, sv.dlin, n_lin, thr[min(c + 1u, size + 1u)], inv_h);
+    uint32_t * out = coords + (static_cast<size_t>(it) * (Qx + Qy) + q_base) * n_pts_pad + i;
+    for (uint32_t q = 0; q < Q; ++q) {
+      const uint32_t j0 = q * R, n = min(R, n_lin - j0);
+      while (Kc <= j0) {   // the region starts beyond threshold c: next cell (thr[size + 1] = +inf ends it)
+        ++c;
+        Kc = Kn;
+        Kn = Kc >= n_lin ? n_lin : count_below(o, sv.dlin, n_lin, thr[min(c + 1u, size + 1u)], inv_h);
+      }
+      uint32_t e = c | (min(n, Kc - j0) << 16);
+      if (is_x) {e |= min(n, Kn - j0) << 22;}
+      out[static_cast<size_t>(q) * n_pts_pad] = e;
     }
-    coords[(static_cast<size_t>(it) * (Qx + Qy) + q) * n_pts_pad + i] = e;
   }
 }
 
@@ -619,7 +651,7 @@ int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   // first moves the statistics to [3..4] for ndt2d_matcher_search_stats
   const uint32_t n_pts_pad = (sv.n_pts + 31u) & ~31u;
   if (PRE) {
-    dim3 grid((sv.n_pts + 127u) / 128u, pl.Qx + pl.Qy, (n_theta + kCoordsSlices - 1u) / kCoordsSlices);
+    dim3 grid((sv.n_pts + 127u) / 128u, 2u, (n_theta + kCoordsSlices - 1u) / kCoordsSlices);
     region_coords_kernel<<<grid, 128, 0, stream>>>(mv, sv, theta_begin, n_theta, pl.RX, pl.RY,
       pl.Qx, pl.Qy, n_pts_pad, d_coords);
     NDT2D_LAUNCH_CHECK(ctr);
