@@ -52,15 +52,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU DURING the timed region.
+
+    Read through NVML in this process (the library nvidia-smi itself is a front end of; same
+    fields as the profiling recipe's `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,
+    clocks_event_reasons.*` line) by a thread polling every few milliseconds: starting an
+    nvidia-smi process right before a 13 ms timed region (5 steps on 8 GPUs) puts its NVML
+    start-up, which touches every GPU of the box, inside the region and skews the ranks.
+    Falls back to the nvidia-smi subprocess when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    _nvml = None
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.handle, self.samples, self.stop_flag, self.thread = None, [], False, None
+        try:
+            if ClockSampler._nvml is None:
+                import pynvml
+                pynvml.nvmlInit()
+                ClockSampler._nvml = pynvml
+            nv = ClockSampler._nvml
+            # CUDA_VISIBLE_DEVICES remaps CUDA ordinals; NVML sees the physical indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.handle = None
+
+    def _poll(self):
+        nv = ClockSampler._nvml
+        period = float(os.environ.get("NDT2D_BENCH_SAMPLER_MS", "4")) * 1e-3
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(period)
 
     def start(self):
+        if self.handle is not None:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -75,6 +121,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.handle is not None:
+            self.stop_flag = True
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            nv = ClockSampler._nvml
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(name for name, bit in bits.items() if any(mask & bit for _, mask in self.samples))
+            sm = [mhz for mhz, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml (in-process, every 4 ms)"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,7 +158,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -429,6 +488,8 @@ def run_ours(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
+    # (NVML is initialised here, long before the timed region: its start-up touches every GPU)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     w = synth.config4(scale=args.scale)
     # a dedicated (non-default) stream shared by torch (events, NCCL) and the library
     stream = torch.cuda.Stream(device=dev)
@@ -444,6 +505,10 @@ def run_ours(args):
     my_candidates = ss.n_theta * nl * nl
     gathered = ss.gathered
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def l2_flush():
+        """Replace the whole L2 (126 MB) between steps: a 256 MiB memset."""
+        flush.zero_()
 
     def barrier():
         if dist is not None:
@@ -466,14 +531,13 @@ def run_ours(args):
         device_step()
     barrier()
     c0 = m.counters()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     evs = []
     kernel_ms_steps = []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        flush.zero_()                       # L2 flush, outside the per-step event pair
+        l2_flush()                          # outside the per-step event pair
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         device_step()
@@ -659,6 +723,7 @@ def run_single_process(args, torch):
     matchScan call with host buffers, so `value` and `e2e` are the same measurement here."""
     from ndt_2d_b200 import ScanMatcherNDT, synth
     n = args.gpus
+    sampler = ClockSampler(0)
     w = synth.config4(scale=args.scale)
     m = ScanMatcherNDT.from_params(w.params, devices=list(range(n)), kernel_variant=args.variant)
     m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
@@ -667,7 +732,6 @@ def run_single_process(args, torch):
     flush = [torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n)]
     for _ in range(max(args.warmup, 1)):
         r = m.match_scan_raw(w.query_pose, w.query_points)
-    sampler = ClockSampler(0)
     sampler.start()
     c0 = m.counters()
     times, kms = [], []

@@ -438,7 +438,7 @@ int add_scans_impl(
   if ((rc = m->d_val1.ensure(np1 * sizeof(uint32_t)))) {return rc;}
   if ((rc = m->d_seglen.ensure(np1 * sizeof(uint32_t)))) {return rc;}
   const size_t sort_blocks = (np1 + 4095) / 4096;
-  if ((rc = m->d_hist.ensure(sort_blocks * 256 * sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_hist.ensure(ndt2d_sort_scratch_bytes(np1)))) {return rc;}
   const size_t scan_n = std::max<size_t>(sort_blocks * 256, g.n_words);
   if ((rc = m->d_scantmp.ensure(((scan_n + 8191) / 8192 + 1) * sizeof(uint32_t)))) {return rc;}
   // +4 words of slack: the search kernel's bulk copies round sizes up to 16 bytes

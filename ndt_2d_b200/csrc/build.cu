@@ -54,12 +54,27 @@ __device__ __forceinline__ uint32_t cell_key(const GridDesc & g, double x, doubl
   return gy * g.size_x + gx;
 }
 
-// NDT::addScan (ndt_model.cpp:132-152): p = pose; p += R(theta) * point.
+// Digits of the radix sort: `passes` digits of `width` <= 8 bits cover bits_needed(n_cells).
+struct DigitPlan
+{
+  int passes, width;
+  uint32_t mask;
+};
+constexpr int kMaxPasses = 4;
+
+// NDT::addScan (ndt_model.cpp:132-152): p = pose; p += R(theta) * point.  The block also
+// histograms every digit of its keys (shared-memory counters, flushed to the global
+// histograms at the end): the one-sweep sort below needs the digit totals of all passes up
+// front and the keys are in registers here anyway.
 __global__ void __launch_bounds__(128) transform_key_kernel(
   GridDesc g, const double4 * __restrict__ scan_tf, const uint64_t * __restrict__ offsets,
   uint32_t n_scans, const double2 * __restrict__ pts, double * __restrict__ wx,
-  double * __restrict__ wy, uint32_t * __restrict__ key, uint32_t * __restrict__ val)
+  double * __restrict__ wy, uint32_t * __restrict__ key, uint32_t * __restrict__ val,
+  DigitPlan dp, uint32_t * __restrict__ ghist)
 {
+  __shared__ uint32_t h[kMaxPasses][256];
+  for (uint32_t k = threadIdx.x; k < kMaxPasses * 256; k += blockDim.x) {(&h[0][0])[k] = 0u;}
+  __syncthreads();
   for (uint32_t s = blockIdx.x; s < n_scans; s += gridDim.x) {
     const double4 tf = scan_tf[s];  // x, y, cos, sin
     const uint64_t lo = offsets[s], hi = offsets[s + 1];
@@ -71,9 +86,19 @@ __global__ void __launch_bounds__(128) transform_key_kernel(
         __dadd_rn(tf.y, __dadd_rn(__dmul_rn(pt.x, tf.w), __dmul_rn(pt.y, tf.z)));
       wx[p] = X;
       wy[p] = Y;
-      key[p] = cell_key(g, X, Y);
+      const uint32_t k = cell_key(g, X, Y);
+      key[p] = k;
       val[p] = static_cast<uint32_t>(p);
+#pragma unroll
+      for (int q = 0; q < kMaxPasses; ++q) {
+        if (q < dp.passes) {atomicAdd(&h[q][(k >> (q * dp.width)) & dp.mask], 1u);}
+      }
     }
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < static_cast<uint32_t>(dp.passes) * 256u; k += blockDim.x) {
+    const uint32_t c = (&h[0][0])[k];
+    if (c) {atomicAdd(ghist + k, c);}
   }
 }
 
@@ -212,82 +237,157 @@ int launch_scan(void * d_data, size_t n, uint32_t * d_tmp, cudaStream_t stream, 
 }
 
 // ------------------------------------------------------------------ K2
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(
-  const uint32_t * __restrict__ keys, size_t n, int shift, uint32_t * __restrict__ hist,
-  uint32_t nblk)
-{
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const size_t tile = static_cast<size_t>(blockIdx.x) * kSortTile;
-#pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    const size_t i = tile + static_cast<size_t>(k) * kSortThreads + threadIdx.x;
-    if (i < n) {
-      atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
-    }
-  }
-  __syncthreads();
-  hist[static_cast<size_t>(threadIdx.x) * nblk + blockIdx.x] = h[threadIdx.x];
-}
+// One-sweep LSD radix sort (Adinets & Merrill's "onesweep" scheme), stable: per digit ONE
+// kernel reads the (key, value) pairs once and writes them once.
+//   * the digit totals of every pass come from transform_key_kernel (ghist), so a block knows
+//     where each digit's output range starts after a 256-entry scan of its own;
+//   * a block takes its tile from a ticket counter (tiles are processed in ticket order, so a
+//     block only ever waits for blocks that started before it), ranks its 4096 pairs stably
+//     (warp w owns 512 consecutive pairs and walks them in order: __match_any_sync + running
+//     per-warp digit counters), publishes its per-digit counts in status[tile][digit] and adds
+//     up its predecessors' by decoupled look-back (thread d follows digit d: a word is
+//     `flag << 30 | count`, flag 1 = this tile's count alone, 2 = inclusive prefix up to this
+//     tile) -- no histogram / scan launches between the passes;
+//   * the tile is first permuted into digit order in shared memory, then written out: the runs
+//     of one digit are contiguous in the output, so consecutive threads store to consecutive
+//     addresses.
+constexpr uint32_t kOsFlagAgg = 1u << 30, kOsFlagInc = 2u << 30, kOsCount = (1u << 30) - 1u;
 
-// Stable scatter.  Warp w owns the contiguous sub-tile
-// [tile + w*32*ITEMS, tile + (w+1)*32*ITEMS) and walks it in element order,
-// so (block, warp, step, lane) order == input order.
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
-  const uint32_t * __restrict__ keys_in, const uint32_t * __restrict__ vals_in, size_t n,
-  int shift, const uint32_t * __restrict__ hist_scanned, uint32_t nblk,
-  uint32_t * __restrict__ keys_out, uint32_t * __restrict__ vals_out)
+struct OnesweepSmem
 {
-  __shared__ uint32_t cnt[kSortWarps][256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) {
-    (&cnt[0][0])[i] = 0;
-  }
-  __syncthreads();
+  uint32_t cnt[kSortWarps][256];   // per-warp digit counters -> per-warp exclusive offsets
+  uint32_t toff[256];              // start of digit d's run in the sorted tile
+  uint32_t gbase[256];             // global position of tile-sorted index j of digit d: gbase[d] + j
+  uint32_t keys[kSortTile];
+  uint32_t vals[kSortTile];
+  uint32_t tile;
+  uint32_t warp_sums[kSortWarps];
+};
 
-  const size_t sub = static_cast<size_t>(blockIdx.x) * kSortTile +
-    static_cast<size_t>(warp) * 32 * kSortItems;
+// LAST: the final pass also writes the world coordinates in sorted (cell) order -- the moment
+// kernel then reads a cell's points contiguously -- instead of a separate gather launch.
+template<bool LAST>
+__global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
+  const uint32_t * __restrict__ keys_in, const uint32_t * __restrict__ vals_in, uint32_t n,
+  int shift, uint32_t mask, const uint32_t * __restrict__ ghist, uint32_t * __restrict__ status,
+  uint32_t * __restrict__ ticket, uint32_t * __restrict__ keys_out, uint32_t * __restrict__ vals_out,
+  const double * __restrict__ wx, const double * __restrict__ wy, double * __restrict__ sx,
+  double * __restrict__ sy)
+{
+  extern __shared__ __align__(16) unsigned char os_raw[];
+  OnesweepSmem & sm = *reinterpret_cast<OnesweepSmem *>(os_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) {sm.tile = atomicAdd(ticket, 1u);}
+  for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) {(&sm.cnt[0][0])[i] = 0u;}
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+
+  // ---- stable ranks inside the tile
+  const uint32_t sub = tile * kSortTile + warp * 32u * kSortItems;
   uint32_t k[kSortItems], v[kSortItems], local[kSortItems];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int s = 0; s < kSortItems; ++s) {
-    const size_t i = sub + static_cast<size_t>(s) * 32 + lane;
+    const uint32_t i = sub + static_cast<uint32_t>(s) * 32u + lane;
     const bool active = i < n;
     k[s] = active ? keys_in[i] : 0u;
     v[s] = active ? vals_in[i] : 0u;
     // inactive lanes get a private pseudo digit so they match nobody
-    const uint32_t d = active ? ((k[s] >> shift) & 255u) : (256u + lane);
+    const uint32_t d = active ? ((k[s] >> shift) & mask) : (256u + lane);
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const uint32_t r = __popc(peers & lt_mask);
     uint32_t base = 0;
-    if (active) {base = cnt[warp][d];}
+    if (active) {base = sm.cnt[warp][d];}
     __syncwarp();
-    if (active && r == 0) {cnt[warp][d] = base + __popc(peers);}
+    if (active && r == 0) {sm.cnt[warp][d] = base + __popc(peers);}
     __syncwarp();
     local[s] = base + r;
   }
   __syncthreads();
+
+  // ---- thread d: digit d's count in this tile, per-warp offsets, the look-back
   {
-    // thread d: exclusive prefix over warps + global base of (digit d, this block)
-    const int d = threadIdx.x;
-    uint32_t run = hist_scanned[static_cast<size_t>(d) * nblk + blockIdx.x];
+    const uint32_t d = tid;
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t t = cnt[w][d];
-      cnt[w][d] = run;
+      const uint32_t t = sm.cnt[w][d];
+      sm.cnt[w][d] = run;
       run += t;
+    }
+    const uint32_t count = run;
+    volatile uint32_t * st = status + static_cast<size_t>(tile) * 256u + d;
+    *st = (tile == 0u ? kOsFlagInc : kOsFlagAgg) | count;
+    // exclusive scans over the digits: of the tile's counts (run starts in the sorted tile) and
+    // of the global totals (where digit d's output range starts)
+    const uint32_t total = ghist[d];
+    uint32_t in_t = count, in_g = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, in_t, o);
+      const uint32_t b = __shfl_up_sync(0xffffffffu, in_g, o);
+      if (lane >= static_cast<uint32_t>(o)) {
+        in_t += a;
+        in_g += b;
+      }
+    }
+    __shared__ uint32_t ws_t[kSortWarps], ws_g[kSortWarps];
+    if (lane == 31u) {
+      ws_t[warp] = in_t;
+      ws_g[warp] = in_g;
+    }
+    __syncthreads();
+    uint32_t off_t = 0, off_g = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      if (static_cast<uint32_t>(w) < warp) {
+        off_t += ws_t[w];
+        off_g += ws_g[w];
+      }
+    }
+    const uint32_t toff = off_t + in_t - count, gdigit = off_g + in_g - total;
+    // look back over the tiles before this one
+    uint32_t excl = 0;
+    if (tile > 0u) {
+      uint32_t t = tile - 1u;
+      for (;;) {
+        volatile const uint32_t * ps = status + static_cast<size_t>(t) * 256u + d;
+        uint32_t w;
+        do {w = *ps;} while ((w >> 30) == 0u);
+        excl += w & kOsCount;
+        if ((w >> 30) == 2u || t == 0u) {break;}
+        --t;
+      }
+      *st = kOsFlagInc | (excl + count);
+    }
+    sm.toff[d] = toff;
+    sm.gbase[d] = gdigit + excl - toff;
+  }
+  __syncthreads();
+
+  // ---- permute the tile into digit order in shared memory
+#pragma unroll
+  for (int s = 0; s < kSortItems; ++s) {
+    const uint32_t i = sub + static_cast<uint32_t>(s) * 32u + lane;
+    if (i < n) {
+      const uint32_t d = (k[s] >> shift) & mask;
+      const uint32_t pos = sm.toff[d] + sm.cnt[warp][d] + local[s];
+      sm.keys[pos] = k[s];
+      sm.vals[pos] = v[s];
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int s = 0; s < kSortItems; ++s) {
-    const size_t i = sub + static_cast<size_t>(s) * 32 + lane;
-    if (i < n) {
-      const uint32_t d = (k[s] >> shift) & 255u;
-      const uint32_t pos = cnt[warp][d] + local[s];
-      keys_out[pos] = k[s];
-      vals_out[pos] = v[s];
+  // ---- write out: tile-sorted index j of digit d goes to gbase[d] + j
+  const uint32_t n_tile = min(static_cast<uint32_t>(kSortTile), n - tile * kSortTile);
+  for (uint32_t j = tid; j < n_tile; j += kSortThreads) {
+    const uint32_t kk = sm.keys[j];
+    const uint32_t pos = sm.gbase[(kk >> shift) & mask] + j;
+    const uint32_t p = sm.vals[j];
+    keys_out[pos] = kk;
+    vals_out[pos] = p;
+    if (LAST) {
+      sx[pos] = wx[p];
+      sy[pos] = wy[p];
     }
   }
 }
@@ -334,19 +434,6 @@ __global__ void __launch_bounds__(256) segment_count_kernel(
     atomicOr(&occ[p >> 5].x, 1u << (p & 31u));
     heads[atomicAdd(n_heads, 1u)] = make_uint2(static_cast<uint32_t>(i), len);
   }
-}
-
-// Sorted-order copies of the world coordinates: the moment kernels then read a cell's
-// points contiguously.
-__global__ void __launch_bounds__(256) gather_sorted_kernel(
-  const uint32_t * __restrict__ val, size_t n, const double * __restrict__ wx,
-  const double * __restrict__ wy, double * __restrict__ sx, double * __restrict__ sy)
-{
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) {return;}
-  const uint32_t p = val[i];
-  sx[i] = wx[p];
-  sy[i] = wy[p];
 }
 
 struct CellStats
@@ -943,6 +1030,13 @@ int bits_needed(uint32_t max_value)
 
 }  // namespace
 
+size_t ndt2d_sort_scratch_bytes(size_t n_points)
+{
+  const size_t nblk = (n_points + kSortTile - 1) / kSortTile;
+  return (static_cast<size_t>(kMaxPasses) * 256 + 64 + static_cast<size_t>(kMaxPasses) * nblk * 256) *
+         sizeof(uint32_t);
+}
+
 bool ndt2d_build_is_small(const GridDesc & g, size_t n_points)
 {
   return n_points > 0 && n_points <= kSmallMaxPoints && g.n_words <= kSmallMaxWords;
@@ -1005,30 +1099,46 @@ int ndt2d_launch_build(
   NDT2D_CUDA_TRY(cudaMemsetAsync(s.n_heads, 0, sizeof(uint32_t), stream));
   int cur = 0;
   if (n_points > 0) {
-    const uint32_t grid = static_cast<uint32_t>(n_scans < 65535u * 8u ? n_scans : 65535u * 8u);
+    if (n_points >= (size_t(1) << 30)) {return NDT2D_ERR_SIZE;}   // 30-bit counts in the look-back words
+    const uint32_t nblk = static_cast<uint32_t>((n_points + kSortTile - 1) / kSortTile);
+    DigitPlan dp;
+    const int bits = bits_needed(g.n_cells);
+    dp.passes = (bits + 7) / 8;
+    dp.width = (bits + dp.passes - 1) / dp.passes;
+    dp.mask = (1u << dp.width) - 1u;
+    // sort scratch (s.hist): [kMaxPasses][256] digit totals | tickets | [passes][nblk][256] status
+    uint32_t * ghist = s.hist;
+    uint32_t * tickets = s.hist + kMaxPasses * 256;
+    uint32_t * status = tickets + 64;
+    NDT2D_CUDA_TRY(cudaMemsetAsync(s.hist, 0, ndt2d_sort_scratch_bytes(n_points), stream));
+    // a few blocks per SM, each looping over scans (one flush of its digit counters per block)
+    const uint32_t grid = static_cast<uint32_t>(n_scans < 148u * 16u ? n_scans : 148u * 16u);
     transform_key_kernel<<<grid, 128, 0, stream>>>(
       g, d_scan_tf, d_offsets, static_cast<uint32_t>(n_scans), d_pts, s.wx, s.wy, s.key[0],
-      s.val[0]);
+      s.val[0], dp, ghist);
     NDT2D_LAUNCH_CHECK(ctr);
-
-    const uint32_t nblk = static_cast<uint32_t>((n_points + kSortTile - 1) / kSortTile);
-    const int bits = bits_needed(g.n_cells);
-    for (int shift = 0; shift < bits; shift += 8) {
-      radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(
-        s.key[cur], n_points, shift, s.hist, nblk);
-      NDT2D_LAUNCH_CHECK(ctr);
-      const int rc = launch_scan<0>(s.hist, static_cast<size_t>(256) * nblk, s.scan_tmp, stream, ctr);
-      if (rc != NDT2D_OK) {return rc;}
-      radix_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(
-        s.key[cur], s.val[cur], n_points, shift, s.hist, nblk, s.key[cur ^ 1], s.val[cur ^ 1]);
+    static bool configured[64] = {false};
+    int dev = 0;
+    NDT2D_CUDA_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+      NDT2D_CUDA_TRY(cudaFuncSetAttribute(radix_onesweep_kernel<false>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(OnesweepSmem))));
+      NDT2D_CUDA_TRY(cudaFuncSetAttribute(radix_onesweep_kernel<true>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(OnesweepSmem))));
+      configured[dev & 63] = true;
+    }
+    for (int q = 0; q < dp.passes; ++q) {
+      auto kernel = q + 1 == dp.passes ? radix_onesweep_kernel<true> : radix_onesweep_kernel<false>;
+      kernel<<<nblk, kSortThreads, sizeof(OnesweepSmem), stream>>>(
+        s.key[cur], s.val[cur], static_cast<uint32_t>(n_points), q * dp.width, dp.mask,
+        ghist + q * 256, status + static_cast<size_t>(q) * nblk * 256u, tickets + q, s.key[cur ^ 1],
+        s.val[cur ^ 1], s.wx, s.wy, s.sx, s.sy);
       NDT2D_LAUNCH_CHECK(ctr);
       cur ^= 1;
     }
     const uint32_t nb = static_cast<uint32_t>((n_points + 255) / 256);
     segment_count_kernel<<<nb, 256, 0, stream>>>(g, s.key[cur], n_points, s.seglen, d_occ,
       s.heads, s.n_heads);
-    NDT2D_LAUNCH_CHECK(ctr);
-    gather_sorted_kernel<<<nb, 256, 0, stream>>>(s.val[cur], n_points, s.wx, s.wy, s.sx, s.sy);
     NDT2D_LAUNCH_CHECK(ctr);
   }
   {

@@ -107,7 +107,7 @@ struct BuildScratch
   uint32_t * key[2];        // ping-pong sort keys (cell index, n_cells = outside)
   uint32_t * val[2];        // ping-pong values (point index)
   uint32_t * seglen;        // per sorted position: segment length (heads only)
-  uint32_t * hist;          // radix histogram [256][n_blocks]
+  uint32_t * hist;          // sort scratch: digit totals, tickets, look-back status (ndt2d_sort_scratch_bytes)
   uint32_t * scan_tmp;      // scratch of the scan kernel
   double * rcp;             // rcp[0] = 1.0, rcp[k] = RN(1 / k), k <= NDT2D_RCP_TABLE (filled by the first build)
   bool rcp_ready;
@@ -133,6 +133,7 @@ struct BuildEntry
   uint32_t n_scans, n_points, rec_cap, pad_;
 };
 bool ndt2d_build_is_small(const GridDesc & g, size_t n_points);
+size_t ndt2d_sort_scratch_bytes(size_t n_points);
 // n models, one CTA each, one launch; d_entries: device array.
 int ndt2d_launch_build_small_batch(const BuildEntry * d_entries, uint32_t n, cudaStream_t stream,
   Counters * ctr);
