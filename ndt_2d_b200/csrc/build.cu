@@ -267,7 +267,7 @@ struct OnesweepSmem
 // LAST: the final pass also writes the world coordinates in sorted (cell) order -- the moment
 // kernel then reads a cell's points contiguously -- instead of a separate gather launch.
 template<bool LAST>
-__global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
+__global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
   const uint32_t * __restrict__ keys_in, const uint32_t * __restrict__ vals_in, uint32_t n,
   int shift, uint32_t mask, const uint32_t * __restrict__ ghist, uint32_t * __restrict__ status,
   uint32_t * __restrict__ ticket, uint32_t * __restrict__ keys_out, uint32_t * __restrict__ vals_out,

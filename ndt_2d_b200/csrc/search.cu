@@ -632,6 +632,46 @@ __global__ void __launch_bounds__(256) score_poses_kernel(
   }
 }
 
+// A handful of poses (scoreScan / scorePoints of the node: ONE pose per scan): one 512-thread
+// block, a thread per scan point, poses one after the other -- a warp per pose walks 360 beams in
+// 12 dependent rounds (24 us), a block does it in one (the call is pure latency).  Results
+// go to `out` and, when given, straight to the host mailbox.
+constexpr uint32_t kFewPosesThreads = 512;
+__global__ void __launch_bounds__(kFewPosesThreads) score_few_poses_kernel(
+  ModelView mv, const double2 * __restrict__ pts, uint32_t n_pts,
+  const double4 * __restrict__ pose_tf, uint32_t n_poses, double sign, int normalise,
+  double * __restrict__ out, HostMailbox hm)
+{
+  __shared__ double warp_acc[kFewPosesThreads / 32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t pose = 0; pose < n_poses; ++pose) {
+    const double4 tf = pose_tf[pose];  // x, y, cos, sin
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < n_pts; i += kFewPosesThreads) {
+      const double2 p = pts[i];
+      const double x = __dadd_rn(__dadd_rn(__dmul_rn(tf.z, p.x), __dmul_rn(-tf.w, p.y)), tf.x);
+      const double y = __dadd_rn(__dadd_rn(__dmul_rn(tf.w, p.x), __dmul_rn(tf.z, p.y)), tf.y);
+      acc += point_likelihood_exact(mv, x, y);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {warp_acc[warp] = acc;}
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (uint32_t w = 0; w < kFewPosesThreads / 32; ++w) {t += warp_acc[w];}
+      double v = sign * t;
+      if (normalise) {v = v / static_cast<double>(n_pts);}
+      out[pose] = v;
+      if (hm.out32) {hm.out32[pose] = v;}
+    }
+    __syncthreads();
+  }
+  if (hm.out32 && threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(hm.flag, hm.seq);
+  }
+}
+
 uint32_t plain_blocks_x(uint32_t n_lin)
 {
   const uint64_t n_cand = static_cast<uint64_t>(n_lin) * n_lin;
@@ -797,6 +837,12 @@ int ndt2d_launch_score_poses(
   const uint32_t grid = (n_poses + warps_per_block - 1) / warps_per_block;
   HostMailbox hm{nullptr, nullptr, 0ull};
   if (host && grid == 1) {hm = *host;}   // (the flag protocol needs a single block)
+  if (n_poses <= 8) {
+    score_few_poses_kernel<<<1, kFewPosesThreads, 0, stream>>>(
+      mv, d_pts, n_pts, d_pose_tf, n_poses, sign, normalise, d_out, hm);
+    NDT2D_LAUNCH_CHECK(ctr);
+    return NDT2D_OK;
+  }
   score_poses_kernel<<<grid, 256, 0, stream>>>(
     mv, d_pts, n_pts, d_pose_tf, n_poses, sign, normalise, d_out, hm);
   NDT2D_LAUNCH_CHECK(ctr);

@@ -66,6 +66,8 @@ def main():
         for r in src[2:]:
             if len(r) <= iT:
                 continue
+            if not (r[iE] or "0").isdigit():
+                continue   # (reports with several kernels repeat the header rows)
             s = re.sub(r"^@!?U?P\d+\s+", "", r[iS].strip())
             op = ".".join(s.split()[0].split(".")[:3]) if s else "?"
             ops[op] += int(r[iE] or 0)
