@@ -247,6 +247,11 @@ NDT2D_API int ndt2d_matcher_group_info(ndt2d_matcher * m, uint64_t * info4);
  * min_pairs (candidate, scan point) pairs (default 1e10, ~0.4 ms of one B200: smaller searches
  * are latency-bound and stay on devices[0]). */
 NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pairs);
+/* The large-search kernel can tally the work it did -- (candidate, point) evaluations that
+ * reached an occupied cell, (point, region) items -- for ndt2d_matcher_search_stats /
+ * _group_search_stats.  The bookkeeping costs about 2 % of the kernel, so it is off by default
+ * (the tallies then read 0); on != 0 turns it on for the searches that follow. */
+NDT2D_API int ndt2d_matcher_set_tallies(ndt2d_matcher * m, int on);
 /* Small searches and small model builds (the per-scan local match: tens of microseconds) skip
  * the CUDA event records that feed search_stats / build_stats kernel times unless on != 0
  * (default off; large searches and builds are always timed). */

@@ -88,6 +88,7 @@ SIGNATURES = {
     "ndt2d_matcher_group_info": (C.c_int, [_vp, _u64p]),
     "ndt2d_matcher_set_group_threshold": (C.c_int, [_vp, C.c_double]),
     "ndt2d_matcher_set_timing": (C.c_int, [_vp, C.c_int]),
+    "ndt2d_matcher_set_tallies": (C.c_int, [_vp, C.c_int]),
     "ndt2d_matcher_group_search_stats": (C.c_int, [_vp, _dp, C.c_size_t, _u64p]),
     "ndt2d_combine_partials": (C.c_int, [_vp, _dp, C.c_size_t, _dp, _ip, _dp, _dp]),
     "ndt2d_combine_partials_host": (

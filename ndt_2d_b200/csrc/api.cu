@@ -242,6 +242,7 @@ struct ndt2d_matcher
   // small searches / builds skip the event records (two driver calls and a bubble between the
   // kernels each) unless asked for: ndt2d_matcher_set_timing
   bool time_small = false;
+  bool tally = false;                // region kernel tallies (ndt2d_matcher_set_tallies)
   unsigned long long host_seq = 0;   // HostMailbox sequence of the last search
   cudaEvent_t evb_begin = nullptr, evb_end = nullptr;  // bracket the kernels of the last build
   bool evb_valid = false;
@@ -280,6 +281,7 @@ SearchView search_view(const ndt2d_matcher * m)
   sv.n_ang = static_cast<uint32_t>(m->dth.size());
   sv.n_lin = static_cast<uint32_t>(m->dlin.size());
   sv.theta_stride = 1;
+  sv.tally = m->tally ? 1u : 0u;
   sv.coords = m->d_coords.as<uint32_t>();
   sv.coords_cap_bytes = m->d_coords.cap;
   sv.chunk_sums = m->d_chunk.as<double>();
@@ -2620,6 +2622,16 @@ NDT2D_API int ndt2d_matcher_set_group_threshold(ndt2d_matcher * m, double min_pa
   if (!m || !(min_pairs >= 0.0)) {return NDT2D_ERR_INVALID;}
   std::lock_guard<std::mutex> lock(m->mu);
   m->group_min_pairs = min_pairs;
+  return NDT2D_OK;
+}
+
+NDT2D_API int ndt2d_matcher_set_tallies(ndt2d_matcher * m, int on)
+{
+  if (!m) {return NDT2D_ERR_INVALID;}
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->tally = on != 0;
+  for (size_t r = 1; r < m->group.size(); ++r) {m->group[r]->tally = m->tally;}
+  for (ndt2d_matcher * s : m->lanes) {s->tally = m->tally;}
   return NDT2D_OK;
 }
 

@@ -82,6 +82,7 @@ struct SearchView
   double * chunk_sums;      // scratch of the point-chunked mode of small searches (may be null)
   size_t chunk_cap_doubles;
   uint32_t theta_stride;  // a search covers theta_begin, theta_begin + stride, ... (< theta_end)
+  uint32_t tally;         // != 0: the region kernel tallies useful evaluations / items (search_stats)
 };
 
 // Per-block partial of the search (8 doubles):

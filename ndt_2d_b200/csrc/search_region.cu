@@ -61,8 +61,12 @@ constexpr uint32_t kPairs = (kMaxRY + 1) / 2;   // rows are held and evaluated t
 #define NDT2D_REGION_WARPS 24
 #endif
 constexpr uint32_t kWarps = NDT2D_REGION_WARPS;  // warps per CTA; one persistent CTA per SM
-// per warp: double totals, [row][lane]
-constexpr uint32_t kWarpSmemBytes = kMaxRY * 32u * static_cast<uint32_t>(sizeof(double));
+// per warp: double totals, [row][lane], then one 32-byte record per lane for the scan points of
+// the current step (exact rotated position + packed splits / occupancy / record ranks): an item
+// reads its point's record with two broadcast loads instead of seven shuffles, and the
+// values do not occupy registers across the item loop
+constexpr uint32_t kWarpTotBytes = kMaxRY * 32u * static_cast<uint32_t>(sizeof(double));
+constexpr uint32_t kWarpSmemBytes = kWarpTotBytes + 32u * 32u;
 // D + thresholds in shared memory up to this: what the warps' totals leave of the 227 KB a CTA
 // can opt in to, at most 64 KB
 constexpr size_t kSmemLeft = 227 * 1024 - 1024 - static_cast<size_t>(kWarpSmemBytes) * kWarps;
@@ -433,7 +437,9 @@ __global__ void __launch_bounds__(256) region_chunk_reduce_kernel(
     theta_begin + it * sv.theta_stride, jx0, jy0, nxc, nyc, lane, job_partials, scores);
 }
 
-template<bool SMEM_TAB, bool PRE>
+// STATS: tally the useful evaluations and items of the launch (ndt2d_matcher_set_tallies; the
+// bookkeeping costs ~2 % of the kernel, so it is off unless asked for).
+template<bool SMEM_TAB, bool PRE, bool STATS>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 search_region_kernel(
   ModelView mv, SearchView sv, uint32_t theta_begin, uint32_t RX, uint32_t RY, uint32_t Qx,
@@ -515,7 +521,7 @@ search_region_batch_kernel(
   double * tot = reinterpret_cast<double *>(sp);
   BatchEntry * slot = reinterpret_cast<BatchEntry *>(sp + kWarpSmemBytes);
   uint32_t cur_search = 0xffffffffu;
-  constexpr bool PRE = false, SMEM_TAB = false;
+  constexpr bool PRE = false, SMEM_TAB = false, STATS = false;
   const uint32_t theta_begin = 0;
   double * const scores = nullptr;
   const uint32_t * const coords = nullptr;
@@ -622,13 +628,13 @@ size_t coords_bytes(const RegionPlan & pl, uint32_t n_theta, uint32_t n_pts)
   return static_cast<size_t>(n_theta) * (pl.Qx + pl.Qy) * n_pts_pad * sizeof(uint32_t);
 }
 
-template<bool S, bool PRE>
+template<bool S, bool PRE, bool STATS>
 int launch_one(RegionPlan & pl, const ModelView & mv, const SearchView & sv,
   uint32_t theta_begin, uint32_t n_theta, double * d_job_partials, double * d_scores,
   uint32_t * d_counter, uint32_t * d_coords, double * d_chunk_sums, cudaStream_t stream,
   Counters * ctr)
 {
-  auto kernel = search_region_kernel<S, PRE>;
+  auto kernel = search_region_kernel<S, PRE, STATS>;
   // per (instantiation, device): opt in to the large dynamic shared memory once, and
   // remember the SM count (both calls cost microseconds that a 100 us search notices)
   static int configured_sms[64] = {0};
@@ -821,8 +827,11 @@ int ndt2d_launch_search_region(
   const bool pre = d_coords && pl.Qx >= 3 && sv.n_pts > 0 &&
     coords_bytes(pl, n_theta, sv.n_pts) <= coords_cap_bytes;
 #define NDT2D_REGION_LAUNCH(S, P) \
-  launch_one<S, P>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
-    d_coords, sv.chunk_sums, stream, ctr)
+  (sv.tally ? \
+   launch_one<S, P, true>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
+     d_coords, sv.chunk_sums, stream, ctr) : \
+   launch_one<S, P, false>(pl, mv, sv, theta_begin, n_theta, d_job_partials, d_scores, d_counter, \
+     d_coords, sv.chunk_sums, stream, ctr))
   if (pl.smem_tab) {
     return pre ? NDT2D_REGION_LAUNCH(true, true) : NDT2D_REGION_LAUNCH(true, false);
   }

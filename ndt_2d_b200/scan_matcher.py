@@ -476,6 +476,10 @@ class ScanMatcherNDT:
                     "probe_call_latency")
         return out
 
+    def set_tallies(self, on: bool) -> None:
+        """Useful-evaluation / item tallies of the large-search kernel (ndt2d_matcher_set_tallies; default off)."""
+        L.check(L.lib.ndt2d_matcher_set_tallies(self.handle, int(bool(on))), "set_tallies")
+
     def set_timing(self, on: bool) -> None:
         """CUDA event timing of small searches / builds too (ndt2d_matcher_set_timing; default off)."""
         L.check(L.lib.ndt2d_matcher_set_timing(self.handle, int(bool(on))), "set_timing")

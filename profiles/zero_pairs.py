@@ -15,6 +15,7 @@ for wl in (synth.config4(), synth.config4_dense()):
     m = ScanMatcherNDT.from_params(wl.params)
     m.add_scans_raw(wl.map_poses, wl.map_offsets, wl.map_points)
     na, nl = m.search_shape()
+    m.set_tallies(True)
     m.stage_scan(wl.query_pose, wl.query_points)
     m.search_staged(0, na, stride=8)
     m.fetch_partial()
