@@ -58,7 +58,7 @@ constexpr uint32_t kMaxRX = 32;                 // region columns (candidates al
 constexpr uint32_t kMaxRY = 25;                 // region rows (candidates along dy) = registers
 constexpr uint32_t kPairs = (kMaxRY + 1) / 2;   // rows are held and evaluated two at a time
 #ifndef NDT2D_REGION_WARPS
-#define NDT2D_REGION_WARPS 24
+#define NDT2D_REGION_WARPS 28
 #endif
 constexpr uint32_t kWarps = NDT2D_REGION_WARPS;  // warps per CTA; one persistent CTA per SM
 // per warp: double totals, [row][lane], then one 32-byte record per lane for the scan points of
