@@ -263,6 +263,7 @@ ModelView model_view(const ndt2d_matcher * m)
   mv.thr_x = m->d_thr;
   mv.thr_y = m->d_thr + (m->g.size_x + 2);
   mv.n_valid_cap = m->rec_cap;
+  mv.n_stiff = m->d_nvalid.as<uint32_t>() + 1;
   return mv;
 }
 
@@ -446,7 +447,7 @@ int add_scans_impl(
   // +4 words of slack: the search kernel's bulk copies round sizes up to 16 bytes
   if ((rc = m->d_occ.ensure((static_cast<size_t>(g.n_words) + 4) * sizeof(uint2)))) {return rc;}
   if ((rc = m->d_occd.ensure((static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t)))) {return rc;}
-  if ((rc = m->d_nvalid.ensure(sizeof(uint32_t)))) {return rc;}
+  if ((rc = m->d_nvalid.ensure(2 * sizeof(uint32_t)))) {return rc;}   // n_valid, n_stiff
   const uint64_t cap64 = std::min<uint64_t>(n_cells64, n_points / 5) + 1;
   m->rec_cap = static_cast<uint32_t>(cap64);
   if ((rc = m->d_rec.ensure(cap64 * NDT2D_REC_DOUBLES * sizeof(double)))) {return rc;}
@@ -1225,7 +1226,7 @@ static int match_scan_batch_fused(
     J.o_rec = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
     J.o_recf = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
     J.o_recv = take(J.rec_cap * NDT2D_REC_DOUBLES * sizeof(double));
-    J.o_nvalid = take(sizeof(uint32_t));
+    J.o_nvalid = take(2 * sizeof(uint32_t));
     J.o_jobp = take(static_cast<size_t>(pl.n_jobs) * NDT2D_BLOCK_PARTIAL * sizeof(double));
     J.o_chunk = take(pl.chunk_doubles ? pl.chunk_doubles * sizeof(double) : 8);
   }
@@ -1296,6 +1297,7 @@ static int match_scan_batch_fused(
     se.mv.thr_x = reinterpret_cast<const double *>(db + J.o_thr);
     se.mv.thr_y = se.mv.thr_x + (J.g.size_x + 2);
     se.mv.n_valid_cap = static_cast<uint32_t>(J.rec_cap);
+    se.mv.n_stiff = be.n_valid + 1;
     se.sv.pts = reinterpret_cast<const double2 *>(db + J.o_q);
     se.sv.trig = reinterpret_cast<const double2 *>(db + J.o_trig);
     se.sv.dth = m->d_dth.as<double>();

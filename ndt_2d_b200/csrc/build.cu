@@ -502,7 +502,7 @@ __device__ __forceinline__ void stats_walk(
 // The packed records of one finished cell (layout: ndt2d_internal.h, ModelView).
 __device__ __forceinline__ void write_records(
   const CellStats & c, const GridDesc & g, double * __restrict__ rr, double * __restrict__ f,
-  double * __restrict__ vt)
+  double * __restrict__ vt, uint32_t * __restrict__ n_stiff)
 {
   // -0.5 * information: scaling by a power of two is exact, so the device
   // exponent (-0.5 q)^T I q keeps the reference's rounding term by term.
@@ -533,6 +533,8 @@ __device__ __forceinline__ void write_records(
   vt[4] = S;
   const float2 tail = make_float2(static_cast<float>(D * (g.lin_res * g.lin_res)), vstiff ? 1.0f : 0.0f);
   *reinterpret_cast<float2 *>(vt + 5) = tail;
+  // the region kernel skips its per-item stiff-cell vote when the model has none
+  if (vstiff) {atomicAdd(n_stiff, 1u);}
 }
 
 // K3b: the cells of the head list replay Cell::addPoint's recurrence and emit their
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(256) segment_moments_kernel(
       if (rank < rec_cap) {
         write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
           rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-          rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+          rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES, n_valid + 1);
       }
     }
   }
@@ -771,6 +773,7 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
   if (tid == 0) {
     sm.n_heads = 0u;
     sm.one = 1.0;
+    n_valid[1] = 0u;   // stiff-cell count (write_records)
   }
   // ---- K1: transform + key (NDT::addScan, ndt_model.cpp:132-152)
   for (uint32_t p = tid; p < n2; p += kSmallThreads) {
@@ -977,7 +980,7 @@ __device__ __forceinline__ void build_small_body(const BuildEntry & e, SmallSmem
         if (rank < rec_cap) {
           write_records(c, g, rec + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
             rec_fast + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES,
-            rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES);
+            rec_vtx + static_cast<size_t>(rank) * NDT2D_REC_DOUBLES, n_valid + 1);
         }
       }
     }
@@ -1095,7 +1098,7 @@ int ndt2d_launch_build(
   }
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint2), stream));
   NDT2D_CUDA_TRY(cudaMemsetAsync(d_occ_dilated, 0, (static_cast<size_t>(g.n_words) + 4) * sizeof(uint32_t), stream));
-  NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, sizeof(uint32_t), stream));
+  NDT2D_CUDA_TRY(cudaMemsetAsync(d_n_valid, 0, 2 * sizeof(uint32_t), stream));   // n_valid, n_stiff
   NDT2D_CUDA_TRY(cudaMemsetAsync(s.n_heads, 0, sizeof(uint32_t), stream));
   int cur = 0;
   if (n_points > 0) {

@@ -62,6 +62,7 @@ struct ModelView
   const double * thr_x;  // size_x + 2 entries (the last is +inf)
   const double * thr_y;  // size_y + 2 entries
   uint32_t n_valid_cap;
+  const uint32_t * n_stiff;  // number of cells flagged stiff in rec_vtx (null: unknown, assume some)
 };
 
 #define NDT2D_REC_DOUBLES 6
