@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "ndt2d_internal.h"
 #include "search_common.cuh"
 
@@ -85,6 +87,7 @@ __device__ __forceinline__ void window_block(
   // (in registers: for a batch launch mv / sv live in shared memory)
   const double * const rec_fast = mv.rec_fast;
   const uint2 * const occ = mv.occ;
+  const bool any_stiff = mv.n_stiff == nullptr || __ldg(mv.n_stiff) != 0u;
 
   for (uint32_t k = threadIdx.x; k < n_lin; k += blockDim.x) {dlin_s[k] = sv.dlin[k];}
 
@@ -152,51 +155,63 @@ __device__ __forceinline__ void window_block(
       }
     }
     __syncthreads();
-    // ---- phase B: this thread's candidate against its group's share of the pass, in point order
+    // ---- phase B: this thread's candidate against its group's share of the pass, in point order.
+    // Two instantiations of the loop: models without stiff cells (the usual case; the build counts
+    // them, ModelView::n_stiff) run it without the stiff-flag bookkeeping and branch.
     if (active) {
       const uint32_t per_group = (np + n_groups - 1u) / n_groups;
       const uint32_t i_end = min(np, (group + 1u) * per_group);
-      int32_t r_cached = -1;
-      bool stiff_cached = false;
-      double2 mean = make_double2(0.0, 0.0), AB = mean, Ds = mean;
       const uint32_t i_begin = min(np, group * per_group);
-      // one pointer walks the point records; this candidate's two bytes sit at fixed offsets
-      const unsigned char * prec = win_smem + static_cast<size_t>(i_begin) * S;
       const uint32_t my_kx = kOffKx + ix, my_ky = off_ky + iy;
-      for (uint32_t i0 = i_begin; i0 < i_end; i0 += kWinBlockPts) {
-        const uint32_t n_blk = min(i_end - i0, kWinBlockPts);
-        float blk = 0.0f;
-        for (uint32_t j = 0; j < n_blk; ++j, prec += S) {
-          // one (candidate, point) evaluation
-          const uint32_t k = static_cast<uint32_t>(prec[my_kx]) + static_cast<uint32_t>(prec[my_ky]);
-          const int32_t r = reinterpret_cast<const int32_t *>(prec + kOffRank)[k];
-          // consecutive beams mostly stay in one cell: the record is fetched only when this
-          // candidate's cell changes; an unoccupied cell evaluates the record at hand and drops
-          // the result -- cheaper than diverging around the arithmetic
-          if (r >= 0 && r != r_cached) {
-            const double2 * f2 = reinterpret_cast<const double2 *>(
-              rec_fast + static_cast<size_t>(r) * NDT2D_REC_DOUBLES);
-            mean = __ldg(f2);
-            AB = __ldg(f2 + 1);
-            Ds = __ldg(f2 + 2);
-            r_cached = r;
-            stiff_cached = ((__double2hiint(Ds.y) & 0x7fffffff) | __double2loint(Ds.y)) != 0;
+      auto phase_b = [&](auto stiff_tag) {
+        constexpr bool STIFF = decltype(stiff_tag)::value;
+        int32_t r_cached = -1;
+        bool stiff_cached = false;
+        double2 mean = make_double2(0.0, 0.0), AB = mean, Ds = mean;
+        // one pointer walks the point records; this candidate's two bytes sit at fixed offsets
+        const unsigned char * prec = win_smem + static_cast<size_t>(i_begin) * S;
+        for (uint32_t i0 = i_begin; i0 < i_end; i0 += kWinBlockPts) {
+          const uint32_t n_blk = min(i_end - i0, kWinBlockPts);
+          float blk = 0.0f;
+          for (uint32_t j = 0; j < n_blk; ++j, prec += S) {
+            // one (candidate, point) evaluation
+            const uint32_t k = static_cast<uint32_t>(prec[my_kx]) + static_cast<uint32_t>(prec[my_ky]);
+            const int32_t r = reinterpret_cast<const int32_t *>(prec + kOffRank)[k];
+            // consecutive beams mostly stay in one cell: the record is fetched only when this
+            // candidate's cell changes; an unoccupied cell evaluates the record at hand and drops
+            // the result -- cheaper than diverging around the arithmetic
+            if (r >= 0 && r != r_cached) {
+              const double2 * f2 = reinterpret_cast<const double2 *>(
+                rec_fast + static_cast<size_t>(r) * NDT2D_REC_DOUBLES);
+              mean = __ldg(f2);
+              AB = __ldg(f2 + 1);
+              Ds = __ldg(f2 + 2);
+              r_cached = r;
+              if (STIFF) {
+                stiff_cached = ((__double2hiint(Ds.y) & 0x7fffffff) | __double2loint(Ds.y)) != 0;
+              }
+            }
+            const double2 o = *reinterpret_cast<const double2 *>(prec);
+            const double x = __dadd_rn(o.x, dx), y = __dadd_rn(o.y, dy);   // scan_matcher_ndt.cpp:123-124
+            const double qx = x - mean.x, qy = y - mean.y;
+            const double e = qx * (AB.x * qx + AB.y * qy) + (Ds.x * qy) * qy;   // log2 of the likelihood
+            float f;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(static_cast<float>(e)));
+            if (STIFF && r >= 0 && stiff_cached) {
+              // stiff cell: the reference's own grouping (see search_common.cuh)
+              f = 0.0f;
+              const uint32_t b0 = *reinterpret_cast<const uint32_t *>(prec + kOffBase);
+              acc += cell_likelihood(occ, mv.rec, b0 + (k / K) * pitch + (k % K), x, y);
+            }
+            blk += (r >= 0) ? f : 0.0f;
           }
-          const double2 o = *reinterpret_cast<const double2 *>(prec);
-          const double x = __dadd_rn(o.x, dx), y = __dadd_rn(o.y, dy);   // scan_matcher_ndt.cpp:123-124
-          const double qx = x - mean.x, qy = y - mean.y;
-          const double e = qx * (AB.x * qx + AB.y * qy) + (Ds.x * qy) * qy;   // log2 of the likelihood
-          float f;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(static_cast<float>(e)));
-          if (r >= 0 && stiff_cached) {
-            // stiff cell: the reference's own grouping (see search_common.cuh)
-            f = 0.0f;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(prec + kOffBase);
-            acc += cell_likelihood(occ, mv.rec, b0 + (k / K) * pitch + (k % K), x, y);
-          }
-          blk += (r >= 0) ? f : 0.0f;
+          acc += static_cast<double>(blk);
         }
-        acc += static_cast<double>(blk);
+      };
+      if (any_stiff) {
+        phase_b(std::true_type{});
+      } else {
+        phase_b(std::false_type{});
       }
     }
   }

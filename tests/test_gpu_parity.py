@@ -275,6 +275,43 @@ def test_match_scan_config4_reduced(o):
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
+def test_instrumentation_switches(o):
+    """Work tallies and small-search event timing are off by default (they cost run time on the
+    hot path) and available on request; results do not depend on them; the C-ABI latency probe
+    times real calls."""
+    w = synth.config4(scale=0.04)
+    m = ScanMatcherNDT.from_params(w.params, kernel_variant=4)       # the region kernel, forced
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    guess = w.true_pose - np.array([0.05, -0.03, 0.06])
+    a = m.match_scan_raw(guess, w.query_points)
+    st = m.search_stats()
+    assert st["useful_evaluations"] == 0 and st["items"] == 0
+    m.set_tallies(True)
+    b = m.match_scan_raw(guess, w.query_points)
+    st = m.search_stats()
+    assert st["useful_evaluations"] > 0 and 0 < st["items"] < st["useful_evaluations"]
+    m.set_tallies(False)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    m.close()
+    w = synth.config1(laser_max_beams=100)
+    m = ScanMatcherNDT.from_params(w.params)
+    m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+    r0 = m.match_scan_raw(w.query_pose, w.query_points)
+    assert m.search_stats()["kernel_ms"] == 0.0                      # small search: no event records
+    m.set_timing(True)
+    r1 = m.match_scan_raw(w.query_pose, w.query_points)
+    assert m.search_stats()["kernel_ms"] > 0.0
+    assert r0[0] == r1[0] and np.array_equal(r0[1], r1[1])
+    us = m.probe_call_latency(w.query_pose, w.query_points, 20)
+    assert us.shape == (20,) and np.all(us > 1.0) and np.all(us < 1.0e5)
+    us = m.probe_call_latency(w.query_pose, w.query_points, 5, (w.map_poses, w.map_offsets, w.map_points))
+    assert np.all(us > 1.0)
+    # the sequence left the handle with the same model: the match is still the same
+    r2 = m.match_scan_raw(w.query_pose, w.query_points)
+    assert r0[0] == r2[0] and np.array_equal(r0[1], r2[1])
+    m.close()
+
+
 def test_match_scan_dense_clutter_reduced(o):
     """The cluttered short-range world of bench.py's floor workload (a third of the (candidate,
     point) pairs in occupied 0.5 m cells), on a window the oracle finishes in seconds: full score
