@@ -110,7 +110,10 @@ NDT2D_API int ndt2d_matcher_reset(ndt2d_matcher * m);
 /* replaces ScanMatcherNDT::addScans (scan_matcher_ndt.cpp:49-74) and through
  * it NDT::NDT / addScan / compute (ndt_model.cpp:118-160).  Always builds a
  * fresh model.  poses: 3 doubles per scan; pt_offsets: n_scans+1 entries, in
- * points; pts_xy: concatenated sensor-frame points. */
+ * points; pts_xy: concatenated sensor-frame points (fewer than 2^30 of them: NDT2D_ERR_SIZE
+ * otherwise).  A model of up to 1 MB of points (every rolling window) is built asynchronously:
+ * the call returns once one copy from the handle's pinned arena and one launch are enqueued, and
+ * the next value-returning call waits for it. */
 NDT2D_API int ndt2d_matcher_add_scans(
   ndt2d_matcher * m, size_t n_scans, const double * poses, const uint64_t * pt_offsets,
   const double * pts_xy);

@@ -648,6 +648,17 @@ HostMailbox mailbox_arm(ndt2d_matcher * m)
   return HostMailbox{h, flag, m->host_seq};
 }
 
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#else
+  asm volatile("" ::: "memory");
+#endif
+}
+
 // `spin`: poll the flag (a local match finishes in tens of microseconds: waking up from a
 // blocking synchronisation would cost as much as the search); falls back to the blocking wait
 // after ~2 ms or on a stream error.  Large searches block right away.
@@ -662,7 +673,7 @@ int mailbox_wait(ndt2d_matcher * m, const HostMailbox & hm, bool spin, double * 
         seen = true;
         break;
       }
-      __builtin_ia32_pause();
+      cpu_relax();
       if ((it & 1023u) == 1023u) {
         if (cudaStreamQuery(m->stream) != cudaErrorNotReady) {break;}   // done or failed
         if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {break;}
