@@ -275,6 +275,27 @@ def test_match_scan_config4_reduced(o):
     check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
 
 
+def test_region_kernel_tables_in_global_memory(o):
+    """A map whose dilated bitmap + threshold tables (57 KB at 0.1 m cells over +-30 m) do not fit
+    next to the region kernel's per-warp shared memory: the instantiation that reads them
+    through L1, with and without the coordinate pre-pass (3 regions per axis are needed for it)."""
+    w = synth.config4(scale=0.03)
+    for lin_size in (0.06, 0.5):
+        p = dict(w.params, ndt_resolution=0.1, search_linear_size=lin_size,
+                 search_angular_size=0.02 if lin_size > 0.1 else w.params["search_angular_size"])
+        m = ScanMatcherNDT.from_params(p, kernel_variant=4)
+        mo = o.new_matcher(p)
+        m.add_scans_raw(w.map_poses, w.map_offsets, w.map_points)
+        mo.add_scans(w.map_poses, w.map_offsets, w.map_points)
+        sx, sy = m.grid_info()[:2]
+        assert (sx + 2) * (sy + 2) // 8 + 8 * (sx + sy + 4) > 24 * 1024
+        guess = w.true_pose - np.array([0.03, -0.02, 0.01])
+        so, do, wo, co, scores_o = mo.match_scan(guess, w.query_points, want_scores=True)
+        sg, dg, wg, cg, _ = m.match_scan_raw(guess, w.query_points)
+        check_match((sg, dg, wg, cg), (so, do, wo, co), m.dump_scores(guess, w.query_points), scores_o)
+        m.close()
+
+
 def test_instrumentation_switches(o):
     """Work tallies and small-search event timing are off by default (they cost run time on the
     hot path) and available on request; results do not depend on them; the C-ABI latency probe
