@@ -12,6 +12,7 @@
 // Everything per point / per candidate runs on the device.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -171,6 +172,11 @@ struct GroupWorker
   std::condition_variable cv;
   std::function<int()> task;
   bool has_task = false, done = false, quit = false;
+  // hints for the short polling phases (the mutex-protected flags above stay the truth): a worker
+  // that has just finished a task polls `pending` for a while before it sleeps, so a burst of
+  // searches -- the loop-closure thread matching one candidate after the other -- finds it awake,
+  // and the dispatching thread polls `finished` instead of sleeping on the condition variable
+  std::atomic<bool> pending{false}, finished{false};
   int rc = 0;
   char err[512] = "";
 };
@@ -2465,11 +2471,25 @@ static int group_create(ndt2d_matcher * m)
     w->th = std::thread([w, dev]() {
           cudaSetDevice(dev);
           std::unique_lock<std::mutex> lk(w->mu);
+          bool hot = false;
           for (;;) {
+            if (hot && !w->has_task && !w->quit) {
+              // just finished a task: poll for the next one for 200 us before sleeping (waking a
+              // sleeping thread costs tens of microseconds, which every device of a search pays)
+              lk.unlock();
+              const auto t0 = std::chrono::steady_clock::now();
+              while (!w->pending.load(std::memory_order_acquire) &&
+                std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200))
+              {
+                cpu_relax();
+              }
+              lk.lock();
+            }
             w->cv.wait(lk, [w]() {return w->has_task || w->quit;});
             if (w->quit) {return;}
             std::function<int()> task = std::move(w->task);
             w->has_task = false;
+            w->pending.store(false, std::memory_order_relaxed);
             lk.unlock();
             g_last_error[0] = 0;
             const int rc = task();
@@ -2477,7 +2497,9 @@ static int group_create(ndt2d_matcher * m)
             w->rc = rc;
             snprintf(w->err, sizeof(w->err), "%s", g_last_error);
             w->done = true;
+            w->finished.store(true, std::memory_order_release);
             w->cv.notify_all();
+            hot = true;
           }
         });
   }
@@ -2497,6 +2519,8 @@ static int group_run(ndt2d_matcher * m, const std::function<int(size_t, ndt2d_ma
       w->task = [&fn, r, s]() {return fn(r, s);};
       w->has_task = true;
       w->done = false;
+      w->finished.store(false, std::memory_order_relaxed);
+      w->pending.store(true, std::memory_order_release);
     }
     w->cv.notify_all();
   }
@@ -2507,6 +2531,15 @@ static int group_run(ndt2d_matcher * m, const std::function<int(size_t, ndt2d_ma
   }
   for (size_t r = 1; r < world; ++r) {
     GroupWorker * w = m->group[r]->worker;
+    {
+      // the workers only enqueue (tens of microseconds): poll before falling back to the cv
+      const auto t0 = std::chrono::steady_clock::now();
+      while (!w->finished.load(std::memory_order_acquire) &&
+        std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2))
+      {
+        cpu_relax();
+      }
+    }
     std::unique_lock<std::mutex> lk(w->mu);
     w->cv.wait(lk, [w]() {return w->done;});
     if (w->rc && !rc) {
@@ -2541,11 +2574,15 @@ static int match_scan_group(
   const bool p2p = m->group_p2p;
   const int variant = m->prm.kernel_variant;
   // every device at once (one host thread each): stage the scan, the libm (cos, sin) of the
-  // device's own theta slices, the strided search + fused exchange, then wait for the stream
+  // device's own theta slices, the strided search + fused exchange.  Nobody waits for a stream
+  // here: with the fused exchange rank 0's finish kernel holds the combined record only after
+  // every device has published its own, and it stores that record into rank 0's host mailbox.
+  HostMailbox hm{nullptr, nullptr, 0ull};
   int rc = group_run(m, [&](size_t r, ndt2d_matcher * s) {
         int rc1 = stage_scan_locked(s, pose3, pts_xy, npts, true);
         if (!rc1) {rc1 = ensure_trig_locked(s, r, n_ang, world);}
         if (rc1) {return rc1;}
+        if (r == 0 && p2p) {hm = mailbox_arm(s);}
         SearchView sv = search_view(s);
         sv.theta_stride = static_cast<uint32_t>(world);
         ExchangeView xv;
@@ -2557,16 +2594,8 @@ static int match_scan_group(
         rc1 = ndt2d_launch_search(model_view(s), sv, static_cast<uint32_t>(r),
             static_cast<uint32_t>(n_ang), variant, s->d_blockpart.as<double>(),
             s->d_partial.as<double>(), nullptr, s->d_counter.as<uint32_t>(), s->stream, &s->ctr,
-            s->ev_begin, s->ev_end, p2p ? &xv : nullptr);
+            s->ev_begin, s->ev_end, p2p ? &xv : nullptr, (r == 0 && p2p) ? &hm : nullptr);
         s->ev_valid = rc1 == NDT2D_OK;
-        if (r != 0) {
-          // rank 0's stream is waited for by the fetch below
-          const cudaError_t e = cudaStreamSynchronize(s->stream);
-          if (e != cudaSuccess && !rc1) {
-            ndt2d_set_error("cudaStreamSynchronize", e, __FILE__, __LINE__);
-            rc1 = NDT2D_ERR_CUDA;
-          }
-        }
         return rc1;
       });
   if (rc) {
@@ -2579,7 +2608,7 @@ static int match_scan_group(
     double r32[32];
     {
       DeviceGuard guard(m->device);
-      if ((rc = fetch_result_locked(m, r32))) {return rc;}
+      if ((rc = mailbox_wait(m, hm, false, r32))) {return rc;}
     }
     for (size_t r = 1; r < world; ++r) {
       ndt2d_matcher * s = m->group[r];
